@@ -1,0 +1,700 @@
+// api.cu -- the C ABI of libb200slam.so (include/b200slam.h): context, device-resident
+// maps, and the host-side orchestration of the kernels in edt.cu / score.cu /
+// particles.cu.  Host-side arithmetic that the reference does on the CPU and whose bits
+// matter (lattice axis values, cosf/sinf, (t - min) * ipixel; Subsystem_1/main.c:424-438)
+// is done here with the same float operations and the host libm.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static char g_create_error[512] = "";
+
+int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" {
+
+int b200slam_abi_version(void) { return B200SLAM_ABI_VERSION; }
+
+const char *b200slam_last_error(const b200slam_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+int b200slam_create(b200slam_ctx **out, int device)
+{
+    if (!out) return B200SLAM_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return b200slam_set_error(nullptr, B200SLAM_ERR_CUDA,
+                                  "no CUDA device (%s); libb200slam has no CPU fallback",
+                                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev)
+        return b200slam_set_error(nullptr, B200SLAM_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+    b200slam_ctx *ctx = new (std::nothrow) b200slam_ctx();
+    if (!ctx) return B200SLAM_ERR_NOMEM;
+    ctx->device = device;
+#define CREATE_TRY(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            b200slam_set_error(nullptr, B200SLAM_ERR_CUDA, "%s -> %s", #expr,                 \
+                               cudaGetErrorString(_e));                                       \
+            b200slam_destroy(ctx);                                                            \
+            return B200SLAM_ERR_CUDA;                                                         \
+        }                                                                                     \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaMalloc(&ctx->d_match, sizeof(MatchDev)));
+    CREATE_TRY(cudaMemset(ctx->d_match, 0xff, sizeof(MatchDev)));
+    CREATE_TRY(cudaHostAlloc(&ctx->h_match, sizeof(MatchDev), cudaHostAllocDefault));
+    CREATE_TRY(cudaMalloc(&ctx->d_keys, sizeof(unsigned long long) * 3 * 64));
+    CREATE_TRY(cudaMalloc(&ctx->d_wsum, sizeof(unsigned long long) * 4));
+    CREATE_TRY(cudaHostAlloc(&ctx->h_wsum, sizeof(unsigned long long) * 2 * 64, cudaHostAllocDefault));
+#undef CREATE_TRY
+    *out = ctx;
+    return B200SLAM_OK;
+}
+
+void b200slam_destroy(b200slam_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    b200slam_comm_destroy(ctx);
+    if (ctx->edt_map) b200slam_map_destroy(ctx, ctx->edt_map);
+    cudaFree(ctx->d_scan_x); cudaFree(ctx->d_scan_y);
+    cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
+    cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match);
+    cudaFree(ctx->d_keys); cudaFree(ctx->d_hit_values);
+    cudaFree(ctx->d_scores);
+    cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
+    cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
+    cudaFree(ctx->d_ancestors); cudaFree(ctx->d_wsum); cudaFreeHost(ctx->h_wsum);
+    cudaFree(ctx->d_edt_scratch);
+    for (int i = 0; i < LAT_SLOTS; ++i)
+        if (ctx->lat_event[i]) cudaEventDestroy(ctx->lat_event[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int b200slam_sync(b200slam_ctx *ctx)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200SLAM_OK;
+}
+
+void *b200slam_stream(b200slam_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+uint64_t b200slam_launch_count(const b200slam_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b200slam_device_info(const b200slam_ctx *ctx, char *name, int *sm_count, int *cc_major,
+                         int *cc_minor, size_t *total_mem)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, ctx->device) != cudaSuccess) return B200SLAM_ERR_CUDA;
+    if (name) { strncpy(name, p.name, 63); name[63] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return B200SLAM_OK;
+}
+
+int b200slam_host_alloc(b200slam_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return B200SLAM_OK;
+}
+
+int b200slam_host_free(b200slam_ctx *ctx, void *p)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaFreeHost(p));
+    return B200SLAM_OK;
+}
+
+/* ---- maps ---------------------------------------------------------------------- */
+
+int b200slam_map_create(b200slam_ctx *ctx, int rows, int cols, b200slam_map **out)
+{
+    if (!ctx || !out) return B200SLAM_ERR_ARG;
+    *out = nullptr;
+    if (rows <= 0 || cols <= 0 || (long long)rows * (((long long)cols + 31) & ~31ll) >= (1ll << 30))
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "map %d x %d unsupported (need 0 < cells < 2^30)",
+                                  rows, cols);
+    b200slam_map *m = new (std::nothrow) b200slam_map();
+    if (!m) return B200SLAM_ERR_NOMEM;
+    m->rows = rows;
+    m->cols = cols;
+    m->occ_pitch = (cols + 31) & ~31;        // rows start on 128-byte lines
+    m->field_pitch = (cols + 31) & ~31;
+    cudaError_t e = cudaMalloc(&m->d_occ, sizeof(int32_t) * (size_t)m->occ_pitch * rows);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&m->d_field_alloc,
+                       sizeof(float) * ((size_t)m->field_pitch * rows + B200SLAM_FIELD_PAD));
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(m->d_field_alloc, 0, sizeof(float) * B200SLAM_FIELD_PAD, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(m->d_occ);
+        cudaFree(m->d_field_alloc);
+        delete m;
+        return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "map alloc %d x %d -> %s", rows, cols,
+                                  cudaGetErrorString(e));
+    }
+    m->d_field = m->d_field_alloc + B200SLAM_FIELD_PAD;
+    *out = m;
+    return B200SLAM_OK;
+}
+
+void b200slam_map_destroy(b200slam_ctx *ctx, b200slam_map *map)
+{
+    if (!map) return;
+    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(map->d_occ);
+    cudaFree(map->d_field_alloc);
+    delete map;
+}
+
+int b200slam_map_set_geometry(b200slam_map *map, float pixel_size, float top_left_x, float top_left_y)
+{
+    if (!map || !(pixel_size > 0.0f)) return B200SLAM_ERR_ARG;
+    map->pixel_size = pixel_size;
+    map->top_left_x = top_left_x;
+    map->top_left_y = top_left_y;
+    map->has_geometry = true;
+    return B200SLAM_OK;
+}
+
+int b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const int32_t *occ, int stride)
+{
+    if (!ctx || !map || !occ || stride < map->cols) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(map->d_occ, sizeof(int32_t) * (size_t)map->occ_pitch, occ,
+                                    sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)map->cols,
+                                    map->rows, cudaMemcpyHostToDevice, ctx->stream));
+    return B200SLAM_OK;
+}
+
+int b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist)
+{
+    if (!ctx || !map) return B200SLAM_ERR_ARG;
+    return edt_launch(ctx, map->d_occ, map->occ_pitch, map->d_field, map->field_pitch, map->rows,
+                      map->cols, max_dist);
+}
+
+int b200slam_map_download_field(b200slam_ctx *ctx, b200slam_map *map, float *out, int stride)
+{
+    if (!ctx || !map || !out || stride < map->cols) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(out, sizeof(float) * (size_t)stride, map->d_field,
+                                    sizeof(float) * (size_t)map->field_pitch,
+                                    sizeof(float) * (size_t)map->cols, map->rows,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200SLAM_OK;
+}
+
+int b200slam_map_upload_field(b200slam_ctx *ctx, b200slam_map *map, const float *field, int stride)
+{
+    if (!ctx || !map || !field || stride < map->cols) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(map->d_field, sizeof(float) * (size_t)map->field_pitch, field,
+                                    sizeof(float) * (size_t)stride, sizeof(float) * (size_t)map->cols,
+                                    map->rows, cudaMemcpyHostToDevice, ctx->stream));
+    return B200SLAM_OK;
+}
+
+int b200slam_map_device_ptrs(b200slam_map *map, int32_t **occ, int *occ_pitch, float **field,
+                             int *field_pitch)
+{
+    if (!map) return B200SLAM_ERR_ARG;
+    if (occ) *occ = map->d_occ;
+    if (occ_pitch) *occ_pitch = map->occ_pitch;
+    if (field) *field = map->d_field;
+    if (field_pitch) *field_pitch = map->field_pitch;
+    return B200SLAM_OK;
+}
+
+int b200slam_edt(b200slam_ctx *ctx, const int32_t *occ, int occ_stride, float *out, int out_stride,
+                 int rows, int cols, float max_dist)
+{
+    if (!ctx || !occ || !out) return B200SLAM_ERR_ARG;
+    if (rows <= 0 || cols <= 0) return B200SLAM_OK;       // empty grid: nothing to write
+    if (occ_stride < cols || out_stride < cols)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "stride smaller than cols");
+    b200slam_map *m = ctx->edt_map;
+    if (!m || m->rows != rows || m->cols != cols) {
+        if (m) b200slam_map_destroy(ctx, m);
+        ctx->edt_map = nullptr;
+        int rc = b200slam_map_create(ctx, rows, cols, &m);
+        if (rc) return rc;
+        ctx->edt_map = m;
+    }
+    int rc = b200slam_map_upload_occupancy(ctx, m, occ, occ_stride);
+    if (rc) return rc;
+    rc = b200slam_map_edt(ctx, m, max_dist);
+    if (rc) return rc;
+    return b200slam_map_download_field(ctx, m, out, out_stride);
+}
+
+/* ---- scan + lattice ------------------------------------------------------------ */
+
+int b200slam_scan_upload(b200slam_ctx *ctx, const float *x, const float *y, int nbeams)
+{
+    if (!ctx || nbeams < 0 || (nbeams > 0 && (!x || !y))) return B200SLAM_ERR_ARG;
+    if (nbeams > ctx->scan_cap) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_scan_x); cudaFree(ctx->d_scan_y); cudaFree(ctx->d_hit_values);
+        ctx->d_scan_x = ctx->d_scan_y = ctx->d_hit_values = nullptr;
+        ctx->scan_cap = 0;
+        const int cap = (nbeams + 255) & ~255;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_scan_x, sizeof(float) * cap));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_scan_y, sizeof(float) * cap));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_hit_values, sizeof(float) * 2 * cap));
+        ctx->scan_cap = cap;
+    }
+    if (nbeams > 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scan_x, x, sizeof(float) * nbeams, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scan_y, y, sizeof(float) * nbeams, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->nbeams = nbeams;
+    return B200SLAM_OK;
+}
+
+float b200slam_lattice_value(float p, float s, int k, int n)
+{
+    volatile float off = (float)(k - n / 2) * s;     // product rounded on its own
+    return p + off;
+}
+
+}  // extern "C"
+
+namespace {
+
+bool is_capturing(b200slam_ctx *ctx)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &st);
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// Fills one slot of the pinned axis tables [ct | st | sxt | syt] and queues its upload.
+// The staging area is a ring of LAT_SLOTS slots, each guarded by an event recorded after
+// the last kernel that reads it, so back-to-back matches never wait on the host.
+int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[3], const float step[3],
+                  const int n[3], LatticeLaunch *L)
+{
+    const int nth = n[0], ntx = n[1], nty = n[2];
+    const size_t need = (size_t)2 * nth + ntx + nty;
+    const bool capturing = is_capturing(ctx);
+    if (need > ctx->lat_cap) {
+        if (capturing)
+            return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "lattice larger than warmed-up scratch during graph capture");
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
+        ctx->h_lat = ctx->d_lat = nullptr;
+        ctx->lat_cap = 0;
+        const size_t cap = (need + 1023) & ~(size_t)1023;
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_lat, sizeof(float) * cap * LAT_SLOTS, cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_lat, sizeof(float) * cap * LAT_SLOTS));
+        for (int i = 0; i < LAT_SLOTS; ++i)
+            if (!ctx->lat_event[i])
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->lat_event[i], cudaEventDisableTiming));
+        ctx->lat_cap = cap;
+    }
+    const int slot = ctx->lat_next;
+    ctx->lat_next = (slot + 1) % LAT_SLOTS;
+    ctx->lat_cur = slot;
+    if (!capturing) CUDA_TRY(ctx, cudaEventSynchronize(ctx->lat_event[slot]));
+    const float ipixel = 1 / map->pixel_size;                             // main.c:383
+    float *ct = ctx->h_lat + (size_t)slot * ctx->lat_cap, *st = ct + nth, *sxt = st + nth, *syt = sxt + ntx;
+    for (int i = 0; i < nth; ++i) {
+        const float th = b200slam_lattice_value(pose0[2], step[2], i, nth);   // main.c:424
+        ct[i] = cosf(th);                                                 // main.c:434
+        st[i] = sinf(th);                                                 // main.c:435
+    }
+    for (int i = 0; i < ntx; ++i) {
+        const float tx = b200slam_lattice_value(pose0[0], step[0], i, ntx);   // main.c:425
+        volatile float d = tx - map->top_left_x;
+        sxt[i] = d * ipixel;                                              // main.c:436
+    }
+    for (int i = 0; i < nty; ++i) {
+        const float ty = b200slam_lattice_value(pose0[1], step[1], i, nty);   // main.c:426
+        volatile float d = ty - map->top_left_y;
+        syt[i] = d * ipixel;                                              // main.c:437
+    }
+    float *dst = ctx->d_lat + (size_t)slot * ctx->lat_cap;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, ct, sizeof(float) * need, cudaMemcpyHostToDevice, ctx->stream));
+    L->map = map;
+    L->nth = nth; L->ntx = ntx; L->nty = nty;
+    L->d_ct = dst; L->d_st = L->d_ct + nth; L->d_sxt = L->d_st + nth; L->d_syt = L->d_sxt + ntx;
+    return B200SLAM_OK;
+}
+
+int check_lattice_args(b200slam_ctx *ctx, const b200slam_map *map, const float *pose0, const float *step,
+                       const int *n)
+{
+    if (!ctx || !map || !pose0 || !step || !n) return B200SLAM_ERR_ARG;
+    if (!map->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
+    if (ctx->nbeams < 0 || !ctx->d_scan_x) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan uploaded");
+    if (n[0] <= 0 || n[1] <= 0 || n[2] <= 0 || (long long)n[0] * n[1] * n[2] > 0xffffffffll)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "lattice %d x %d x %d unsupported", n[0], n[1], n[2]);
+    return B200SLAM_OK;
+}
+
+int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], const float step[3],
+                  const int n[3], int64_t row_begin, int64_t row_end, bool want_scores, bool allreduce)
+{
+    int rc = check_lattice_args(ctx, map, pose0, step, n);
+    if (rc) return rc;
+    const int64_t nrows = (int64_t)n[0] * n[1];
+    if (row_begin < 0 || row_end > nrows || row_begin > row_end)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "row range [%lld,%lld) outside [0,%lld)",
+                                  (long long)row_begin, (long long)row_end, (long long)nrows);
+    LatticeLaunch L;
+    rc = stage_lattice(ctx, map, pose0, step, n, &L);
+    if (rc) return rc;
+    L.row_begin = row_begin;
+    L.row_end = row_end;
+    L.d_scores = nullptr;
+    if (want_scores) {
+        const size_t need = (size_t)nrows * n[2];
+        if (need > ctx->scores_cap) {
+            if (is_capturing(ctx))
+                return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "score table allocation during graph capture");
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_scores);
+            ctx->d_scores = nullptr;
+            ctx->scores_cap = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->d_scores, sizeof(float) * need));
+            ctx->scores_cap = need;
+        }
+        L.d_scores = ctx->d_scores;
+    }
+    rc = lattice_launch(ctx, L);
+    if (rc) return rc;
+    bool gathered = false;
+    if (allreduce && ctx->nccl_comm && ctx->nranks > 1) {
+        rc = comm_allgather_u64(ctx, &ctx->d_match->key, ctx->d_keys, 1);
+        if (rc) return rc;
+        gathered = true;
+    }
+    rc = trace_launch(ctx, L, gathered);
+    if (rc) return rc;
+    if (!is_capturing(ctx)) CUDA_TRY(ctx, cudaEventRecord(ctx->lat_event[ctx->lat_cur], ctx->stream));
+    ctx->last.valid = true;
+    ctx->last.is_poses = false;
+    for (int i = 0; i < 3; ++i) {
+        ctx->last.n[i] = n[i];
+        ctx->last.pose0[i] = pose0[i];
+        ctx->last.step[i] = step[i];
+    }
+    return B200SLAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result)
+{
+    if (!ctx || !result) return B200SLAM_ERR_ARG;
+    if (!ctx->last.valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no match queued");
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_match, ctx->d_match, sizeof(MatchDev), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const MatchDev &m = *ctx->h_match;
+    memset(result, 0, sizeof(*result));
+    if (m.key == ~0ull) {               // empty shard
+        result->best_index = -1;
+        result->best_score = INFINITY;
+        return B200SLAM_OK;
+    }
+    const uint32_t bits = (uint32_t)(m.key >> 32);
+    memcpy(&result->best_score, &bits, 4);
+    result->best_index = (int64_t)(m.key & 0xffffffffull);
+    result->best_hits = m.best_hits;
+    result->last_hits = m.last_hits;
+    if (!ctx->last.is_poses) {
+        const int ntx = ctx->last.n[1], nty = ctx->last.n[2];
+        const int64_t lin = result->best_index;
+        const int ity = (int)(lin % nty);
+        const int itx = (int)((lin / nty) % ntx);
+        const int ith = (int)(lin / nty / ntx);
+        result->best_pose[0] = b200slam_lattice_value(ctx->last.pose0[0], ctx->last.step[0], itx, ntx);
+        result->best_pose[1] = b200slam_lattice_value(ctx->last.pose0[1], ctx->last.step[1], ity, nty);
+        result->best_pose[2] = b200slam_lattice_value(ctx->last.pose0[2], ctx->last.step[2], ith, ctx->last.n[0]);
+    } else if (ctx->last_poses_host) {
+        const int64_t local = result->best_index - ctx->last_index_base;
+        if (local >= 0 && local < ctx->last_P)
+            for (int i = 0; i < 3; ++i) result->best_pose[i] = ctx->last_poses_host[3 * local + i];
+    }
+    return B200SLAM_OK;
+}
+
+int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
+                                 const float step[3], const int n[3], int64_t row_begin, int64_t row_end)
+{
+    return queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, false);
+}
+
+int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
+                                const float step[3], const int n[3], int64_t row_begin, int64_t row_end,
+                                int allreduce, b200slam_match *result)
+{
+    int rc = queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, allreduce != 0);
+    if (rc) return rc;
+    return b200slam_match_fetch(ctx, result);
+}
+
+int b200slam_score_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
+                           const float step[3], const int n[3], float *scores, float *last_hit_values,
+                           b200slam_match *result)
+{
+    if (!n) return B200SLAM_ERR_ARG;
+    const int64_t nrows = (int64_t)n[0] * n[1];
+    int rc = queue_lattice(ctx, map, pose0, step, n, 0, nrows, scores != nullptr, false);
+    if (rc) return rc;
+    if (scores)
+        CUDA_TRY(ctx, cudaMemcpyAsync(scores, ctx->d_scores, sizeof(float) * (size_t)nrows * n[2],
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    b200slam_match tmp;
+    rc = b200slam_match_fetch(ctx, result ? result : &tmp);
+    if (rc) return rc;
+    const b200slam_match *m = result ? result : &tmp;
+    if (last_hit_values && m->last_hits > 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(last_hit_values, ctx->d_hit_values + ctx->scan_cap,
+                                      sizeof(float) * (size_t)m->last_hits, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return B200SLAM_OK;
+}
+
+int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3],
+                       const float search_resolution[3], float pose_out[3], float *best_hits,
+                       int *best_hits_size)
+{
+    if (!pose || !search_resolution || !pose_out) return B200SLAM_ERR_ARG;
+    // main.c:386-387: t = searchResolution[0] for both translations, r = searchResolution[2].
+    // The five sweeps of the while loop (main.c:440-591) re-score the same 27 candidates
+    // (the lattice is built once, :422-438, and the refinement at :577-580 is commented
+    // out), so one sweep gives the identical FastMatchParameters.
+    const float step[3] = {search_resolution[0], search_resolution[0], search_resolution[2]};
+    const int n[3] = {3, 3, 3};
+    b200slam_match m;
+    int rc = b200slam_score_lattice(ctx, map, pose, step, n, nullptr, best_hits, &m);
+    if (rc) return rc;
+    pose_out[0] = m.best_pose[0];                                         // main.c:592-594
+    pose_out[1] = m.best_pose[1];
+    pose_out[2] = m.best_pose[2];
+    if (best_hits_size) *best_hits_size = m.best_hits;                    // main.c:557
+    return B200SLAM_OK;
+}
+
+/* ---- pose lists / particles ---------------------------------------------------- */
+
+int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *poses, const float *ct,
+                         const float *st, int64_t P, int64_t index_base, float *scores, int32_t *hits,
+                         b200slam_match *result)
+{
+    if (!ctx || !map || P < 0 || (P > 0 && !poses)) return B200SLAM_ERR_ARG;
+    if (!map->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
+    if (!ctx->d_scan_x) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan uploaded");
+    if (P + index_base > 0xffffffffll) return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "too many poses");
+    if ((size_t)P > ctx->pose_cap) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
+        cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
+        ctx->d_pose_soa = nullptr; ctx->d_hits = nullptr; ctx->h_pose_stage = nullptr;
+        ctx->d_q = nullptr; ctx->d_block_sums = nullptr; ctx->d_weights = nullptr;
+        ctx->pose_cap = 0;
+        const size_t cap = ((size_t)P + 4095) & ~(size_t)4095;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_pose_soa, sizeof(float) * 4 * cap));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_hits, sizeof(int32_t) * cap));
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_pose_stage, sizeof(float) * 4 * cap, cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_q, sizeof(unsigned long long) * cap));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_block_sums, sizeof(unsigned long long) * (cap / 1024 + 2)));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_weights, sizeof(float) * cap));
+        ctx->pose_cap = cap;
+    }
+    if ((size_t)P > ctx->scores_cap) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_scores);
+        ctx->d_scores = nullptr;
+        ctx->scores_cap = 0;
+        const size_t cap = ((size_t)P + 4095) & ~(size_t)4095;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_scores, sizeof(float) * cap));
+        ctx->scores_cap = cap;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // staging buffer free again
+    const size_t cap = ctx->pose_cap;
+    float *hx = ctx->h_pose_stage, *hy = hx + cap, *hct = hy + cap, *hst = hct + cap;
+    for (int64_t p = 0; p < P; ++p) {
+        hx[p] = poses[3 * p + 0];
+        hy[p] = poses[3 * p + 1];
+        hct[p] = ct ? ct[p] : cosf(poses[3 * p + 2]);                     // main.c:434
+        hst[p] = st ? st[p] : sinf(poses[3 * p + 2]);                     // main.c:435
+    }
+    if (P > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pose_soa, ctx->h_pose_stage, sizeof(float) * 4 * cap,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    int rc = poses_launch(ctx, map, P, index_base, ctx->d_scores, ctx->d_hits);
+    if (rc) return rc;
+    ctx->last.valid = true;
+    ctx->last.is_poses = true;
+    ctx->last_P = P;
+    ctx->last_index_base = index_base;
+    ctx->last_poses_host = poses;
+    if (scores && P > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(scores, ctx->d_scores, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hits && P > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(hits, ctx->d_hits, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (result) {
+        // best_hits of the winner comes from the per-pose hit counts
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_match, ctx->d_match, sizeof(MatchDev), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        rc = b200slam_match_fetch(ctx, result);
+        if (rc) return rc;
+        result->best_hits = 0;
+        result->last_hits = 0;
+        if (result->best_index >= 0) {
+            int32_t h2[1];
+            const int64_t local = result->best_index - index_base;
+            CUDA_TRY(ctx, cudaMemcpy(h2, ctx->d_hits + local, sizeof(int32_t), cudaMemcpyDeviceToHost));
+            result->best_hits = h2[0];
+            CUDA_TRY(ctx, cudaMemcpy(h2, ctx->d_hits + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+            result->last_hits = h2[0];
+        }
+    } else {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->last_poses_host = nullptr;      // caller's buffer is only borrowed during this call
+    return B200SLAM_OK;
+}
+
+int b200slam_weights_resample(b200slam_ctx *ctx, float beta, uint32_t u0_q32, float *weights,
+                              uint64_t *wsum, int32_t *ancestors, int64_t *k_begin, int64_t *k_count)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    if (!ctx->last.valid || !ctx->last.is_poses)
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_score_poses must run first");
+    return particles_weights_resample(ctx, ctx->last_P, beta, u0_q32, weights, wsum, ancestors, k_begin,
+                                      k_count);
+}
+
+int b200slam_pyramid_match(b200slam_ctx *ctx, b200slam_map *const *maps, int levels,
+                           const float pose0[3], const float *steps, const int *n,
+                           b200slam_match *results)
+{
+    if (!ctx || !maps || levels <= 0 || !pose0 || !steps || !n || !results) return B200SLAM_ERR_ARG;
+    // main.c:901-918: each level is seeded with the previous level's winner.
+    float seed[3] = {pose0[0], pose0[1], pose0[2]};
+    const bool multi = ctx->nccl_comm && ctx->nranks > 1;
+    for (int l = 0; l < levels; ++l) {
+        const int *nl = n + 3 * l;
+        const int64_t nrows = (int64_t)nl[0] * nl[1];
+        int64_t rb = 0, re = nrows;
+        if (multi) b200slam_shard_range(nrows, ctx->nranks, ctx->rank, &rb, &re);
+        int rc = b200slam_score_lattice_rows(ctx, maps[l], seed, steps + 3 * l, nl, rb, re, multi ? 1 : 0,
+                                             &results[l]);
+        if (rc) return rc;
+        for (int i = 0; i < 3; ++i) seed[i] = results[l].best_pose[i];
+    }
+    return B200SLAM_OK;
+}
+
+/* ---- CUDA graphs: capture a launch-bound sequence once, replay it ------------------ */
+
+struct b200slam_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t kernels = 0;
+};
+
+int b200slam_graph_begin(b200slam_ctx *ctx)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    ctx->graph_launch_mark = ctx->launches;
+    CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    return B200SLAM_OK;
+}
+
+int b200slam_graph_end(b200slam_ctx *ctx, b200slam_graph **out)
+{
+    if (!ctx || !out) return B200SLAM_ERR_ARG;
+    *out = nullptr;
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(ctx, cudaStreamEndCapture(ctx->stream, &g));
+    b200slam_graph *G = new (std::nothrow) b200slam_graph();
+    if (!G) { cudaGraphDestroy(g); return B200SLAM_ERR_NOMEM; }
+    G->graph = g;
+    G->kernels = ctx->launches - ctx->graph_launch_mark;
+    ctx->launches = ctx->graph_launch_mark;      // captured launches have not run yet
+    cudaError_t e = cudaGraphInstantiate(&G->exec, g, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g);
+        delete G;
+        return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+    }
+    *out = G;
+    return B200SLAM_OK;
+}
+
+int b200slam_graph_launch(b200slam_ctx *ctx, b200slam_graph *g)
+{
+    if (!ctx || !g) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->kernels;
+    return B200SLAM_OK;
+}
+
+void b200slam_graph_destroy(b200slam_ctx *ctx, b200slam_graph *g)
+{
+    if (!g) return;
+    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+
+/* ---- sharding helpers (pure host) ----------------------------------------------- */
+
+void b200slam_shard_range(int64_t total, int nranks, int rank, int64_t *begin, int64_t *end)
+{
+    if (nranks <= 0) nranks = 1;
+    const int64_t base = total / nranks, rem = total % nranks;
+    const int64_t b = rank * base + (rank < rem ? rank : rem);
+    if (begin) *begin = b;
+    if (end) *end = b + base + (rank < rem ? 1 : 0);
+}
+
+uint64_t b200slam_pack_key(float score, uint32_t index) { return pack_key(score, index); }
+
+void b200slam_unpack_key(uint64_t key, float *score, uint32_t *index)
+{
+    const uint32_t bits = (uint32_t)(key >> 32);
+    if (score) memcpy(score, &bits, 4);
+    if (index) *index = (uint32_t)(key & 0xffffffffull);
+}
+
+uint64_t b200slam_merge_keys(const uint64_t *keys, int n)
+{
+    uint64_t best = ~0ull;
+    for (int i = 0; i < n; ++i) best = keys[i] < best ? keys[i] : best;
+    return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// comm.cu -- multi-GPU exchange: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// The path shards by candidate rows / particles with the map replicated (SURVEY.md
+// section 8e), so the only data-path collectives are all-gathers of a few bytes per rank:
+// the packed (score, index) arg-min key and the integer weight sums.  NCCL is resolved
+// with dlopen at b200slam_comm_init time, so a single-GPU user of libb200slam.so needs no
+// NCCL at all, and a process that already loaded a libnccl.so.2 (e.g. torch's bundled one)
+// shares it instead of loading a second copy.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "common.cuh"
+
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    char why[256] = "";
+};
+
+NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) {
+        snprintf(api.why, sizeof api.why, "dlopen(libnccl.so.2) failed: %s", dlerror());
+        return &api;
+    }
+#define SYM(field, name)                                                             \
+    do {                                                                             \
+        api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name));  \
+        if (!api.field) {                                                            \
+            snprintf(api.why, sizeof api.why, "dlsym(%s) failed", name);             \
+            api.handle = nullptr;                                                    \
+            return &api;                                                             \
+        }                                                                            \
+    } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return &api;
+}
+
+}  // namespace
+
+int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send, unsigned long long *d_recv,
+                       int count_per_rank)
+{
+    NcclApi *api = nccl_api();
+    if (!api->handle || !ctx->nccl_comm)
+        return b200slam_set_error(ctx, B200SLAM_ERR_NCCL, "no communicator (%s)", api->why);
+    ncclResult_t r = api->AllGather(d_send, d_recv, (size_t)count_per_rank, ncclUint64,
+                                    (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != ncclSuccess)
+        return b200slam_set_error(ctx, B200SLAM_ERR_NCCL, "ncclAllGather -> %s", api->GetErrorString(r));
+    return B200SLAM_OK;
+}
+
+extern "C" {
+
+int b200slam_comm_unique_id(void *id_out)
+{
+    static_assert(sizeof(ncclUniqueId) == B200SLAM_UNIQUE_ID_BYTES, "unique id size");
+    if (!id_out) return B200SLAM_ERR_ARG;
+    NcclApi *api = nccl_api();
+    if (!api->handle) return b200slam_set_error(nullptr, B200SLAM_ERR_NCCL, "%s", api->why);
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess)
+        return b200slam_set_error(nullptr, B200SLAM_ERR_NCCL, "ncclGetUniqueId -> %s", api->GetErrorString(r));
+    memcpy(id_out, &id, sizeof id);
+    return B200SLAM_OK;
+}
+
+int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id_in)
+{
+    if (!ctx || !id_in || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return B200SLAM_ERR_ARG;
+    NcclApi *api = nccl_api();
+    if (!api->handle) return b200slam_set_error(ctx, B200SLAM_ERR_NCCL, "%s", api->why);
+    if (ctx->nccl_comm) b200slam_comm_destroy(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id_in, sizeof id);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = api->CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess)
+        return b200slam_set_error(ctx, B200SLAM_ERR_NCCL, "ncclCommInitRank -> %s", api->GetErrorString(r));
+    ctx->nccl_comm = comm;
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return B200SLAM_OK;
+}
+
+int b200slam_comm_destroy(b200slam_ctx *ctx)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    if (ctx->nccl_comm) {
+        NcclApi *api = nccl_api();
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (api->handle) api->CommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->nranks = 1;
+    ctx->rank = 0;
+    return B200SLAM_OK;
+}
+
+}  // extern "C"

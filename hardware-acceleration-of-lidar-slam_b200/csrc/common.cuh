@@ -1,0 +1,150 @@
+// common.cuh -- internals shared by the translation units of libb200slam.so.
+// Nothing here is visible through the C ABI (include/b200slam.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200slam.h"
+
+// Cells of padding in front of every distance field: field[-1] is a zero the scoring
+// kernels read for out-of-bounds beams (adding +0.0f leaves a score unchanged).
+#define B200SLAM_FIELD_PAD 32
+#define LAT_SLOTS 4
+
+struct b200slam_map {
+    int rows = 0, cols = 0;
+    int occ_pitch = 0;       // elements
+    int field_pitch = 0;     // elements
+    int32_t *d_occ = nullptr;
+    float *d_field_alloc = nullptr;   // allocation start (pad in front)
+    float *d_field = nullptr;         // [0][0]
+    float pixel_size = 1.0f, top_left_x = 0.0f, top_left_y = 0.0f;
+    bool has_geometry = false;
+};
+
+// Device-side result block of a match (read back by b200slam_match_fetch).
+struct MatchDev {
+    unsigned long long key;     // (score bits << 32) | global linear index
+    int best_hits;
+    int last_hits;
+};
+
+struct b200slam_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    uint64_t launches = 0;
+
+    // scan (sensor frame), device resident
+    float *d_scan_x = nullptr, *d_scan_y = nullptr;
+    int nbeams = 0, scan_cap = 0;
+
+    // lattice axis tables: host-pinned staging + device copy
+    float *h_lat = nullptr, *d_lat = nullptr;
+    size_t lat_cap = 0;          // floats per slot
+    cudaEvent_t lat_event[LAT_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    int lat_next = 0, lat_cur = 0;
+    uint64_t graph_launch_mark = 0;
+
+    // match result
+    MatchDev *d_match = nullptr;
+    MatchDev *h_match = nullptr;            // pinned
+    unsigned long long *d_keys = nullptr;   // all-gather landing zone [nranks]
+    float *d_hit_values = nullptr;          // [2][scan_cap]: best / last candidate
+    // bookkeeping of the last queued lattice match (host side)
+    struct {
+        bool valid = false;
+        int n[3] = {0, 0, 0};
+        float pose0[3] = {0, 0, 0};
+        float step[3] = {0, 0, 0};
+        bool is_poses = false;
+    } last;
+
+    // optional full score table
+    float *d_scores = nullptr;
+    size_t scores_cap = 0;       // floats
+
+    // pose-list scoring (particles)
+    float *d_pose_soa = nullptr;  // x | y | ct | st, each [pose_cap]
+    size_t pose_cap = 0;
+    int32_t *d_hits = nullptr;
+    float *h_pose_stage = nullptr;   // pinned staging [4][pose_cap]
+    int64_t last_P = 0;
+    int64_t last_index_base = 0;
+    const float *last_poses_host = nullptr;
+
+    // particle weights / resampling scratch
+    unsigned long long *d_q = nullptr;        // fixed-point weights / inclusive prefix [pose_cap]
+    unsigned long long *d_block_sums = nullptr;
+    float *d_weights = nullptr;
+    int32_t *d_ancestors = nullptr;
+    size_t anc_cap = 0;
+    unsigned long long *d_wsum = nullptr;     // [4] scratch scalars
+    unsigned long long *h_wsum = nullptr;     // pinned [4]
+
+    // generic EDT scratch (u16 column distances)
+    uint16_t *d_edt_scratch = nullptr;
+    size_t edt_scratch_cap = 0;
+    // one-shot host EDT: cached map
+    b200slam_map *edt_map = nullptr;
+
+    // NCCL (dlopen'ed lazily; see comm.cu)
+    void *nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
+
+#define CUDA_TRY(ctx, expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return b200slam_set_error((ctx), B200SLAM_ERR_CUDA, "%s:%d %s -> %s", __FILE__,  \
+                                      __LINE__, #expr, cudaGetErrorString(_e));              \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                    \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        CUDA_TRY((ctx), cudaGetLastError());                                                 \
+    } while (0)
+
+// ---- internal entry points between translation units ---------------------------------
+int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
+               int field_pitch, int rows, int cols, float max_dist);
+
+struct LatticeLaunch {
+    const b200slam_map *map;
+    int nth, ntx, nty;
+    const float *d_ct, *d_st, *d_sxt, *d_syt;
+    int64_t row_begin, row_end;
+    float *d_scores;   // optional
+};
+int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
+int trace_launch(b200slam_ctx *ctx, const LatticeLaunch &L, bool use_gathered_keys);
+int poses_launch(b200slam_ctx *ctx, const b200slam_map *map, int64_t P, int64_t index_base,
+                 float *d_scores, int32_t *d_hits);
+
+int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32,
+                               float *weights, uint64_t *wsum, int32_t *ancestors,
+                               int64_t *k_begin, int64_t *k_count);
+
+int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send,
+                       unsigned long long *d_recv, int count_per_rank);
+
+// packed arg-min key helpers (scores are sums of non-negative floats, so the IEEE bit
+// pattern orders like the value and uint64 min == (lowest score, then lowest index))
+__host__ __device__ inline unsigned long long pack_key(float score, unsigned int index)
+{
+#ifdef __CUDA_ARCH__
+    return ((unsigned long long)__float_as_uint(score) << 32) | index;
+#else
+    uint32_t b;
+    memcpy(&b, &score, 4);
+    return ((unsigned long long)b << 32) | index;
+#endif
+}

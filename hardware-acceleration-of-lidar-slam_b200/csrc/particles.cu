@@ -1,0 +1,274 @@
+// particles.cu -- FastSLAM-style particle weights, normalisation and systematic
+// resampling on top of the pose-list scores (extension asked for by BASELINE.json; the
+// reference has no particle filter -- SURVEY.md section 0).  The definition is the one in
+// include/b200slam.h / oracle/slam_oracle.c (orc_weights_resample):
+//   w_i = exp_det(-beta * (score_i - score_min)),  q_i = (uint64)(w_i * 2^32),
+//   W = sum q_i,  weight_i = (float)((double)q_i / W),
+//   T_k = U + floor(k*W/N),  ancestor_k = first i with inclusive prefix C_i > T_k.
+// Weights are integers, so the prefix sum is associative and the resampled indices are
+// the same for any blocking, any GPU count and the CPU oracle.  exp_det uses only IEEE
+// basic operations in double (no FMA contraction), so it is bit-identical to the host.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PT_THREADS = 256;
+constexpr int PT_ITEMS = 4;
+constexpr int PT_BLOCK = PT_THREADS * PT_ITEMS;     // particles per CTA
+
+__device__ __forceinline__ float exp_det(float x)
+{
+    double xd = (double)x;
+    if (!(xd > -80.0)) return 0.0f;
+    if (xd > 0.0) xd = 0.0;
+    const double LOG2E = 1.4426950408889634;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    const double kf = rint(__dmul_rn(xd, LOG2E));
+    double r = __dsub_rn(xd, __dmul_rn(kf, LN2_HI));
+    r = __dsub_rn(r, __dmul_rn(kf, LN2_LO));
+    const double c[14] = {
+        1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040,
+        1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600,
+        1.0 / 6227020800.0};
+    double p = c[13];
+#pragma unroll
+    for (int i = 12; i >= 0; --i) p = __dadd_rn(__dmul_rn(p, r), c[i]);
+    const int k = (int)kf;
+    const double two_k = __longlong_as_double((long long)(1023 + k) << 52);
+    return __double2float_rn(__dmul_rn(p, two_k));
+}
+
+__device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long v, int lane)
+{
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, v, s);
+        if (lane >= s) v += o;
+    }
+    return v;
+}
+
+// q_i and per-CTA sums.  keys: packed arg-min keys (one per rank); their min carries
+// score_min in its upper 32 bits.
+__global__ void __launch_bounds__(PT_THREADS)
+weights_kernel(const float *__restrict__ scores, long long N, float beta,
+               const unsigned long long *__restrict__ keys, int nkeys,
+               unsigned long long *__restrict__ q, unsigned long long *__restrict__ block_sums)
+{
+    __shared__ unsigned long long wsum[PT_THREADS / 32];
+    unsigned long long key = ~0ull;
+    for (int k = 0; k < nkeys; ++k) key = keys[k] < key ? keys[k] : key;
+    const float smin = __uint_as_float((unsigned int)(key >> 32));
+    const long long base = (long long)blockIdx.x * PT_BLOCK + (long long)threadIdx.x * PT_ITEMS;
+    unsigned long long local = 0;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const long long i = base + j;
+        if (i < N) {
+            const float d = __fsub_rn(scores[i], smin);
+            const float w = exp_det(-__fmul_rn(beta, d));
+            const unsigned long long qi = (unsigned long long)__dmul_rn((double)w, 4294967296.0);
+            q[i] = qi;
+            local += qi;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
+    if (lane == 0) wsum[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) t += wsum[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// Exclusive scan of the per-CTA sums (one CTA); total -> out_total[0].
+__global__ void __launch_bounds__(1024)
+block_sums_scan_kernel(unsigned long long *__restrict__ block_sums, int nb,
+                       unsigned long long *__restrict__ out_total)
+{
+    __shared__ unsigned long long wtot[32];
+    __shared__ unsigned long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const unsigned long long v = i < nb ? block_sums[i] : 0;
+        unsigned long long inc = warp_incl_scan(v, lane);
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long t = wtot[lane];
+            t = warp_incl_scan(t, lane);
+            wtot[lane] = t;
+        }
+        __syncthreads();
+        const unsigned long long before = carry + (warp ? wtot[warp - 1] : 0);
+        if (i < nb) block_sums[i] = before + inc - v;     // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_total[0] = carry;
+}
+
+// In-place inclusive prefix C_i (local to this rank) and normalised weights.
+// totals: [0] = local W, [1] = global W (== local on one GPU).
+__global__ void __launch_bounds__(PT_THREADS)
+prefix_kernel(unsigned long long *__restrict__ q, long long N,
+              const unsigned long long *__restrict__ block_offsets,
+              const unsigned long long *__restrict__ totals, float *__restrict__ weights)
+{
+    __shared__ unsigned long long wtot[PT_THREADS / 32];
+    const long long base = (long long)blockIdx.x * PT_BLOCK + (long long)threadIdx.x * PT_ITEMS;
+    const double W = (double)totals[1];
+    unsigned long long v[PT_ITEMS];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const long long i = base + j;
+        v[j] = i < N ? q[i] : 0;
+        if (weights && i < N) weights[i] = __double2float_rn(__ddiv_rn((double)v[j], W));
+        tsum += v[j];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long inc = warp_incl_scan(tsum, lane);
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    unsigned long long before = block_offsets[blockIdx.x];
+    for (int w = 0; w < warp; ++w) before += wtot[w];
+    unsigned long long run = before + inc - tsum;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const long long i = base + j;
+        run += v[j];
+        if (i < N) q[i] = run;
+    }
+}
+
+// Systematic resampling: slot k -> first local particle whose (rank-offset) inclusive
+// prefix exceeds T_k.  Slots [k_begin, k_begin + k_count) are the ones whose ancestor
+// lives on this rank.
+__global__ void __launch_bounds__(256)
+resample_kernel(const unsigned long long *__restrict__ C, long long N_local, long long N_global,
+                unsigned long long rank_offset, unsigned long long Wd, unsigned long long Wm,
+                unsigned long long U, long long k_begin, long long k_count,
+                long long index_base, int *__restrict__ ancestors)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k_count) return;
+    const unsigned long long k = (unsigned long long)(k_begin + s);
+    const unsigned long long T = U + k * Wd + (k * Wm) / (unsigned long long)N_global;
+    const unsigned long long t = T - rank_offset;      // T >= rank_offset for owned slots
+    long long lo = 0, hi = N_local - 1;                // first i with C[i] > t
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (C[mid] > t) hi = mid; else lo = mid + 1;
+    }
+    ancestors[s] = (int)(lo + index_base);
+}
+
+// number of slots k in [0, N) with T_k < c  (T_k is non-decreasing in k)
+long long slots_below(unsigned long long c, unsigned long long U, unsigned long long Wd,
+                      unsigned long long Wm, long long N)
+{
+    long long lo = 0, hi = N;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        const unsigned long long T = U + (unsigned long long)mid * Wd +
+                                     ((unsigned long long)mid * Wm) / (unsigned long long)N;
+        if (T < c) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace
+
+int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32,
+                               float *weights, uint64_t *wsum, int32_t *ancestors,
+                               int64_t *k_begin_out, int64_t *k_count_out)
+{
+    if (N <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scored poses");
+    const int nb = (int)((N + PT_BLOCK - 1) / PT_BLOCK);
+    const bool multi = ctx->nccl_comm != nullptr && ctx->nranks > 1;
+    const unsigned long long *keys = &ctx->d_match->key;
+    int nkeys = 1;
+    if (multi) {
+        int rc = comm_allgather_u64(ctx, &ctx->d_match->key, ctx->d_keys, 1);
+        if (rc) return rc;
+        keys = ctx->d_keys;
+        nkeys = ctx->nranks;
+    }
+    weights_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_scores, N, beta, keys, nkeys, ctx->d_q,
+                                                       ctx->d_block_sums);
+    LAUNCH_CHECK(ctx);
+    block_sums_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums, nb, ctx->d_wsum);
+    LAUNCH_CHECK(ctx);
+
+    // totals: local W in d_wsum[0]; gather every rank's W and N for the global picture
+    unsigned long long rank_offset = 0, Wglobal = 0;
+    long long Nglobal = N, index_base = ctx->last_index_base;
+    if (multi) {
+        // d_wsum[1] = local N, so one 16-byte all-gather carries both
+        unsigned long long nloc = (unsigned long long)N;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_wsum + 1, &nloc, 8, cudaMemcpyHostToDevice, ctx->stream));
+        unsigned long long *d_all = ctx->d_keys + ctx->nranks;      // [nranks][2]
+        int rc = comm_allgather_u64(ctx, ctx->d_wsum, d_all, 2);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_wsum, d_all, 16 * ctx->nranks, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        Nglobal = 0;
+        for (int r = 0; r < ctx->nranks; ++r) {
+            if (r < ctx->rank) rank_offset += ctx->h_wsum[2 * r];
+            Wglobal += ctx->h_wsum[2 * r];
+            Nglobal += (long long)ctx->h_wsum[2 * r + 1];
+        }
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_wsum, ctx->d_wsum, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        Wglobal = ctx->h_wsum[0];
+    }
+    const unsigned long long Wlocal = multi ? ctx->h_wsum[2 * ctx->rank] : Wglobal;
+    if (Wglobal == 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "all particle weights are zero");
+    // d_wsum[1] <- global W for the normalisation
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_wsum + 1, &Wglobal, 8, cudaMemcpyHostToDevice, ctx->stream));
+    prefix_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_q, N, ctx->d_block_sums, ctx->d_wsum,
+                                                      weights ? ctx->d_weights : nullptr);
+    LAUNCH_CHECK(ctx);
+
+    const unsigned long long Wd = Wglobal / (unsigned long long)Nglobal;
+    const unsigned long long Wm = Wglobal % (unsigned long long)Nglobal;
+    const unsigned long long U = (unsigned long long)(((unsigned __int128)Wd * u0_q32) >> 32);
+    // owned slots: rank_offset <= T_k < rank_offset + Wlocal
+    const long long k_begin = slots_below(rank_offset, U, Wd, Wm, Nglobal);
+    const long long k_end = slots_below(rank_offset + Wlocal, U, Wd, Wm, Nglobal);
+    const long long k_count = k_end - k_begin;
+    if (ancestors && k_count > 0) {
+        if ((size_t)k_count > ctx->anc_cap) {
+            if (ctx->d_ancestors) cudaFree(ctx->d_ancestors);
+            ctx->d_ancestors = nullptr;
+            ctx->anc_cap = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->d_ancestors, sizeof(int32_t) * (size_t)k_count));
+            ctx->anc_cap = (size_t)k_count;
+        }
+        const unsigned grid = (unsigned)((k_count + 255) / 256);
+        resample_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_q, N, Nglobal, rank_offset, Wd, Wm, U,
+                                                       k_begin, k_count, index_base, ctx->d_ancestors);
+        LAUNCH_CHECK(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ancestors, ctx->d_ancestors, sizeof(int32_t) * (size_t)k_count,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (weights)
+        CUDA_TRY(ctx, cudaMemcpyAsync(weights, ctx->d_weights, sizeof(float) * (size_t)N,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (wsum) *wsum = Wglobal;
+    if (k_begin_out) *k_begin_out = k_begin;
+    if (k_count_out) *k_count_out = k_count;
+    return B200SLAM_OK;
+}

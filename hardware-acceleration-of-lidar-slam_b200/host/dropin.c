@@ -1,0 +1,170 @@
+/*
+ * dropin.c -- the reference's own C function names on top of libb200slam.so.
+ *
+ * libb200slam_dropin.so exports, with the reference's exact signatures,
+ *     void euclidean_distance_transform (int[200][200], float[200][200], int, int)
+ *     void euclidean_distance_transform2(int[400][400], float[400][400], int, int)
+ *         (Subsystem_1/main_accelerated.c:215,250; Subsystem_1/main.c:223,247 -- 3rd
+ *          argument = #columns, 4th = #rows at the only call site, main.c:355-356)
+ *     void FastMatch (const float POSE[3], const float searchResolution[3])
+ *     void FastMatch2(const float POSE[3], const float searchResolution[3])
+ *         (Subsystem_1/main.c:381,598)
+ * so that the unmodified reference program, built as a shared object, calls the GPU path
+ * when this library precedes it in the link order (ELF symbol interposition, see
+ * INTEGRATION.md).  FastMatch* read the reference's globals `scan` and `occ_grid` and write
+ * `FastMatchParameters`, exactly like the functions they replace; the struct layouts below
+ * restate main.c:60-66, 200-212, 374-378 and must match them.
+ *
+ * Errors: the reference functions return void and cannot fail, and there is no CPU
+ * fallback by design, so any failure prints the library's message and aborts.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "b200slam.h"
+
+#define REF_COLUMN 1079                       /* main.c:7 */
+
+typedef struct {                              /* main.c:60-66 */
+    float x[REF_COLUMN];
+    float y[REF_COLUMN];
+    float tx[REF_COLUMN];
+    float ty[REF_COLUMN];
+    int size;
+} ScanData;
+
+typedef struct {                              /* main.c:200-212 */
+    int grid[200][200];
+    int grid_size[2];
+    float metric_grid[200][200];
+    float pixel_size;
+    float top_left_corner[2];
+    int grid2[400][400];
+    int grid_size2[2];
+    float metric_grid2[400][400];
+    float pixel_size2;
+    float top_left_corner2[2];
+} MyGrid;
+
+typedef struct {                              /* main.c:374-378 */
+    float pose[3];
+    float bestHits[2500];
+    int bestHits_size;
+} MyFastMatchParameters;
+
+/* Defined by the reference translation unit this library is loaded next to. */
+extern ScanData scan __attribute__((weak));
+extern MyGrid occ_grid __attribute__((weak));
+extern MyFastMatchParameters FastMatchParameters __attribute__((weak));
+
+static b200slam_ctx *g_ctx;
+/* Device-resident twins of metric_grid / metric_grid2, kept from the last transform so
+ * FastMatch does not re-upload the field it was just handed. */
+static struct {
+    b200slam_map *map;
+    int rows, cols;
+    const float *host_field;                  /* which host array the device copy mirrors */
+} g_maps[2];
+
+static void die(const char *what, int rc)
+{
+    fprintf(stderr, "libb200slam_dropin: %s failed (%d): %s\n", what, rc, b200slam_last_error(g_ctx));
+    abort();
+}
+
+static b200slam_ctx *ctx(void)
+{
+    if (!g_ctx) {
+        const char *dev = getenv("B200SLAM_DEVICE");
+        int rc = b200slam_create(&g_ctx, dev ? atoi(dev) : 0);
+        if (rc) die("b200slam_create", rc);
+    }
+    return g_ctx;
+}
+
+static b200slam_map *slot_map(int slot, int rows, int cols)
+{
+    if (!g_maps[slot].map || g_maps[slot].rows != rows || g_maps[slot].cols != cols) {
+        if (g_maps[slot].map) b200slam_map_destroy(ctx(), g_maps[slot].map);
+        g_maps[slot].map = NULL;
+        int rc = b200slam_map_create(ctx(), rows, cols, &g_maps[slot].map);
+        if (rc) die("b200slam_map_create", rc);
+        g_maps[slot].rows = rows;
+        g_maps[slot].cols = cols;
+        g_maps[slot].host_field = NULL;
+    }
+    return g_maps[slot].map;
+}
+
+static void edt_common(int slot, const int *in, float *out, int stride, int ncols, int nrows)
+{
+    if (nrows <= 0 || ncols <= 0) return;
+    b200slam_map *m = slot_map(slot, nrows, ncols);
+    int rc = b200slam_map_upload_occupancy(ctx(), m, in, stride);
+    if (rc) die("b200slam_map_upload_occupancy", rc);
+    rc = b200slam_map_edt(ctx(), m, 10.0f);                     /* MAX_DIST, main.c:224 */
+    if (rc) die("b200slam_map_edt", rc);
+    rc = b200slam_map_download_field(ctx(), m, out, stride);    /* writes rows x cols only */
+    if (rc) die("b200slam_map_download_field", rc);
+    g_maps[slot].host_field = out;
+}
+
+void euclidean_distance_transform(int input_map[200][200], float output_distance_map[200][200],
+                                  int height, int width)
+{
+    /* argument names as in main_accelerated.c:215; call site passes (nCols, nRows). */
+    edt_common(0, &input_map[0][0], &output_distance_map[0][0], 200, height, width);
+}
+
+void euclidean_distance_transform2(int input_map[400][400], float output_distance_map[400][400],
+                                   int height, int width)
+{
+    edt_common(1, &input_map[0][0], &output_distance_map[0][0], 400, height, width);
+}
+
+static void fastmatch_common(int slot, const float POSE[3], const float searchResolution[3])
+{
+    if (!&scan || !&occ_grid || !&FastMatchParameters) {
+        fprintf(stderr, "libb200slam_dropin: FastMatch needs the reference globals scan / occ_grid / "
+                        "FastMatchParameters (load next to the reference object)\n");
+        abort();
+    }
+    const int rows = slot ? occ_grid.grid_size2[0] : occ_grid.grid_size[0];      /* main.c:388,605 */
+    const int cols = slot ? occ_grid.grid_size2[1] : occ_grid.grid_size[1];      /* main.c:389,606 */
+    const float *field = slot ? &occ_grid.metric_grid2[0][0] : &occ_grid.metric_grid[0][0];
+    const int stride = slot ? 400 : 200;
+    b200slam_map *m = slot_map(slot, rows, cols);
+    int rc;
+    if (g_maps[slot].host_field != field) {       /* field did not come from our transform */
+        rc = b200slam_map_upload_field(ctx(), m, field, stride);
+        if (rc) die("b200slam_map_upload_field", rc);
+        g_maps[slot].host_field = field;
+    }
+    rc = b200slam_map_set_geometry(m, slot ? occ_grid.pixel_size2 : occ_grid.pixel_size,
+                                   slot ? occ_grid.top_left_corner2[0] : occ_grid.top_left_corner[0],
+                                   slot ? occ_grid.top_left_corner2[1] : occ_grid.top_left_corner[1]);
+    if (rc) die("b200slam_map_set_geometry", rc);
+    rc = b200slam_scan_upload(ctx(), scan.x, scan.y, scan.size);                 /* main.c:417-421 */
+    if (rc) die("b200slam_scan_upload", rc);
+    rc = b200slam_fastmatch(ctx(), m, POSE, searchResolution, FastMatchParameters.pose,
+                            FastMatchParameters.bestHits, &FastMatchParameters.bestHits_size);
+    if (rc) die("b200slam_fastmatch", rc);
+}
+
+void FastMatch(const float POSE[3], const float searchResolution[3])
+{
+    fastmatch_common(0, POSE, searchResolution);
+}
+
+void FastMatch2(const float POSE[3], const float searchResolution[3])
+{
+    fastmatch_common(1, POSE, searchResolution);
+}
+
+/* The host field array may be rewritten by someone other than our transform (tests do);
+ * callers can force a re-upload on the next FastMatch. */
+void b200slam_dropin_invalidate(void)
+{
+    g_maps[0].host_field = NULL;
+    g_maps[1].host_field = NULL;
+}

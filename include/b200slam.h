@@ -1,0 +1,210 @@
+/*
+ * b200slam.h -- C ABI of libb200slam.so, the B200 (sm_100a) implementation of the
+ * lidar-SLAM hot path of circuitpotato/Hardware-Acceleration-of-LIDAR-SLAM:
+ * the clamped occupancy-grid Euclidean distance transform and the scan-matching /
+ * particle-weighting loop.
+ *
+ * Plain C: opaque handles, pointers and sizes only; no C++/CUDA/torch types cross this
+ * boundary.  Every function returns B200SLAM_OK (0) or a negative error code and never
+ * throws; b200slam_last_error() gives the message.  There is NO CPU fallback: without a
+ * CUDA device b200slam_create() fails and nothing else can be called.
+ *
+ * Citations `file:line` are to the reference tree; they name the reference interface the
+ * entry point replaces.  The reference-named drop-in wrappers
+ *   euclidean_distance_transform / euclidean_distance_transform2 / FastMatch / FastMatch2
+ * live in libb200slam_dropin.so (host/dropin.c) on top of this ABI -- see INTEGRATION.md.
+ *
+ * Conventions (reference): grid[row = y][col = x], row-major;
+ * strides are in ELEMENTS; poses are {x, y, theta} in metres / radians, theta applied as
+ * R(-theta) (Subsystem_1/main.c:462-463); candidate order is theta slowest, then x, then y
+ * (main.c:443,468,487) and ties go to the lowest linear index (strict `<`, main.c:549).
+ */
+#ifndef B200SLAM_H
+#define B200SLAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SLAM_OK          0
+#define B200SLAM_ERR_ARG    (-1)   /* bad argument / unsupported size            */
+#define B200SLAM_ERR_CUDA   (-2)   /* CUDA runtime error (message has the cause) */
+#define B200SLAM_ERR_NCCL   (-3)   /* NCCL missing or failed                     */
+#define B200SLAM_ERR_NOMEM  (-4)
+#define B200SLAM_ERR_STATE  (-5)   /* call order (e.g. no scan uploaded)         */
+
+#define B200SLAM_ABI_VERSION 1
+
+typedef struct b200slam_ctx b200slam_ctx;   /* one per process per GPU; not thread-safe,   */
+typedef struct b200slam_map b200slam_map;   /* like the reference's global scratch state   */
+
+/* Result of a match.  Mirrors what FastMatch leaves behind in FastMatchParameters
+ * (main.c:374-379, 554-557, 592-594). */
+typedef struct {
+    int64_t best_index;    /* global linear candidate index of the winner             */
+    float   best_score;    /* sum of distance-field values over in-bounds beams        */
+    float   best_pose[3];  /* {x, y, theta} of the winner                              */
+    int32_t best_hits;     /* number of in-bounds beams of the winner (bestHits_size)  */
+    int32_t last_hits;     /* number of in-bounds beams of the LAST candidate scored   */
+} b200slam_match;
+
+/* ---- context ------------------------------------------------------------------- */
+
+int  b200slam_abi_version(void);
+/* Creates the context on CUDA device `device` (one stream, scratch buffers).  Fails with
+ * B200SLAM_ERR_CUDA when there is no usable GPU. */
+int  b200slam_create(b200slam_ctx **out, int device);
+void b200slam_destroy(b200slam_ctx *ctx);
+/* Message of the last failure on this context (ctx == NULL: last create failure). */
+const char *b200slam_last_error(const b200slam_ctx *ctx);
+/* Blocks until everything queued on the context's stream has finished. */
+int  b200slam_sync(b200slam_ctx *ctx);
+/* The context's cudaStream_t, for callers that time with CUDA events or interoperate. */
+void *b200slam_stream(b200slam_ctx *ctx);
+/* Number of kernels this library has launched on the context since creation. */
+uint64_t b200slam_launch_count(const b200slam_ctx *ctx);
+/* name: >= 64 bytes. */
+int  b200slam_device_info(const b200slam_ctx *ctx, char *name, int *sm_count, int *cc_major,
+                          int *cc_minor, size_t *total_mem);
+/* Pinned host memory for callers that want full-speed H2D/D2H through the host calls. */
+int  b200slam_host_alloc(b200slam_ctx *ctx, size_t bytes, void **out);
+int  b200slam_host_free(b200slam_ctx *ctx, void *p);
+
+/* ---- distance transform ---------------------------------------------------------
+ * Replaces euclidean_distance_transform / euclidean_distance_transform2
+ * (Subsystem_1/main.c:223-269, Subsystem_1/main_accelerated.c:215-283,
+ *  Submodule_2/Accelereated_Euclidean_Distance_Transform.c:1-69) and the FPGA register call
+ * euclidean_distance_compute (Submodule_2/Hadrware_acclereated.cpp:223-233):
+ *     out[r][c] = d2min < max_dist^2 ? sqrtf(d2min) : max_dist
+ * with d2min the integer squared distance to the nearest non-zero cell inside the
+ * rows x cols sub-rectangle.  Bit-exact with the reference. */
+
+/* One-shot host call: H2D occupancy, transform on the GPU, D2H field.  Writes only
+ * out[0..rows)[0..cols) (main.c:225-226). */
+int b200slam_edt(b200slam_ctx *ctx, const int32_t *occ, int occ_stride, float *out,
+                 int out_stride, int rows, int cols, float max_dist);
+
+/* Device-resident map (the MyGrid container, main.c:200-213: grid + metric_grid +
+ * grid_size + pixel_size + top_left_corner). */
+int  b200slam_map_create(b200slam_ctx *ctx, int rows, int cols, b200slam_map **out);
+void b200slam_map_destroy(b200slam_ctx *ctx, b200slam_map *map);
+/* pixel_size / top_left_corner = {minX, minY} (main.c:357-362). */
+int  b200slam_map_set_geometry(b200slam_map *map, float pixel_size, float top_left_x,
+                               float top_left_y);
+int  b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const int32_t *occ,
+                                   int stride);
+/* occ -> field entirely on the device (async on the context's stream). */
+int  b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist);
+int  b200slam_map_download_field(b200slam_ctx *ctx, b200slam_map *map, float *out, int stride);
+/* Install a precomputed distance field (e.g. one produced by another GPU). */
+int  b200slam_map_upload_field(b200slam_ctx *ctx, b200slam_map *map, const float *field,
+                               int stride);
+/* Raw device pointers and pitches (elements), for zero-copy producers / consumers. */
+int  b200slam_map_device_ptrs(b200slam_map *map, int32_t **occ, int *occ_pitch, float **field,
+                              int *field_pitch);
+
+/* ---- scan matching ---------------------------------------------------------------
+ * Replaces the candidate-scoring loop of FastMatch / FastMatch2 (main.c:381-596, 598-809). */
+
+/* Sensor-frame scan points (ScanData.x/.y/.size, main.c:60-69), kept on the device until
+ * replaced. */
+int b200slam_scan_upload(b200slam_ctx *ctx, const float *x, const float *y, int nbeams);
+
+/* Axis value k of an n-point lattice axis centred on p: p + (float)(k - n/2) * s
+ * (n == 3 gives {p - s, p, p + s}, main.c:424-426, bit for bit). */
+float b200slam_lattice_value(float p, float s, int k, int n);
+
+/* Scores every candidate of the lattice {theta} x {tx} x {ty} around pose0 against `map`
+ * and returns the arg-min (lowest score, then lowest linear index).
+ *   step = {tx step, ty step, theta step}   (searchResolution, main.c:386-387)
+ *   n    = {n_theta, n_tx, n_ty}
+ *   scores          optional host [n0*n1*n2]: every candidate's score
+ *   last_hit_values optional host [nbeams]: in-bounds field values of the LAST candidate
+ *                   (what FastMatchParameters.bestHits holds after the call, main.c:515)
+ * cos/sin of the lattice angles come from the host libm, exactly as main.c:434-435. */
+int b200slam_score_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
+                           const float step[3], const int n[3], float *scores,
+                           float *last_hit_values, b200slam_match *result);
+
+/* Same, restricted to the theta-major rows [row_begin, row_end) of the n0*n1 (theta, tx)
+ * rows -- the unit candidates are sharded by across GPUs.  `result` is the shard-local
+ * arg-min with GLOBAL best_index.  With a communicator (b200slam_comm_init) and
+ * allreduce != 0 the per-rank bests are all-gathered and every rank returns the global
+ * winner. */
+int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
+                                const float step[3], const int n[3], int64_t row_begin,
+                                int64_t row_end, int allreduce, b200slam_match *result);
+
+/* Queues the same lattice match on the context's stream WITHOUT reading anything back
+ * (for device-timed loops and CUDA-graph capture); fetch with b200slam_match_fetch. */
+int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
+                                 const float step[3], const int n[3], int64_t row_begin,
+                                 int64_t row_end);
+int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result);
+
+/* Arbitrary pose / particle list: poses[P][3] = {x, y, theta}; ct/st optional [P]
+ * (cosf/sinf(theta) from the host libm when NULL).  scores (optional host [P]) and
+ * hits (optional host [P]) are copied back when given; the scores also stay on the device
+ * for b200slam_weights_resample.  index_base is added to best_index (shard offset). */
+int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *poses,
+                         const float *ct, const float *st, int64_t P, int64_t index_base,
+                         float *scores, int32_t *hits, b200slam_match *result);
+
+/* The reference call itself: 3x3x3 lattice around `pose` with t = search_resolution[0],
+ * r = search_resolution[2]; pose_out / best_hits / best_hits_size are exactly what
+ * FastMatch leaves in FastMatchParameters (main.c:374-379): the winner's pose, the winner's
+ * hit count, and the LAST candidate's hit values. */
+int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3],
+                       const float search_resolution[3], float pose_out[3], float *best_hits,
+                       int *best_hits_size);
+
+/* ---- CUDA graphs -----------------------------------------------------------------
+ * The replay loop's per-scan work (EDT + two matches, main.c:865-918) is a handful of
+ * microsecond-scale kernels; capture the *_async / map_edt calls once and replay them.
+ * Between begin and end only b200slam_map_edt and b200slam_score_lattice_async may be
+ * called, with scratch already sized by an identical un-captured call. */
+typedef struct b200slam_graph b200slam_graph;
+int  b200slam_graph_begin(b200slam_ctx *ctx);
+int  b200slam_graph_end(b200slam_ctx *ctx, b200slam_graph **out);
+int  b200slam_graph_launch(b200slam_ctx *ctx, b200slam_graph *graph);
+void b200slam_graph_destroy(b200slam_ctx *ctx, b200slam_graph *graph);
+
+/* ---- particle weights + systematic resampling (extension; not in the reference) ----
+ * Uses the scores of the most recent b200slam_score_poses call (device-resident):
+ *   w_i = exp_det(-beta * (score_i - score_min)),  q_i = (uint64)(w_i * 2^32),
+ *   W = sum q_i,  weights[i] = (float)((double)q_i / W),
+ *   T_k = U + floor(k*W/N),  U = ((W div N) * u0_q32) >> 32,
+ *   ancestors[k] = first i with inclusive prefix sum of q > T_k.
+ * Integer weights make the prefix sum associative, so the indices are identical on the
+ * CPU oracle, one GPU and eight GPUs.  With a communicator, score_min and W are global
+ * and ancestors holds this rank's slice [k_begin, k_end) of the N_global slots
+ * (k_begin/k_count returned), with GLOBAL ancestor indices. */
+int b200slam_weights_resample(b200slam_ctx *ctx, float beta, uint32_t u0_q32, float *weights,
+                              uint64_t *wsum, int32_t *ancestors, int64_t *k_begin,
+                              int64_t *k_count);
+
+/* ---- multi-resolution match (generalises the 2-level schedule of main.c:901-918) ---- */
+int b200slam_pyramid_match(b200slam_ctx *ctx, b200slam_map *const *maps, int levels,
+                           const float pose0[3], const float *steps /*[levels][3]*/,
+                           const int *n /*[levels][3]*/, b200slam_match *results /*[levels]*/);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------------------
+ * Only per-shard bests (8 B/rank) and weight sums (16 B/rank) are exchanged. */
+#define B200SLAM_UNIQUE_ID_BYTES 128
+int b200slam_comm_unique_id(void *id_out /*[128]*/);            /* rank 0 */
+int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id /*[128]*/);
+int b200slam_comm_destroy(b200slam_ctx *ctx);
+/* Even split of `total` units over nranks (pure host arithmetic). */
+void b200slam_shard_range(int64_t total, int nranks, int rank, int64_t *begin, int64_t *end);
+/* Packed (score, index) key used for the arg-min exchange and its merge (pure host). */
+uint64_t b200slam_pack_key(float score, uint32_t index);
+void     b200slam_unpack_key(uint64_t key, float *score, uint32_t *index);
+uint64_t b200slam_merge_keys(const uint64_t *keys, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SLAM_H */

@@ -1,0 +1,102 @@
+"""GPU parity: CUDA distance transform (through the C ABI) vs the CPU oracle and the
+reference's golden vectors.  Bar: bit-exact (integer d2min -> IEEE sqrtf)."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+
+def test_edt_golden_vectors(ctx, edt_golden):
+    g = edt_golden
+    for k in range(int(g["count"])):
+        occ = g[f"occ_{k}"].astype(np.int32)
+        out = ctx.edt(occ)
+        assert np.array_equal(bits(out), bits(g[f"out_{k}"])), f"golden EDT case {k}"
+
+
+@pytest.mark.parametrize("rows,cols,p", [
+    (1, 1, 1.0), (1, 1, 0.0), (1, 97, 0.1), (83, 1, 0.1), (7, 9, 0.3), (31, 33, 0.05), (64, 64, 0.01),
+    (65, 63, 0.01), (200, 200, 0.01), (400, 400, 0.05), (157, 127, 0.02), (300, 1000, 0.001),
+    (1000, 300, 0.003), (513, 767, 0.0), (90, 2111, 0.02),
+])
+def test_edt_matches_oracle_bernoulli(ctx, oracle, synth, rows, cols, p):
+    occ = synth.grid_bernoulli(rows, cols, p, seed=rows * 7919 + cols)
+    assert np.array_equal(bits(ctx.edt(occ)), bits(oracle.edt(occ)))
+
+
+def test_edt_rooms_and_nonbinary_occupancy(ctx, oracle, synth):
+    occ = synth.grid_rooms(700, 900, seed=4)
+    assert np.array_equal(bits(ctx.edt(occ)), bits(oracle.edt(occ)))
+    # any non-zero cell is an obstacle (Subsystem_1/main.c:227 tests truthiness)
+    occ2 = occ * np.int32(-7) + (occ * synth.grid_bernoulli(700, 900, 0.5, seed=9)) * np.int32(1 << 20)
+    assert np.array_equal(bits(ctx.edt(occ2)), bits(oracle.edt((occ2 != 0).astype(np.int32))))
+
+
+def test_edt_reference_strides_and_stale_border(ctx, oracle, synth):
+    # the reference keeps a fixed 400-wide array and only rows x cols is written
+    # (main.c:225-226); everything outside must be left untouched
+    rows, cols = 157, 127
+    inp = np.zeros((400, 400), np.int32)
+    inp[:rows, :cols] = synth.grid_bernoulli(rows, cols, 0.02, seed=31)
+    inp[rows:, :] = 1          # stale junk outside the sub-rectangle must not influence it
+    inp[:, cols:] = 1
+    out = np.full((400, 400), np.float32(-3.0))
+    ctx.edt(inp[:rows, :cols], out=out[:rows, :cols])
+    assert np.array_equal(bits(out[:rows, :cols]), bits(oracle.edt(np.ascontiguousarray(inp[:rows, :cols]))))
+    assert np.all(out[rows:, :] == -3.0) and np.all(out[:, cols:] == -3.0)
+
+
+@pytest.mark.parametrize("max_dist", [0.5, 1.0, 1.5, 2.0, 3.0, 4.5, 7.0, 10.0, 12.0, 15.0, 16.0, 20.0])
+def test_edt_other_max_dist(ctx, oracle, synth, max_dist):
+    occ = synth.grid_bernoulli(140, 190, 0.004, seed=int(max_dist * 10))
+    assert np.array_equal(bits(ctx.edt(occ, max_dist)), bits(oracle.edt(occ, max_dist)))
+
+
+def test_edt_device_resident_map(ctx, oracle, synth):
+    occ = synth.grid_rooms(333, 450, seed=8)
+    m = ctx.new_map(333, 450)
+    try:
+        m.upload_occupancy(occ).edt()
+        assert np.array_equal(bits(m.download_field()), bits(oracle.edt(occ)))
+        # idempotent re-run on resident data
+        m.edt()
+        assert np.array_equal(bits(m.download_field()), bits(oracle.edt(occ)))
+    finally:
+        m.close()
+
+
+def test_edt_2048_full_size(ctx, oracle, synth):
+    # BASELINE configs[1] grid size, compared cell for cell with the oracle
+    occ = synth.grid_bernoulli(2048, 2048, 0.01)
+    out = ctx.edt(occ)
+    assert np.array_equal(bits(out), bits(oracle.edt(occ)))
+
+
+def test_edt_8192_properties_and_tiles(ctx, oracle, synth):
+    # BASELINE configs[3] grid size: size-independent properties + oracle on sampled tiles
+    n = 8192
+    occ = synth.grid_bernoulli(n, n, 0.002)
+    out = ctx.edt(occ)
+    assert np.all(out[occ != 0] == 0.0)
+    assert float(out.max()) == 10.0 and float(out.min()) == 0.0
+    allowed = np.unique(np.concatenate([np.sqrt(np.arange(100, dtype=np.float32)), [np.float32(10.0)]]))
+    assert np.all(np.isin(np.unique(out), allowed))
+    # an interior tile depends only on the tile plus a 9-cell halo
+    for (r0, c0) in [(0, 0), (4000, 4100), (8192 - 300, 8192 - 300), (0, 8192 - 280), (5000, 0)]:
+        r1, c1 = min(r0 + 300, n), min(c0 + 300, n)
+        rr0, cc0, rr1, cc1 = max(r0 - 9, 0), max(c0 - 9, 0), min(r1 + 9, n), min(c1 + 9, n)
+        ref = oracle.edt(np.ascontiguousarray(occ[rr0:rr1, cc0:cc1]))
+        want = ref[r0 - rr0:r0 - rr0 + (r1 - r0), c0 - cc0:c0 - cc0 + (c1 - c0)]
+        assert np.array_equal(bits(out[r0:r1, c0:c1]), bits(want)), (r0, c0)
+    # monotone under adding obstacles
+    occ2 = occ.copy()
+    occ2[::97, ::89] = 1
+    out2 = ctx.edt(occ2)
+    assert np.all(out2 <= out)
+
+
+def test_edt_empty_shapes(ctx):
+    out = ctx.edt(np.zeros((0, 5), np.int32))
+    assert out.shape == (0, 5)

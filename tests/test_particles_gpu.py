@@ -1,0 +1,55 @@
+"""GPU parity: particle weights, normalisation and systematic resampling vs the CPU oracle.
+PARITY UNPINNED by the reference (it has no particle filter); the oracle's
+orc_weights_resample is the definition.  Bar: ancestor indices and integer weight sum
+bit-exact, float weights bit-exact (same IEEE operations), checked against 1e-5 as well."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("P,beta", [(1, 1.0), (7, 0.5), (1024, 0.2), (1025, 2.0), (100000, 0.05)])
+def test_weights_and_resample_match_oracle(ctx, oracle, synth, P, beta):
+    w = synth.make_workload("tiny")
+    field = oracle.edt(w["occ"])
+    m = ctx.new_map(*field.shape)
+    try:
+        m.set_geometry(w["pixel"], w["top_left"]).upload_field(field)
+        nb = 720 if P >= 100000 else 180
+        sx, sy = synth.scan_fixed_count(w["occ"], float(w["pixel"]), w["top_left"], w["true_pose"], nb)
+        ctx.scan_upload(sx, sy)
+        poses = synth.particles_gaussian(P, w["true_pose"], 0.25, 0.05)
+        om = oracle.make_map(field, w["pixel"], w["top_left"])
+        _, oscores, _ = oracle.score_poses(om, sx, sy, poses)
+        _, scores, _ = ctx.score_poses(m, poses)
+        assert np.array_equal(bits(scores), bits(oscores))
+        u0 = 0x80000000          # u0 = 0.5 slot
+        ow, oq, oW, oanc = oracle.weights_resample(oscores, beta, u0)
+        gw, gW, ganc, kb, kc = ctx.weights_resample(P, beta, u0)
+        assert gW == oW
+        assert kb == 0 and kc == P
+        assert np.array_equal(ganc, oanc)
+        assert np.allclose(gw, ow, rtol=1e-5, atol=0.0) and np.array_equal(bits(gw), bits(ow))
+    finally:
+        m.close()
+
+
+def test_resample_is_sorted_and_proportional(ctx, oracle, synth):
+    w = synth.make_workload("tiny")
+    field = oracle.edt(w["occ"])
+    m = ctx.new_map(*field.shape)
+    try:
+        m.set_geometry(w["pixel"], w["top_left"]).upload_field(field)
+        ctx.scan_upload(w["scan_x"], w["scan_y"])
+        P = 20000
+        poses = synth.particles_gaussian(P, w["true_pose"], 0.4, 0.1, seed=5)
+        ctx.score_poses(m, poses)
+        gw, gW, anc, _, _ = ctx.weights_resample(P, 0.1, 12345)
+        assert np.all(np.diff(anc) >= 0)
+        counts = np.bincount(anc, minlength=P)
+        assert np.all(np.abs(counts - gw.astype(np.float64) * P) <= 1.0 + 1e-3)
+        assert abs(float(gw.astype(np.float64).sum()) - 1.0) < 1e-5
+    finally:
+        m.close()

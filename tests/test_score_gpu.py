@@ -1,0 +1,234 @@
+"""GPU parity: candidate-lattice / pose-list scoring through the C ABI vs the CPU oracle
+and the reference's FastMatch golden vectors.  Bar: best index, pose and hit counts
+bit-exact; scores bit-exact too (the kernel keeps the reference's summation order), which
+is stricter than the 1e-5 relative tolerance north_star allows."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5   # north_star tolerance for scores; asserted in addition to bit-equality
+
+
+def _setup(ctx, oracle, w, field=None):
+    field = oracle.edt(w["occ"]) if field is None else field
+    rows, cols = field.shape
+    m = ctx.new_map(rows, cols)
+    m.set_geometry(w["pixel"], w["top_left"]).upload_field(field)
+    ctx.scan_upload(w["scan_x"], w["scan_y"])
+    om = oracle.make_map(field, w["pixel"], w["top_left"])
+    return m, om
+
+
+def _check_lattice(ctx, oracle, m, om, w, n, step=None, pose0=None):
+    step = w["step"] if step is None else step
+    pose0 = w["pose0"] if pose0 is None else pose0
+    ores, oscores, olast = oracle.score_lattice(om, w["scan_x"], w["scan_y"], pose0, step, n, want_last_hits=True)
+    res, scores, last = ctx.score_lattice(m, pose0, step, n, want_scores=True, want_last_hits=True)
+    assert np.allclose(scores, oscores, rtol=REL_TOL, atol=0.0)
+    assert np.array_equal(bits(scores), bits(oscores)), "scores not bit-identical"
+    assert res.best_index == ores.best_index
+    assert np.float32(res.best_score).tobytes() == np.float32(ores.best_score).tobytes()
+    assert np.array_equal(bits(res.pose()), bits(np.array(list(ores.best_pose), np.float32)))
+    assert res.best_hits == ores.best_hits and res.last_hits == ores.last_hits
+    assert np.array_equal(bits(last[:res.last_hits]), bits(olast[:ores.last_hits]))
+    return res
+
+
+def test_fastmatch_golden_vectors(ctx, fastmatch_golden):
+    g = fastmatch_golden
+    for k in range(int(g["count"])):
+        field = g[f"field_{k}"]
+        pixel, tlx, tly = g[f"geom_{k}"]
+        m = ctx.new_map(*field.shape)
+        try:
+            m.set_geometry(pixel, (tlx, tly)).upload_field(field)
+            ctx.scan_upload(g[f"scan_x_{k}"], g[f"scan_y_{k}"])
+            pose, hits, n = ctx.fastmatch(m, g[f"pose_{k}"], g[f"res_{k}"])
+            last = int(g[f"out_last_{k}"])
+            assert np.array_equal(bits(pose), bits(g[f"out_pose_{k}"])), f"case {k} pose"
+            assert n == int(g[f"out_size_{k}"]), f"case {k} bestHits_size"
+            assert np.array_equal(bits(hits[:last]), bits(g[f"out_hits_{k}"])), f"case {k} bestHits"
+        finally:
+            m.close()
+
+
+@pytest.mark.parametrize("n", [(3, 3, 3), (1, 1, 1), (2, 5, 7), (8, 16, 16), (5, 33, 9), (4, 70, 67), (3, 40, 130)])
+def test_lattice_matches_oracle_shapes(ctx, oracle, synth, n):
+    w = synth.make_workload("tiny")
+    m, om = _setup(ctx, oracle, w)
+    try:
+        _check_lattice(ctx, oracle, m, om, w, n)
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("nbeams", [0, 1, 31, 64, 65, 129, 1079, 2500])
+def test_lattice_ragged_beam_counts(ctx, oracle, synth, nbeams):
+    w = synth.make_workload("tiny")
+    x, y = synth.scan_fixed_count(w["occ"], float(w["pixel"]), w["top_left"], w["true_pose"], max(nbeams, 1))
+    w["scan_x"], w["scan_y"] = x[:nbeams], y[:nbeams]
+    m, om = _setup(ctx, oracle, w)
+    try:
+        _check_lattice(ctx, oracle, m, om, w, (4, 9, 10))
+    finally:
+        m.close()
+
+
+def test_lattice_exact_ties_pick_lowest_index(ctx, oracle, synth):
+    # translation steps far below a pixel: many candidates hit identical cells in identical
+    # order, so scores tie exactly and the winner must be the lowest linear index
+    w = synth.make_workload("tiny")
+    m, om = _setup(ctx, oracle, w)
+    try:
+        res = _check_lattice(ctx, oracle, m, om, w, (3, 12, 12), step=np.array([0.002, 0.002, 1e-5], np.float32))
+        _, scores, _ = ctx.score_lattice(m, w["pose0"], np.array([0.002, 0.002, 1e-5], np.float32), (3, 12, 12),
+                                         want_scores=True)
+        tied = np.nonzero(bits(scores) == bits(np.float32(res.best_score)))[0]
+        assert len(tied) > 1 and res.best_index == tied.min()
+    finally:
+        m.close()
+
+
+def test_lattice_partially_and_fully_outside(ctx, oracle, synth):
+    w = synth.make_workload("tiny")
+    m, om = _setup(ctx, oracle, w)
+    try:
+        # lattice straddling the map border: some candidates lose beams, some lose all
+        far = np.array([w["top_left"][0] + 1.0, w["top_left"][1] + 0.5, 0.3], np.float32)
+        _check_lattice(ctx, oracle, m, om, w, (3, 20, 20), step=np.array([0.4, 0.4, 0.05], np.float32), pose0=far)
+        # everything outside: every score is 0, index 0 wins (zero-hit quirk)
+        out = np.array([500.0, -700.0, 0.0], np.float32)
+        res = _check_lattice(ctx, oracle, m, om, w, (2, 3, 4), pose0=out)
+        assert res.best_index == 0 and res.best_score == 0.0 and res.best_hits == 0
+    finally:
+        m.close()
+
+
+def test_lattice_on_field_computed_on_device(ctx, oracle, synth):
+    # EDT and matcher chained on the device (no host round trip of the field)
+    w = synth.make_workload("tiny")
+    rows, cols = w["occ"].shape
+    m = ctx.new_map(rows, cols)
+    try:
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+        ctx.scan_upload(w["scan_x"], w["scan_y"])
+        om = oracle.make_map(oracle.edt(w["occ"]), w["pixel"], w["top_left"])
+        _check_lattice(ctx, oracle, m, om, w, (8, 16, 16))
+    finally:
+        m.close()
+
+
+def test_lattice_row_shards_merge_to_global_best(ctx, oracle, synth, b200slam):
+    # the multi-GPU decomposition, emulated on one GPU: each shard's packed key merged on
+    # the host must equal the un-sharded winner (lowest score, then lowest global index)
+    w = synth.make_workload("tiny")
+    m, om = _setup(ctx, oracle, w)
+    try:
+        n = (6, 20, 12)
+        whole = ctx.score_lattice(m, w["pose0"], w["step"], n)[0]
+        for nranks in (2, 3, 8):
+            keys = []
+            for r in range(nranks):
+                b, e = b200slam.shard_range(n[0] * n[1], nranks, r)
+                part = ctx.score_lattice_rows(m, w["pose0"], w["step"], n, b, e)
+                if part.best_index >= 0:
+                    assert b * n[2] <= part.best_index < e * n[2]
+                    keys.append(b200slam.pack_key(part.best_score, part.best_index))
+            s, i = b200slam.unpack_key(b200slam.merge_keys(keys))
+            assert i == whole.best_index and np.float32(s) == np.float32(whole.best_score)
+    finally:
+        m.close()
+
+
+def test_config1_full_size_64k_x_360(ctx, oracle, synth):
+    # BASELINE configs[1] at full size: 2048^2 map, 64 x 32 x 32 lattice, 360 beams
+    w = synth.make_workload("config1")
+    rows, cols = w["occ"].shape
+    m = ctx.new_map(rows, cols)
+    try:
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+        field = m.download_field()
+        assert np.array_equal(bits(field), bits(oracle.edt(w["occ"])))
+        ctx.scan_upload(w["scan_x"], w["scan_y"])
+        om = oracle.make_map(field, w["pixel"], w["top_left"])
+        _check_lattice(ctx, oracle, m, om, w, w["n"])
+    finally:
+        m.close()
+
+
+def test_pose_list_matches_oracle(ctx, oracle, synth):
+    w = synth.make_workload("tiny")
+    m, om = _setup(ctx, oracle, w)
+    try:
+        for P in (1, 31, 1000, 4097):
+            poses = synth.particles_gaussian(P, w["true_pose"], 0.6, 0.2, seed=P)
+            ores, oscores, ohits = oracle.score_poses(om, w["scan_x"], w["scan_y"], poses)
+            res, scores, hits = ctx.score_poses(m, poses)
+            assert np.array_equal(bits(scores), bits(oscores))
+            assert np.array_equal(hits, ohits)
+            assert res.best_index == ores.best_index and res.best_hits == ores.best_hits
+            assert np.array_equal(bits(res.pose()), bits(poses[ores.best_index]))
+        # index_base shifts the reported winner (shard offset)
+        res2, _, _ = ctx.score_poses(m, poses, index_base=1000)
+        assert res2.best_index == ores.best_index + 1000
+    finally:
+        m.close()
+
+
+def test_pyramid_match_three_levels(ctx, oracle, synth):
+    # coarse-to-fine over three independently rasterised maps (p, 2p, 4p), SURVEY 8a-a9
+    base = synth.make_workload("tiny")
+    occ_f = base["occ"]
+    maps, omaps = [], []
+    try:
+        for lvl, f in enumerate((4, 2, 1)):                 # coarsest first
+            rows, cols = occ_f.shape[0] // f, occ_f.shape[1] // f
+            occ = occ_f[:rows * f, :cols * f].reshape(rows, f, cols, f).max(axis=(1, 3)).astype(np.int32)
+            pixel, tl = synth.centred_geometry(rows, cols, 0.1 * f)
+            field = oracle.edt(occ)
+            mp = ctx.new_map(rows, cols)
+            mp.set_geometry(pixel, tl).upload_occupancy(occ).edt()
+            maps.append(mp)
+            omaps.append(oracle.make_map(field, pixel, tl))
+        ctx.scan_upload(base["scan_x"], base["scan_y"])
+        steps = np.array([[0.2, 0.2, 0.035], [0.1, 0.1, 0.0175], [0.05, 0.05, 0.008727]], np.float32)
+        ns = np.array([[9, 11, 11], [5, 7, 7], [3, 5, 5]], np.int32)
+        got = ctx.pyramid_match(maps, base["pose0"], steps, ns)
+        want = oracle.pyramid_match(omaps, base["scan_x"], base["scan_y"], base["pose0"], steps, ns)
+        for g, wv in zip(got, want):
+            assert g.best_index == wv.best_index and g.best_hits == wv.best_hits
+            assert np.array_equal(bits(g.pose()), bits(np.array(list(wv.best_pose), np.float32)))
+            assert np.float32(g.best_score).tobytes() == np.float32(wv.best_score).tobytes()
+    finally:
+        for mp in maps:
+            mp.close()
+
+
+def test_graph_replay_matches_eager(ctx, oracle, synth):
+    w = synth.make_workload("tiny")
+    rows, cols = w["occ"].shape
+    m = ctx.new_map(rows, cols)
+    try:
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"])
+        ctx.scan_upload(w["scan_x"], w["scan_y"])
+        n = (8, 16, 16)
+        m.edt()
+        ctx.score_lattice_async(m, w["pose0"], w["step"], n)
+        eager = ctx.match_fetch()
+        before = ctx.launch_count()
+        ctx.graph_begin()
+        m.edt()
+        ctx.score_lattice_async(m, w["pose0"], w["step"], n)
+        g = ctx.graph_end()
+        assert ctx.launch_count() == before
+        for _ in range(3):
+            ctx.graph_launch(g)
+        again = ctx.match_fetch()
+        assert ctx.launch_count() == before + 3 * 3        # EDT + lattice + trace per replay
+        assert again.best_index == eager.best_index and again.best_hits == eager.best_hits
+        ctx.graph_destroy(g)
+    finally:
+        m.close()
