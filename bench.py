@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- pose x beam evals/s and EDT Mcells/s of the b200slam hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config1|config3|tiny]
+    python bench.py --impl reference ...        # the reference's own CPU code, same metric
+
+A "step" is one pass of the hot path over one batch of synthetic input: the clamped EDT of
+the occupancy grid followed by the correlative scan match of every lattice candidate against
+the fresh distance field, ending in the arg-min (BASELINE.json configs[1]: 2048x2048 grid,
+64 x 32 x 32 = 65 536 candidate poses x 360 beams).
+
+Own arm, per rank (one process per GPU; torch.distributed only for barrier / max-over-ranks):
+  * `value`  : whole-job pose x beam evals / s with inputs resident in HBM: K steps replayed
+               back to back as CUDA graphs (the step is a handful of microsecond kernels),
+               bracketed by barrier + sync, timed with CUDA events on the library's stream,
+               max over ranks.  Steps cycle through a ring of distinct maps larger than L2.
+  * per-kernel durations (eager pass, CUDA events around every kernel) -> `roofline`
+  * `e2e`    : the same step through the host-buffer C ABI calls: H2D of the int32 grid and
+               the scan from pinned memory and D2H of the match result inside the timed region
+  * `cpu_baseline` (rank 0, N == 1): the reference's own EDT2 + FastMatch2 (oracle/_ref) or the
+               oracle port, 1 core, on a bounded sample of the same workload
+N > 1: weak scaling -- every rank keeps the per-GPU workload (map replicated, its own block
+of theta rows of an N-times larger lattice) and the per-rank bests are all-gathered with
+NCCL inside the step.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "hardware-acceleration-of-lidar-slam_b200"
+
+METRIC = "pose_x_beam_evals_per_s"
+UNIT = "evals/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ----------------------------------------------------------------------------------------
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full summary, or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = the upper half of the samples (idle samples bracket the region)
+        load = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(smax), "samples": len(sm),
+                "power_w_max": max(power), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_sample(w, synth, budget_s: float = 12.0, want_kind: str | None = None) -> dict:
+    """Times the reference CPU path on a bounded sample of workload `w` (1 core: the reference
+    is single-threaded).  kind "reference": the reference's own euclidean_distance_transform2
+    and FastMatch2, compiled unmodified (oracle/_ref); kind "port": the oracle restatement."""
+    from oracle import pyoracle
+    orc = pyoracle.Oracle()
+    rows, cols = w["occ"].shape
+    n = w["n"]
+    nb_full = len(w["scan_x"])
+    evals_full = n[0] * n[1] * n[2] * nb_full
+    cells_full = rows * cols
+    use_ref = pyoracle.reference_available() and want_kind != "port"
+    S = min(400, rows, cols)
+    r0, c0 = (rows - S) // 2, (cols - S) // 2
+    crop = np.ascontiguousarray(w["occ"][r0:r0 + S, c0:c0 + S])
+    pixel = float(w["pixel"])
+    tl = (np.float32(w["top_left"][0] + c0 * pixel), np.float32(w["top_left"][1] + r0 * pixel))
+    nb = min(nb_full, 1079)
+    sx, sy = w["scan_x"][:nb], w["scan_y"][:nb]
+    res3 = np.array([w["step"][0], w["step"][1], w["step"][2]], np.float32)
+    if use_ref:
+        ref = pyoracle.Reference("accel")
+        t0 = time.perf_counter()
+        field = ref.edt(crop, fine=True)                      # reference EDT2, <= 400 x 400
+        t_edt = time.perf_counter() - t0
+        ref.set_map(field, pixel, tl, fine=True)
+        ref.set_scan(sx, sy)
+        calls, t0 = 0, time.perf_counter()
+        while True:
+            ref.fastmatch(w["pose0"], res3, fine=True)        # 5 sweeps x 27 candidates
+            calls += 1
+            t_fm = time.perf_counter() - t0
+            if t_fm > max(1.0, budget_s - t_edt) or calls >= 20000:
+                break
+        evals = calls * 135 * nb
+        kind = "reference"
+        what = (f"reference euclidean_distance_transform2 on a {S}x{S} crop ({t_edt:.3f} s) + {calls} x "
+                f"reference FastMatch2 (135 candidate evals x {nb} beams each, {t_fm:.3f} s)")
+    else:
+        t0 = time.perf_counter()
+        field = orc.edt(crop, variant="scatter")              # the reference's scatter-form loop nest
+        t_edt = time.perf_counter() - t0
+        om = orc.make_map(field, pixel, tl)
+        nn = (min(n[0], 16), n[1], n[2])
+        t0 = time.perf_counter()
+        orc.score_lattice(om, sx, sy, w["pose0"], w["step"], nn, want_scores=False)
+        t_fm = time.perf_counter() - t0
+        evals = nn[0] * nn[1] * nn[2] * nb
+        kind = "port"
+        what = (f"oracle scatter-form EDT on a {S}x{S} crop ({t_edt:.3f} s) + oracle lattice "
+                f"{nn[0]}x{nn[1]}x{nn[2]} x {nb} beams ({t_fm:.3f} s)")
+    evals_per_s = evals / t_fm
+    cells_per_s = S * S / t_edt
+    # one full step on this CPU at the sampled rates (the EDT term is generous to the
+    # reference: its loop nest is O(occupied x cells), so it slows down with area)
+    t_step = cells_full / cells_per_s + evals_full / evals_per_s
+    return {"value": evals_full / t_step, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": what + "; value = full-step evals / (cells/rate_edt + evals/rate_match), extrapolated",
+            "match_evals_per_s": evals_per_s, "edt_mcells_per_s": cells_per_s / 1e6,
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference_arm(args, synth):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = synth.make_workload(args.workload)
+    K, W = args.steps, args.warmup
+    per = max(0.4, min(4.0, 150.0 / max(K + W, 1)))
+    vals, last = [], None
+    t_all = time.perf_counter()
+    for i in range(W + K):
+        s = cpu_sample(w, synth, budget_s=per)
+        if i >= W:
+            vals.append(s["value"])
+        last = s
+        if time.perf_counter() - t_all > 240 and len(vals) >= 3:
+            break
+    v = statistics.median(vals)
+    n = w["n"]
+    evals_full = n[0] * n[1] * n[2] * len(w["scan_x"])
+    last["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": W, "ms_per_step": evals_full / v * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, args, 1), "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, args, world) -> dict:
+    rows, cols = w["occ"].shape
+    n = w["n"]
+    return {"workload": f"{args.workload}: synthetic {rows}x{cols} occupancy grid EDT (max_dist 10) + "
+                        f"correlative scan match over {n[0] * world}x{n[1]}x{n[2]} = {n[0] * n[1] * n[2] * world} "
+                        f"candidate poses x {len(w['scan_x'])} beams",
+            "grid": [rows, cols], "lattice_per_gpu": list(n), "beams": len(w["scan_x"]),
+            "pixel_m": float(w["pixel"]), "lattice_step": [float(x) for x in w["step"]],
+            "parallelism": f"candidate rows sharded over {world} GPU(s), map replicated",
+            "l2": "ring of distinct maps larger than the 126 MB L2, one per step"}
+
+
+# ----------------------------------------------------------------------------------------
+def run_b200_arm(args, synth):
+    mod = importlib.import_module(PKG)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+
+    w = synth.make_workload(args.workload)
+    rows, cols = w["occ"].shape
+    nth, ntx, nty = w["n"]
+    nbeams = len(w["scan_x"])
+    n_global = (nth * world, ntx, nty)
+    row_b, row_e = rank * nth * ntx, (rank + 1) * nth * ntx
+    evals_per_rank = nth * ntx * nty * nbeams
+    cells = rows * cols
+
+    ctx = mod.Context(local_rank)
+    if world > 1:
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+
+    # ring of maps so that consecutive steps never find their inputs in L2
+    set_bytes = cells * 8
+    ring = max(2, min(16, -(-2 * L2_BYTES // set_bytes) + 1))
+    occs, maps = [], []
+    for i in range(ring):
+        occ = w["occ"] if i == 0 else synth.grid_rooms(rows, cols, synth.SEED_GRID + i)
+        pin = ctx.pinned_empty((rows, cols), np.int32)
+        pin[...] = occ
+        occs.append(pin)
+        m = ctx.new_map(rows, cols)
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(pin)
+        maps.append(m)
+    scan_x = ctx.pinned_empty((nbeams,), np.float32); scan_x[...] = w["scan_x"]
+    scan_y = ctx.pinned_empty((nbeams,), np.float32); scan_y[...] = w["scan_y"]
+    ctx.scan_upload(scan_x, scan_y)
+    allreduce = world > 1
+
+    def step_async(i):
+        m = maps[i % ring]
+        m.edt(10.0)
+        ctx.score_lattice_async(m, w["pose0"], w["step"], n_global, row_b, row_e, allreduce)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up (sizes every scratch buffer; also checks the result is sane) ----------
+    for i in range(W):
+        step_async(i)
+    first = ctx.match_fetch()
+    assert first.best_index >= 0
+
+    # ---- pass A: eager, CUDA events around every kernel -> per-kernel durations ---------
+    KA = min(K, 300)
+    barrier()
+    for i in range(KA):
+        ctx.event_record(3 * i)
+        maps[i % ring].edt(10.0)
+        ctx.event_record(3 * i + 1)
+        ctx.score_lattice_async(maps[i % ring], w["pose0"], w["step"], n_global, row_b, row_e)
+        ctx.event_record(3 * i + 2)
+    ctx.sync()
+    edt_ms = [ctx.event_elapsed_ms(3 * i, 3 * i + 1) for i in range(KA)]
+    lat_ms = [ctx.event_elapsed_ms(3 * i + 1, 3 * i + 2) for i in range(KA)]
+    edt_ms_avg, lat_ms_avg = sum(edt_ms) / KA, sum(lat_ms) / KA
+
+    # ---- pass B: the timed region.  One CUDA graph per ring slot, K replays --------------
+    graphs = []
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            for i in range(ring):
+                ctx.graph_begin()
+                step_async(i)
+                graphs.append(ctx.graph_end())
+        except mod.B200SlamError as e:
+            if rank == 0:
+                print(f"[bench] graph capture unavailable ({e}); timing eager launches", file=sys.stderr)
+            use_graph = False
+            graphs = []
+    for i in range(W):
+        ctx.graph_launch(graphs[i % ring]) if use_graph else step_async(i)
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.event_record(4000)
+    for i in range(K):
+        ctx.graph_launch(graphs[i % ring]) if use_graph else step_async(i)
+    ctx.event_record(4001)
+    barrier()
+    dev_ms = ctx.event_elapsed_ms(4000, 4001)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    last = ctx.match_fetch()
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------
+    KE = max(3, min(K, 50 if cells <= (1 << 23) else 10))
+    res = mod.Match()
+
+    def step_e2e(i):
+        m = maps[i % ring]
+        m.upload_occupancy(occs[i % ring])                     # H2D int32 grid (pinned)
+        m.edt(10.0)
+        ctx.scan_upload(scan_x, scan_y)                        # H2D scan (pinned)
+        return ctx.score_lattice_rows(m, w["pose0"], w["step"], n_global, row_b, row_e, allreduce)  # D2H result
+
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(KE):
+        res = step_e2e(i)
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = cells * 4 + 2 * nbeams * 4 + (2 * n_global[0] + ntx + nty) * 4
+    d2h = 16
+
+    # ---- max over ranks ---------------------------------------------------------------
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_s, edt_ms_avg, lat_ms_avg], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, edt_ms_avg, lat_ms_avg = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        ms_per_step = dev_ms / K
+        total_evals = evals_per_rank * world
+        value = total_evals / (ms_per_step * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        edt_bytes = 8.0 * cells                                              # 8 B / cell
+        lat_bytes = 4.0 * evals_per_rank + 4.0 * nth * ntx * nty + 8.0 * nbeams   # 4 B / eval + 4 B / pose
+        roofs = {
+            "edt_fused_kernel": {"bound": "hbm", "achieved": edt_bytes / (edt_ms_avg * 1e-3) / 1e9, "peak": peak,
+                                 "unit": "GB/s", "ms": edt_ms_avg, "algorithmic_bytes": edt_bytes,
+                                 "traffic": ncu_traffic(f"edt_fused_kernel:{args.workload}"),
+                                 "mcells_per_s": cells / (edt_ms_avg * 1e-3) / 1e6},
+            "lattice_kernel": {"bound": "hbm", "achieved": lat_bytes / (lat_ms_avg * 1e-3) / 1e9, "peak": peak,
+                               "unit": "GB/s", "ms": lat_ms_avg, "algorithmic_bytes": lat_bytes,
+                               "traffic": ncu_traffic(f"lattice_kernel:{args.workload}"),
+                               "evals_per_s": evals_per_rank / (lat_ms_avg * 1e-3),
+                               "note": "gathers are served by L1/L2 (field is cache resident), so this "
+                                       "HBM-equivalent figure may exceed the DRAM peak; ms includes the "
+                                       "2-warp trace kernel"},
+        }
+        for r in roofs.values():
+            r["frac"] = r["achieved"] / r["peak"]
+        dom = max(roofs, key=lambda k: roofs[k]["ms"])
+        roofline = dict(roofs[dom])
+        roofline["kernel"] = dom
+        roofline["peak_source"] = peak_src
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(w, args, world), ring_maps=ring,
+                           timing="cuda-graph replay" if use_graph else "eager launches"),
+            "edt_mcells_per_s": cells / (edt_ms_avg * 1e-3) / 1e6,
+            "match_evals_per_s_per_gpu": evals_per_rank / (lat_ms_avg * 1e-3),
+            "roofline": roofline, "rooflines": roofs,
+            "e2e": {"value": total_evals / (e2e_s / KE), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / KE * 1e3, "steps": KE},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "result": {"best_index": int(last.best_index), "best_score": float(last.best_score),
+                       "best_hits": int(last.best_hits), "e2e_best_index": int(res.best_index)},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_sample(w, synth, budget_s=args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+
+    for g in graphs:
+        ctx.graph_destroy(g)
+    for m in maps:
+        m.close()
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config1", choices=["config1", "config3", "tiny"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    synth = importlib.import_module(PKG + ".synth")
+    if args.impl == "reference":
+        run_reference_arm(args, synth)
+    else:
+        run_b200_arm(args, synth)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,7 +92,7 @@ def load_library() -> C.CDLL:
         "b200slam_score_lattice": (i, [vp, vp, c_float_p, c_float_p, c_int_p, vp, vp, C.POINTER(Match)]),
         "b200slam_score_lattice_rows": (i, [vp, vp, c_float_p, c_float_p, c_int_p, C.c_int64, C.c_int64, i,
                                             C.POINTER(Match)]),
-        "b200slam_score_lattice_async": (i, [vp, vp, c_float_p, c_float_p, c_int_p, C.c_int64, C.c_int64]),
+        "b200slam_score_lattice_async": (i, [vp, vp, c_float_p, c_float_p, c_int_p, C.c_int64, C.c_int64, i]),
         "b200slam_match_fetch": (i, [vp, C.POINTER(Match)]),
         "b200slam_score_poses": (i, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.POINTER(Match)]),
         "b200slam_fastmatch": (i, [vp, vp, c_float_p, c_float_p, c_float_p, vp, c_int_p]),
@@ -100,6 +100,8 @@ def load_library() -> C.CDLL:
         "b200slam_graph_end": (i, [vp, C.POINTER(vp)]),
         "b200slam_graph_launch": (i, [vp, vp]),
         "b200slam_graph_destroy": (None, [vp, vp]),
+        "b200slam_event_record": (i, [vp, i]),
+        "b200slam_event_elapsed_ms": (i, [vp, i, i, c_float_p]),
         "b200slam_weights_resample": (i, [vp, f, C.c_uint32, vp, c_u64_p, vp, c_i64_p, c_i64_p]),
         "b200slam_pyramid_match": (i, [vp, C.POINTER(vp), i, c_float_p, c_float_p, c_int_p, C.POINTER(Match)]),
         "b200slam_comm_unique_id": (i, [vp]),
@@ -308,11 +310,11 @@ class Context:
                                                        row_end, 1 if allreduce else 0, C.byref(res)))
         return res
 
-    def score_lattice_async(self, m: Map, pose0, step, n, row_begin=None, row_end=None):
+    def score_lattice_async(self, m: Map, pose0, step, n, row_begin=None, row_end=None, allreduce=False):
         if row_begin is None:
             row_begin, row_end = 0, int(n[0]) * int(n[1])
         self._check(self.L.b200slam_score_lattice_async(self.h, m.h, _f3(pose0), _f3(step), _i3(n), row_begin,
-                                                        row_end))
+                                                        row_end, 1 if allreduce else 0))
 
     def match_fetch(self) -> Match:
         res = Match()
@@ -375,6 +377,15 @@ class Context:
 
     def graph_destroy(self, g):
         self.L.b200slam_graph_destroy(self.h, g)
+
+    # -- timing ----------------------------------------------------------------------
+    def event_record(self, slot: int):
+        self._check(self.L.b200slam_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        self._check(self.L.b200slam_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
 
     # -- multi-GPU -------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:

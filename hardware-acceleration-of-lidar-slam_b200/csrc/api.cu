@@ -85,6 +85,8 @@ void b200slam_destroy(b200slam_ctx *ctx)
     cudaFree(ctx->d_edt_scratch);
     for (int i = 0; i < LAT_SLOTS; ++i)
         if (ctx->lat_event[i]) cudaEventDestroy(ctx->lat_event[i]);
+    for (int i = 0; i < 4096; ++i)
+        if (ctx->timing[i]) cudaEventDestroy(ctx->timing[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -445,9 +447,10 @@ int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result)
 }
 
 int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
-                                 const float step[3], const int n[3], int64_t row_begin, int64_t row_end)
+                                 const float step[3], const int n[3], int64_t row_begin, int64_t row_end,
+                                 int allreduce)
 {
-    return queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, false);
+    return queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, allreduce != 0);
 }
 
 int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
@@ -668,6 +671,26 @@ void b200slam_graph_destroy(b200slam_ctx *ctx, b200slam_graph *g)
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
     delete g;
+}
+
+/* ---- device timing ------------------------------------------------------------------ */
+
+int b200slam_event_record(b200slam_ctx *ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= 4096) return B200SLAM_ERR_ARG;
+    if (!ctx->timing[slot]) CUDA_TRY(ctx, cudaEventCreate(&ctx->timing[slot]));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->timing[slot], ctx->stream));
+    return B200SLAM_OK;
+}
+
+int b200slam_event_elapsed_ms(b200slam_ctx *ctx, int slot_start, int slot_stop, float *ms)
+{
+    if (!ctx || !ms || slot_start < 0 || slot_start >= 4096 || slot_stop < 0 || slot_stop >= 4096 ||
+        !ctx->timing[slot_start] || !ctx->timing[slot_stop])
+        return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->timing[slot_stop]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->timing[slot_start], ctx->timing[slot_stop]));
+    return B200SLAM_OK;
 }
 
 /* ---- sharding helpers (pure host) ----------------------------------------------- */

@@ -92,6 +92,9 @@ struct b200slam_ctx {
     // one-shot host EDT: cached map
     b200slam_map *edt_map = nullptr;
 
+    // timing events (lazily created)
+    cudaEvent_t timing[4096] = {};
+
     // NCCL (dlopen'ed lazily; see comm.cu)
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;

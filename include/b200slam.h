@@ -142,7 +142,7 @@ int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const floa
  * (for device-timed loops and CUDA-graph capture); fetch with b200slam_match_fetch. */
 int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
                                  const float step[3], const int n[3], int64_t row_begin,
-                                 int64_t row_end);
+                                 int64_t row_end, int allreduce);
 int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result);
 
 /* Arbitrary pose / particle list: poses[P][3] = {x, y, theta}; ct/st optional [P]
@@ -171,6 +171,12 @@ int  b200slam_graph_begin(b200slam_ctx *ctx);
 int  b200slam_graph_end(b200slam_ctx *ctx, b200slam_graph **out);
 int  b200slam_graph_launch(b200slam_ctx *ctx, b200slam_graph *graph);
 void b200slam_graph_destroy(b200slam_ctx *ctx, b200slam_graph *graph);
+
+/* ---- device timing ------------------------------------------------------------------
+ * CUDA events on the context's stream (the only stream the kernels run on), so callers can
+ * time kernels without a CUDA binding of their own.  slot in [0, 4096). */
+int b200slam_event_record(b200slam_ctx *ctx, int slot);
+int b200slam_event_elapsed_ms(b200slam_ctx *ctx, int slot_start, int slot_stop, float *ms);
 
 /* ---- particle weights + systematic resampling (extension; not in the reference) ----
  * Uses the scores of the most recent b200slam_score_poses call (device-resident):
