@@ -12,85 +12,219 @@
 //     pass 2 (along y):  d2(x,y) = min_{|dy|<=R} dy^2 + h(x,y+dy)^2   (packed min-plus)
 // followed by a table lookup d2 -> sqrtf(d2) (IEEE sqrt, so bit-identical to the host).
 //
-// edt_fused_kernel: one warp owns a strip of 64 output columns and marches down a chunk
-// of rows.  Per row it reads three aligned 128-byte lines of int32 occupancy (the only
-// global reads), turns them into three 32-bit ballots, and every lane extracts the
-// 2R+1-bit neighbourhood of its two columns with one funnel shift each; the nearest set
-// bit on either side comes from one BREV + one FLO.  The 4*h^2 values of the lane's two
-// columns are packed as u16x2 and kept in a register window of 4R rows; pass 2 is then
-// 2R+1 VIADDMNMX.U16x2 (min(a + imm, c) on both halves, a native sm_90+/sm_100 DPX
-// instruction) per output row pair with immediates 4*dy^2.  No shared-memory staging of
-// the grid, no intermediate in global memory: algorithmic traffic is 4 B read + 4 B
-// written per cell, which is the HBM roofline the kernel is measured against.
+// edt_tma_kernel -- one CTA owns a block of 64*NW columns and a chunk of rows:
+//   * a producer warp streams the int32 occupancy through a ring of shared-memory stages
+//     with TMA (cp.async.bulk.tensor.2d, R rows x (64*NW + 64) columns per stage, box
+//     origin shifted by -(R+1) columns; out-of-bounds cells are zero-filled by the TMA
+//     unit, so the kernel has no load-side bounds checks).  mbarrier full/empty pairs are
+//     the only synchronisation in the steady state;
+//   * NW consumer warps each own a strip of 64 output columns and march down the chunk.
+//     Per row a warp turns three 32-cell words of the stage into ballots; every lane
+//     extracts the 2R+2-bit neighbourhood of its two columns with one funnel shift each,
+//     and the nearest set bit on either side comes from one BREV + one FLO.  128*h^2 of
+//     the lane's two columns is packed as u16x2 and kept in a register window of 3R rows;
+//     pass 2 is 2R VIADDMNMX.U16x2 (min(a + imm, c) on both halves, the sm_90+/sm_100 DPX
+//     instruction) per output row with immediates 128*dy^2;
+//   * 128*d2 is directly the byte offset of a bank-replicated sqrt table in shared memory
+//     (entry d2, lane's own bank: conflict-free), and the two f32 results go out as two
+//     aligned 128-byte warp stores.
+// The ALU pipe (VIADDMNMX/SHF/LOP3, one warp instruction per two cycles per SM
+// sub-partition) bounds pass 2; HBM traffic is the algorithmic 4 B read + 4 B written per
+// cell (halo re-reads hit L2).
+#include <cuda.h>
+
+#include <climits>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int EDT_WARPS = 4;                 // warps (column strips) per CTA
-constexpr int EDT_THREADS = EDT_WARPS * 32;
-constexpr int EDT_MAX_FUSED_R = 14;          // 2R+2 window bits must fit 32
-constexpr int EDT_LUT_MAX = 232;             // >= (R+1)^2 + 1 for R = 14
+constexpr int EDT_MAX_FUSED_R = 14;          // 2R+2 window bits must fit 32; sums fit u16
 
-template <int R>
-__device__ __forceinline__ uint32_t h2x4(uint32_t X)
+// ---- mbarrier / TMA primitives (inline PTX) -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
-    // X bit k = occupancy of column (c - (R+1) + k), c = this lane's output column.
-    // Fold the right-hand side onto the left so that bit (R+1-d) is set iff a cell at
-    // horizontal distance d (either side) is occupied; the highest set bit is the
-    // nearest one.  Returns (2h)^2 = 4h^2; no occupied cell in reach gives (2R+4)^2,
-    // which clamps.
-    constexpr uint32_t MASK = ((1u << (R + 1)) - 1u) << 1;
-    const uint32_t M = (X | (__brev(X) >> (29 - 2 * R))) & MASK;
-    const int t = 2 * __clz(M) + (2 * R - 60);
-    return (uint32_t)(t * t);
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
 }
 
+// 128 * h^2 for the window X: bit k = occupancy of column (c - (R+1) + k), c = this
+// lane's output column.  The right-hand side is folded onto the left so that bit (R+1-d)
+// is set iff a cell at horizontal distance d (either side) is occupied; the highest set
+// bit is the nearest one.  No occupied cell in reach gives h = R+2, which clamps.
 template <int R>
-__global__ void __launch_bounds__(EDT_THREADS)
-edt_fused_kernel(const int32_t *__restrict__ occ, long occ_pitch, float *__restrict__ out,
-                 long out_pitch, int rows, int cols, int chunk_rows, int nstrips, int t2,
-                 float max_dist)
+__device__ __forceinline__ uint32_t h2x128(uint32_t X)
 {
-    constexpr int B = 2 * R;       // rows produced per batch
-    constexpr int WN = 4 * R;      // window rows held in registers
+    constexpr uint32_t MASK = ((1u << (R + 1)) - 1u) << 1;
+    const uint32_t M = (X | (__brev(X) >> (29 - 2 * R))) & MASK;
+    const int z = __clz(M);                       // h = z - (30 - R)
+    const int u = 8 * z + 8 * (R - 30);           // 8h   (IMAD: fma pipe, the idle one)
+    const int v = 16 * z + 16 * (R - 30);         // 16h
+    return (uint32_t)(u * v);
+}
 
-    __shared__ float lut[EDT_LUT_MAX];
-    for (int d = threadIdx.x; d <= t2; d += EDT_THREADS)
-        lut[d] = d < t2 ? __fsqrt_rn((float)d) : max_dist;
+// Pass 2 for the R rows of one batch: window rows r .. r+2R feed output row r.
+// CHECK = false is the interior path (no row / column predicates).
+template <int R, bool CHECK>
+__device__ __forceinline__ void edt_emit_rows(const uint32_t (&win)[3 * R], const unsigned char *lut,
+                                              uint32_t lane4, uint32_t clampv, unsigned char *pb,
+                                              uint32_t pitch_bytes, int rows_left, bool s0, bool s1)
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        uint32_t a0 = win[r + R];
+        uint32_t a1 = 0xffffffffu;
+#pragma unroll
+        for (int d = 1; d <= R; ++d) {
+            const uint32_t k = (uint32_t)(128 * d * d) * 0x00010001u;
+            a0 = __viaddmin_u16x2(win[r + R - d], k, a0);
+            a1 = __viaddmin_u16x2(win[r + R + d], k, a1);
+        }
+        const uint32_t a = __vimin3_u16x2(a0, a1, clampv);
+        const float f0 = *reinterpret_cast<const float *>(lut + ((a & 0xffffu) | lane4));
+        const float f1 = *reinterpret_cast<const float *>(lut + (__umulhi(a, 65536u) + lane4));
+        float *o = reinterpret_cast<float *>(pb + (uint64_t)pitch_bytes * (uint32_t)r);
+        if (CHECK) {
+            if (r < rows_left) {
+                if (s0) o[0] = f0;
+                if (s1) o[32] = f1;
+            }
+        } else {
+            o[0] = f0;
+            o[32] = f1;
+        }
+    }
+}
+
+template <int R, int NW>
+struct EdtCfg {
+    // The TMA box origin must be 16-byte aligned in global memory, so the stage starts SH
+    // columns left of the CTA's first output column (SH = R+1 rounded up to 4) and the
+    // ballot loads skip the DELTA = SH - (R+1) surplus columns.
+    static constexpr int SH = (R + 1 + 3) & ~3;
+    static constexpr int DELTA = SH - (R + 1);
+    static constexpr int BOX_COLS = 64 * NW + 32 + 4;        // one box per stage (<= 256)
+    static constexpr int STAGE_BYTES = ((R * BOX_COLS * 4) + 127) & ~127;
+    static constexpr uint32_t TX_BYTES = R * BOX_COLS * 4;
+    static constexpr int THREADS = 32 * (NW + 1);
+    static_assert(BOX_COLS <= 256, "TMA box dimension limit");
+};
+
+// Dynamic shared memory: [stage ring][sqrt table][mbarriers]
+template <int R, int NW, int NST>
+__global__ void __launch_bounds__(EdtCfg<R, NW>::THREADS)
+edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out, uint32_t pitch_bytes,
+               int rows, int cols, int chunk_batches, int t2, float max_dist)
+{
+    using C = EdtCfg<R, NW>;
+    constexpr int B = R;                          // rows per stage / batch
+    constexpr int WN = 3 * R;                     // register window rows
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *lut = smem_raw + (size_t)NST * C::STAGE_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(lut + (size_t)(t2 + 1) * 128);
+    uint64_t *empty = full + NST;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * (64 * NW);
+    const int y0 = blockIdx.y * chunk_batches * B;
+    const int out_rows = min(chunk_batches * B, rows - y0);
+    const int nb_out = (out_rows + B - 1) / B;
+    const int nbl = nb_out + 2;                   // stages to stream: halo + chunk + halo
+    const int nactive = min(NW, (cols - x0 + 63) / 64);
+
+    for (int d = tid; d <= t2; d += C::THREADS) {
+        const float v = d < t2 ? __fsqrt_rn((float)d) : max_dist;
+        float4 *p = reinterpret_cast<float4 *>(lut + (size_t)d * 128);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) p[q] = make_float4(v, v, v, v);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nactive);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int strip = blockIdx.x * EDT_WARPS + (threadIdx.x >> 5);
-    if (strip >= nstrips) return;
-    const int y0 = blockIdx.y * chunk_rows;
-    const int y1 = min(y0 + chunk_rows, rows);
+    if (warp == NW) {
+        // ---- producer: one lane streams the chunk through the stage ring --------------
+        if (lane == 0) {
+            for (int t = 0; t < nbl; ++t) {
+                const int s = t % NST;
+                if (t >= NST) mbar_wait(&empty[s], ((t / NST) - 1) & 1);
+                mbar_expect_tx(&full[s], C::TX_BYTES);
+                tma_load_2d(smem_raw + (size_t)s * C::STAGE_BYTES, &tmap, &full[s], x0 - C::SH, y0 - R + t * B);
+            }
+        }
+        return;
+    }
+    if (warp >= nactive) return;
 
-    // Ballot words start at column b (a multiple of 32, so every load instruction reads
-    // one aligned 128-byte line); this lane outputs columns b+lane+R+1 and +32.
-    const int b = strip * 64 - 32;
-    const int cl0 = b + lane, cl1 = cl0 + 32, cl2 = cl0 + 64;
-    const bool v0 = cl0 >= 0 && cl0 < cols, v1 = cl1 < cols, v2 = cl2 < cols;
-    const int co0 = cl0 + R + 1, co1 = co0 + 32;
-    const bool s0 = co0 >= 0 && co0 < cols, s1 = co1 < cols;
-    const uint32_t clampv = (uint32_t)(4 * t2) * 0x00010001u;
+    // ---- consumers: warp j owns output columns [x0 + 64j, x0 + 64j + 64) ---------------
+    // Stage column q is grid column x0 - SH + q.  Strip j ballots the three 32-cell words
+    // starting at stage column 64j + DELTA, i.e. grid column x0 + 64j - (R+1): bit k of the
+    // funnel-shifted window of output column c is then grid column c - (R+1) + k.  (The top
+    // lanes of the third word may read past the row; those bits are never used.)
+    const int woff = 64 * warp + C::DELTA + lane;
+    const int c0 = x0 + 64 * warp + lane, c1 = c0 + 32;
+    const bool s0 = c0 < cols, s1 = c1 < cols;
+    const bool interior = x0 + 64 * warp + 64 <= cols;
+    unsigned char *obase = reinterpret_cast<unsigned char *>(out + c0);
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const uint32_t clampv = (uint32_t)(128 * t2) * 0x00010001u;
 
     uint32_t win[WN];
 #pragma unroll
     for (int i = 0; i < WN; ++i) win[i] = 0;
 
-    for (int yb = y0 - B; yb < y1; yb += B) {
-        // ---- global loads: rows yb+R .. yb+R+B-1, three aligned lines each ----------
+    for (int t = 0; t < nbl; ++t) {
+        const int s = t % NST;
+        mbar_wait(&full[s], (t / NST) & 1);
+        const int *st = reinterpret_cast<const int *>(smem_raw + (size_t)s * C::STAGE_BYTES) + woff;
+        // ---- pass 1: horizontal nearest-occupied distance from the ballots ------------
         int ld[B][3];
 #pragma unroll
         for (int r = 0; r < B; ++r) {
-            const int row = yb + R + r;
-            const bool rowok = row >= 0 && row < rows;
-            const int32_t *p = occ + (long)row * occ_pitch;
-            ld[r][0] = (rowok && v0) ? __ldg(p + cl0) : 0;
-            ld[r][1] = (rowok && v1) ? __ldg(p + cl1) : 0;
-            ld[r][2] = (rowok && v2 && lane < 2 * R + 2) ? __ldg(p + cl2) : 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ld[r][i] = st[r * C::BOX_COLS + 32 * i];
         }
-        // ---- pass 1: horizontal nearest-occupied distance from the ballots ----------
 #pragma unroll
         for (int r = 0; r < B; ++r) {
             const uint32_t w0 = __ballot_sync(0xffffffffu, ld[r][0] != 0);
@@ -98,34 +232,22 @@ edt_fused_kernel(const int32_t *__restrict__ occ, long occ_pitch, float *__restr
             const uint32_t w2 = __ballot_sync(0xffffffffu, ld[r][2] != 0);
             const uint32_t X0 = __funnelshift_r(w0, w1, lane);
             const uint32_t X1 = __funnelshift_r(w1, w2, lane);
-            win[B + r] = h2x4<R>(X0) | (h2x4<R>(X1) << 16);
+            win[2 * R + r] = h2x128<R>(X0) + (h2x128<R>(X1) << 16);
         }
-        // ---- pass 2: vertical min-plus with the parabola, two columns per op --------
-        if (yb >= y0) {
-#pragma unroll
-            for (int r = 0; r < B; ++r) {
-                const int y = yb + r;
-                if (y < y1) {
-                    uint32_t a0 = win[r + R];
-                    uint32_t a1 = 0xffffffffu;
-#pragma unroll
-                    for (int d = 1; d <= R; ++d) {
-                        const uint32_t k = (uint32_t)(4 * d * d) * 0x00010001u;
-                        a0 = __viaddmin_u16x2(win[r + R - d], k, a0);
-                        a1 = __viaddmin_u16x2(win[r + R + d], k, a1);
-                    }
-                    const uint32_t a = __vminu2(__vminu2(a0, a1), clampv);
-                    const float f0 = *(const float *)((const char *)lut + (a & 0xffffu));
-                    const float f1 = *(const float *)((const char *)lut + (a >> 16));
-                    float *o = out + (long)y * out_pitch;
-                    if (s0) o[co0] = f0;
-                    if (s1) o[co1] = f1;
-                }
-            }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        // ---- pass 2: vertical min-plus with the parabola, two columns per op ----------
+        if (t >= 2) {
+            const int yb = y0 + (t - 2) * B;
+            unsigned char *pb = obase + (size_t)(uint32_t)yb * pitch_bytes;
+            if (interior && yb + B <= rows)
+                edt_emit_rows<R, false>(win, lut, lane4, clampv, pb, pitch_bytes, 0, true, true);
+            else
+                edt_emit_rows<R, true>(win, lut, lane4, clampv, pb, pitch_bytes, rows - yb, s0, s1);
         }
-        // ---- slide the window down by B rows ---------------------------------------
+        // ---- slide the window down by B rows ------------------------------------------
 #pragma unroll
-        for (int i = 0; i < B; ++i) win[i] = win[i + B];
+        for (int i = 0; i < 2 * R; ++i) win[i] = win[i + B];
     }
 }
 
@@ -159,27 +281,93 @@ __global__ void edt_generic_rows(const uint16_t *__restrict__ g, float *__restri
     out[(long)r * out_pitch + c] = best < t2 ? __fsqrt_rn((float)best) : max_dist;
 }
 
-template <int R>
-int launch_fused(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
-                 int field_pitch, int rows, int cols, int t2, float max_dist)
+// ---- host side ----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
 {
-    constexpr int B = 2 * R;
-    const int nstrips = (cols + 30 - R) / 64 + 1;
-    const int gx = (nstrips + EDT_WARPS - 1) / EDT_WARPS;
-    // Rows per chunk: a multiple of the batch height; tall chunks amortise the 2R halo
-    // rows, short ones give small grids enough warps (aim for >= 16 per SM).
-    const int want_warps = ctx->sm_count * 16;
-    int chunks = (want_warps + nstrips - 1) / nstrips;
-    int chunk_rows = (rows + chunks - 1) / chunks;
-    chunk_rows = ((chunk_rows + B - 1) / B) * B;
-    if (chunk_rows < 2 * B) chunk_rows = 2 * B;
-    if (chunk_rows > 8 * B) chunk_rows = 8 * B;
-    const int gy = (rows + chunk_rows - 1) / chunk_rows;
-    dim3 grid(gx, gy);
-    edt_fused_kernel<R><<<grid, EDT_THREADS, 0, ctx->stream>>>(
-        d_occ, occ_pitch, d_field, field_pitch, rows, cols, chunk_rows, nstrips, t2, max_dist);
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int R, int NW, int NST>
+size_t edt_smem_bytes(int t2)
+{
+    using C = EdtCfg<R, NW>;
+    return (size_t)NST * C::STAGE_BYTES + (size_t)(t2 + 1) * 128 + 2 * NST * sizeof(uint64_t);
+}
+
+template <int R, int NW, int NST>
+int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field, int field_pitch,
+               int rows, int cols, int t2, float max_dist)
+{
+    using C = EdtCfg<R, NW>;
+    auto kern = edt_tma_kernel<R, NW, NST>;
+    const size_t smem = edt_smem_bytes<R, NW, NST>(t2);
+    static int occupancy = 0;        // resident CTAs per SM (per instantiation)
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+        occupancy = 0;
+    }
+    if (occupancy == 0) {
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kern, C::THREADS, smem));
+        if (occupancy < 1) occupancy = 1;
+    }
+
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)occ_pitch * sizeof(int32_t)};
+    const cuuint32_t box[2] = {(cuuint32_t)C::BOX_COLS, (cuuint32_t)R};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<int32_t *>(d_occ), gdim, gstr, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS)
+        return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "cuTensorMapEncodeTiled -> %d (pitch %d)", (int)cr,
+                                  occ_pitch);
+
+    // Rows per CTA: a chunk of `cb` batches of R rows costs cb + ~2.5 batch times (two halo
+    // stages that only run pass 1, plus the pipeline fill); pick the cb that minimises
+    // waves x cost for the number of CTAs the GPU holds at once.
+    const int gx = (cols + 64 * NW - 1) / (64 * NW);
+    const int nbatch = (rows + R - 1) / R;
+    const long resident = (long)ctx->sm_count * occupancy;
+    int best_cb = 1;
+    double best_cost = 1e300;
+    for (int cb = 1; cb <= 96 && cb <= nbatch; ++cb) {
+        const long gy = (nbatch + cb - 1) / cb;
+        const long waves = (gx * gy + resident - 1) / resident;
+        const double cost = (double)waves * (cb + 2.5);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_cb = cb; }
+    }
+    const int gy = (nbatch + best_cb - 1) / best_cb;
+    kern<<<dim3(gx, gy), C::THREADS, smem, ctx->stream>>>(tmap, d_field, (uint32_t)field_pitch * 4u, rows, cols, best_cb, t2,
+                                                         max_dist);
     LAUNCH_CHECK(ctx);
     return B200SLAM_OK;
+}
+
+template <int R>
+int launch_fused(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field, int field_pitch,
+                 int rows, int cols, int t2, float max_dist)
+{
+    return launch_tma<R, 3, 3>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
 }
 
 }  // namespace
@@ -197,13 +385,18 @@ int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     int t2 = R * R;
     while ((float)t2 < thr) t2++;       // smallest integer d2 that is NOT < max_dist^2
 
-    switch (R) {
+    // The TMA path needs a 16-byte aligned base and pitch (always true for b200slam_map).
+    const bool tma_ok = (occ_pitch % 4 == 0) && ((uintptr_t)d_occ % 16 == 0);
+    if (tma_ok) {
+        switch (R) {
 #define CASE(RR) case RR: return launch_fused<RR>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
-        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
-        CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+            CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
 #undef CASE
-        default: break;
+            default: break;
+        }
     }
+    static_assert(EDT_MAX_FUSED_R == 14, "switch above covers 1..14");
     // R == 0 (max_dist <= 1) or R > 14: generic two-pass kernels.
     const size_t need = (size_t)rows * cols;
     if (need > ctx->edt_scratch_cap) {

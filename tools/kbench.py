@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""tools/kbench.py -- per-kernel timings on the GPU box (development aid, not the bench contract).
+
+    python tools/kbench.py edt      # EDT on 400^2 / 2048^2 / 8192^2, rooms and bernoulli grids
+    python tools/kbench.py lattice  # lattice matcher at the BASELINE.json shapes
+    python tools/kbench.py poses    # pose-list scorer + weights/resample (config 2)
+
+Times with CUDA events on the library's stream; inputs rotate through a ring larger than L2.
+"""
+from __future__ import annotations
+
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "hardware-acceleration-of-lidar-slam_b200"
+PEAK = 6542.7
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def time_loop(ctx, fn, iters, warm=3):
+    for i in range(warm):
+        fn(i)
+    ctx.sync()
+    ctx.event_record(0)
+    for i in range(iters):
+        fn(i)
+    ctx.event_record(1)
+    ctx.sync()
+    return ctx.event_elapsed_ms(0, 1) / iters
+
+
+def bench_edt(mod, synth, ctx, sizes):
+    for rows, cols in sizes:
+        cells = rows * cols
+        ring = max(2, min(12, (2 * 126 * 2 ** 20) // (cells * 8) + 1))
+        for kind in ("rooms", "bern0.01", "bern0.05", "empty"):
+            maps = []
+            for i in range(ring):
+                if kind == "rooms":
+                    occ = synth.grid_rooms(rows, cols, synth.SEED_GRID + i)
+                elif kind == "empty":
+                    occ = np.zeros((rows, cols), np.int32)
+                else:
+                    occ = synth.grid_bernoulli(rows, cols, float(kind[4:]), synth.SEED_GRID + i)
+                m = ctx.new_map(rows, cols)
+                m.upload_occupancy(occ)
+                maps.append(m)
+                if kind != "rooms" and i >= 1 and cells >= 2 ** 26:
+                    break
+            n = len(maps)
+            iters = 50 if cells <= 2 ** 22 else 20
+            ms = time_loop(ctx, lambda i: maps[i % n].edt(10.0), iters)
+            gbs = cells * 8 / (ms * 1e-3) / 1e9
+            print(f"edt {rows}x{cols} {kind:9s} ring={n:2d}  {ms * 1e3:9.2f} us  {cells / ms / 1e3:10.1f} Mcells/s  "
+                  f"{gbs:8.1f} GB/s  frac={gbs / PEAK:.3f}", flush=True)
+            for m in maps:
+                m.close()
+
+
+def bench_lattice(mod, synth, ctx, names):
+    for name in names:
+        w = synth.make_workload(name)
+        rows, cols = w["occ"].shape
+        m = ctx.new_map(rows, cols)
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+        ctx.scan_upload(w["scan_x"], w["scan_y"])
+        n = w["n"]
+        evals = n[0] * n[1] * n[2] * len(w["scan_x"])
+        ms = time_loop(ctx, lambda i: ctx.score_lattice_async(m, w["pose0"], w["step"], n), 20 if evals > 1e9 else 100)
+        r = ctx.match_fetch()
+        print(f"lattice {name} {n} x {len(w['scan_x'])} beams: {ms * 1e3:9.2f} us  {evals / ms / 1e9:8.2f} Gevals/s "
+              f"best={r.best_index} score={r.best_score:.3f}", flush=True)
+        m.close()
+
+
+def bench_poses(mod, synth, ctx):
+    w = synth.make_workload("config1")
+    rows, cols = w["occ"].shape
+    m = ctx.new_map(rows, cols)
+    m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+    x, y = synth.scan_fixed_count(w["occ"], float(w["pixel"]), w["top_left"], w["true_pose"], 720)
+    ctx.scan_upload(x, y)
+    P = 100000
+    poses = synth.particles_gaussian(P, w["true_pose"])
+    import time
+    for _ in range(3):
+        ctx.score_poses(m, poses, want_hits=False)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ctx.score_poses(m, poses, want_hits=False)
+    t1 = time.perf_counter()
+    for _ in range(10):
+        ctx.weights_resample(P, 0.05, 0x80000000, want_weights=True)
+    t2 = time.perf_counter()
+    print(f"poses 100k x 720 (host call incl. H2D/D2H): {(t1 - t0) / 10 * 1e3:.3f} ms  "
+          f"{P * 720 / ((t1 - t0) / 10) / 1e9:.2f} Gevals/s; weights+resample {(t2 - t1) / 10 * 1e3:.3f} ms", flush=True)
+    m.close()
+
+
+def main():
+    what = sys.argv[1:] or ["edt", "lattice", "poses"]
+    mod = importlib.import_module(PKG)
+    synth = importlib.import_module(PKG + ".synth")
+    with mod.Context(0) as ctx:
+        print(ctx.device_info(), flush=True)
+        if "edt" in what:
+            bench_edt(mod, synth, ctx, [(400, 400), (2048, 2048), (8192, 8192)])
+        if "edtbig" in what:
+            bench_edt(mod, synth, ctx, [(8192, 8192)])
+        if "lattice" in what:
+            bench_lattice(mod, synth, ctx, ["tiny", "config1", "config3"])
+        if "poses" in what:
+            bench_poses(mod, synth, ctx)
+
+
+if __name__ == "__main__":
+    main()
