@@ -13,21 +13,22 @@
 // followed by a table lookup d2 -> sqrtf(d2) (IEEE sqrt, so bit-identical to the host).
 //
 // edt_tma_kernel -- one CTA owns a block of 64*NW columns and a chunk of rows:
-//   * a producer warp streams the int32 occupancy through a ring of shared-memory stages
-//     with TMA (cp.async.bulk.tensor.2d, R rows x (64*NW + 64) columns per stage, box
-//     origin shifted by -(R+1) columns; out-of-bounds cells are zero-filled by the TMA
-//     unit, so the kernel has no load-side bounds checks).  mbarrier full/empty pairs are
-//     the only synchronisation in the steady state;
+//   * the int32 occupancy streams through a ring of shared-memory stages with TMA
+//     (cp.async.bulk.tensor.2d, one box of R rows x (64*NW + 36) columns per stage, box
+//     origin 16-byte aligned left of the strip; out-of-bounds cells are zero-filled by the
+//     TMA unit, so the kernel has no load-side bounds checks).  There is no producer
+//     warp: the last of the NW warps to finish reading a stage (shared-memory arrival
+//     counter) re-arms its mbarrier and issues the refill, so nothing ever spins;
 //   * NW consumer warps each own a strip of 64 output columns and march down the chunk.
 //     Per row a warp turns three 32-cell words of the stage into ballots; every lane
 //     extracts the 2R+2-bit neighbourhood of its two columns with one funnel shift each,
-//     and the nearest set bit on either side comes from one BREV + one FLO.  128*h^2 of
+//     and the nearest set bit on either side comes from one BREV + one FLO.  64*h^2 of
 //     the lane's two columns is packed as u16x2 and kept in a register window of 3R rows;
 //     pass 2 is 2R VIADDMNMX.U16x2 (min(a + imm, c) on both halves, the sm_90+/sm_100 DPX
-//     instruction) per output row with immediates 128*dy^2;
-//   * 128*d2 is directly the byte offset of a bank-replicated sqrt table in shared memory
-//     (entry d2, lane's own bank: conflict-free), and the two f32 results go out as two
-//     aligned 128-byte warp stores.
+//     instruction) per output row with immediates 64*dy^2;
+//   * 64*d2 is directly the byte offset of a 16-bank-replicated sqrt table in shared
+//     memory (entry d2, bank lane%16: at most 2-way conflicts), and the two f32 results go
+//     out as two aligned 128-byte warp stores.
 // The ALU pipe (VIADDMNMX/SHF/LOP3, one warp instruction per two cycles per SM
 // sub-partition) bounds pass 2; HBM traffic is the algorithmic 4 B read + 4 B written per
 // cell (halo re-reads hit L2).
@@ -81,19 +82,20 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
-// 128 * h^2 for the window X: bit k = occupancy of column (c - (R+1) + k), c = this
+constexpr int EDT_SCALE = 64;                // packed u16 values are EDT_SCALE * d2 = LUT byte offset
+
+// 64 * h^2 for the window X: bit k = occupancy of column (c - (R+1) + k), c = this
 // lane's output column.  The right-hand side is folded onto the left so that bit (R+1-d)
 // is set iff a cell at horizontal distance d (either side) is occupied; the highest set
 // bit is the nearest one.  No occupied cell in reach gives h = R+2, which clamps.
 template <int R>
-__device__ __forceinline__ uint32_t h2x128(uint32_t X)
+__device__ __forceinline__ uint32_t h2scaled(uint32_t X)
 {
     constexpr uint32_t MASK = ((1u << (R + 1)) - 1u) << 1;
     const uint32_t M = (X | (__brev(X) >> (29 - 2 * R))) & MASK;
     const int z = __clz(M);                       // h = z - (30 - R)
-    const int u = 8 * z + 8 * (R - 30);           // 8h   (IMAD: fma pipe, the idle one)
-    const int v = 16 * z + 16 * (R - 30);         // 16h
-    return (uint32_t)(u * v);
+    const int u = 8 * z + 8 * (R - 30);           // 8h
+    return (uint32_t)(u * u);                     // 64 h^2
 }
 
 // Pass 2 for the R rows of one batch: window rows r .. r+2R feed output row r.
@@ -109,7 +111,7 @@ __device__ __forceinline__ void edt_emit_rows(const uint32_t (&win)[3 * R], cons
         uint32_t a1 = 0xffffffffu;
 #pragma unroll
         for (int d = 1; d <= R; ++d) {
-            const uint32_t k = (uint32_t)(128 * d * d) * 0x00010001u;
+            const uint32_t k = (uint32_t)(EDT_SCALE * d * d) * 0x00010001u;
             a0 = __viaddmin_u16x2(win[r + R - d], k, a0);
             a1 = __viaddmin_u16x2(win[r + R + d], k, a1);
         }
@@ -139,11 +141,11 @@ struct EdtCfg {
     static constexpr int BOX_COLS = 64 * NW + 32 + 4;        // one box per stage (<= 256)
     static constexpr int STAGE_BYTES = ((R * BOX_COLS * 4) + 127) & ~127;
     static constexpr uint32_t TX_BYTES = R * BOX_COLS * 4;
-    static constexpr int THREADS = 32 * (NW + 1);
+    static constexpr int THREADS = 32 * NW;
     static_assert(BOX_COLS <= 256, "TMA box dimension limit");
 };
 
-// Dynamic shared memory: [stage ring][sqrt table][mbarriers]
+// Dynamic shared memory: [stage ring][sqrt table][mbarriers][arrival counters]
 template <int R, int NW, int NST>
 __global__ void __launch_bounds__(EdtCfg<R, NW>::THREADS)
 edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out, uint32_t pitch_bytes,
@@ -155,8 +157,8 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *lut = smem_raw + (size_t)NST * C::STAGE_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(lut + (size_t)(t2 + 1) * 128);
-    uint64_t *empty = full + NST;
+    uint64_t *full = reinterpret_cast<uint64_t *>(lut + (size_t)(t2 + 1) * EDT_SCALE);
+    int *arrivals = reinterpret_cast<int *>(full + NST);      // per stage, monotonically increasing
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -169,32 +171,24 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
 
     for (int d = tid; d <= t2; d += C::THREADS) {
         const float v = d < t2 ? __fsqrt_rn((float)d) : max_dist;
-        float4 *p = reinterpret_cast<float4 *>(lut + (size_t)d * 128);
+        float4 *p = reinterpret_cast<float4 *>(lut + (size_t)d * EDT_SCALE);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) p[q] = make_float4(v, v, v, v);
+        for (int q = 0; q < EDT_SCALE / 16; ++q) p[q] = make_float4(v, v, v, v);
     }
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], nactive);
+            arrivals[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // prologue: fill the ring
+        for (int t = 0; t < NST && t < nbl; ++t) {
+            mbar_expect_tx(&full[t], C::TX_BYTES);
+            tma_load_2d(smem_raw + (size_t)t * C::STAGE_BYTES, &tmap, &full[t], x0 - C::SH, y0 - R + t * B);
+        }
     }
     __syncthreads();
-
-    if (warp == NW) {
-        // ---- producer: one lane streams the chunk through the stage ring --------------
-        if (lane == 0) {
-            for (int t = 0; t < nbl; ++t) {
-                const int s = t % NST;
-                if (t >= NST) mbar_wait(&empty[s], ((t / NST) - 1) & 1);
-                mbar_expect_tx(&full[s], C::TX_BYTES);
-                tma_load_2d(smem_raw + (size_t)s * C::STAGE_BYTES, &tmap, &full[s], x0 - C::SH, y0 - R + t * B);
-            }
-        }
-        return;
-    }
     if (warp >= nactive) return;
 
     // ---- consumers: warp j owns output columns [x0 + 64j, x0 + 64j + 64) ---------------
@@ -207,8 +201,8 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
     const bool s0 = c0 < cols, s1 = c1 < cols;
     const bool interior = x0 + 64 * warp + 64 <= cols;
     unsigned char *obase = reinterpret_cast<unsigned char *>(out + c0);
-    const uint32_t lane4 = (uint32_t)lane * 4u;
-    const uint32_t clampv = (uint32_t)(128 * t2) * 0x00010001u;
+    const uint32_t lane4 = (uint32_t)(lane & 15) * 4u;
+    const uint32_t clampv = (uint32_t)(EDT_SCALE * t2) * 0x00010001u;
 
     uint32_t win[WN];
 #pragma unroll
@@ -232,10 +226,19 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
             const uint32_t w2 = __ballot_sync(0xffffffffu, ld[r][2] != 0);
             const uint32_t X0 = __funnelshift_r(w0, w1, lane);
             const uint32_t X1 = __funnelshift_r(w1, w2, lane);
-            win[2 * R + r] = h2x128<R>(X0) + (h2x128<R>(X1) << 16);
+            win[2 * R + r] = h2scaled<R>(X0) + (h2scaled<R>(X1) << 16);
         }
+        // ---- stage consumed: the last warp to get here refills it ----------------------
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lane == 0 && t + NST < nbl) {
+            const int old = atomicAdd(&arrivals[s], 1);
+            if (old + 1 == nactive * (t / NST + 1)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full[s], C::TX_BYTES);
+                tma_load_2d(smem_raw + (size_t)s * C::STAGE_BYTES, &tmap, &full[s], x0 - C::SH,
+                            y0 - R + (t + NST) * B);
+            }
+        }
         // ---- pass 2: vertical min-plus with the parabola, two columns per op ----------
         if (t >= 2) {
             const int yb = y0 + (t - 2) * B;
@@ -306,7 +309,7 @@ template <int R, int NW, int NST>
 size_t edt_smem_bytes(int t2)
 {
     using C = EdtCfg<R, NW>;
-    return (size_t)NST * C::STAGE_BYTES + (size_t)(t2 + 1) * 128 + 2 * NST * sizeof(uint64_t);
+    return (size_t)NST * C::STAGE_BYTES + (size_t)(t2 + 1) * EDT_SCALE + NST * (sizeof(uint64_t) + sizeof(int));
 }
 
 template <int R, int NW, int NST>
