@@ -57,9 +57,15 @@ int b200slam_create(b200slam_ctx **out, int device)
     CREATE_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaMalloc(&ctx->d_match, sizeof(MatchDev)));
-    CREATE_TRY(cudaMemset(ctx->d_match, 0xff, sizeof(MatchDev)));
     CREATE_TRY(cudaHostAlloc(&ctx->h_match, sizeof(MatchDev), cudaHostAllocDefault));
-    CREATE_TRY(cudaMalloc(&ctx->d_keys, sizeof(unsigned long long) * 3 * 64));
+    {
+        MatchDev init;
+        init.work_key = ~0ull; init.tickets = 0; init.pad = 0; init.key = ~0ull;
+        init.best_hits = 0; init.last_hits = 0;
+        CREATE_TRY(cudaMemcpy(ctx->d_match, &init, sizeof init, cudaMemcpyHostToDevice));
+    }
+    CREATE_TRY(cudaMalloc(&ctx->d_keys, sizeof(unsigned long long) * 256));
+    CREATE_TRY(cudaHostAlloc(&ctx->h_keys, sizeof(unsigned long long) * 128, cudaHostAllocDefault));
     CREATE_TRY(cudaMalloc(&ctx->d_wsum, sizeof(unsigned long long) * 4));
     CREATE_TRY(cudaHostAlloc(&ctx->h_wsum, sizeof(unsigned long long) * 2 * 64, cudaHostAllocDefault));
 #undef CREATE_TRY
@@ -77,7 +83,7 @@ void b200slam_destroy(b200slam_ctx *ctx)
     cudaFree(ctx->d_scan_x); cudaFree(ctx->d_scan_y);
     cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
     cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match);
-    cudaFree(ctx->d_keys); cudaFree(ctx->d_hit_values);
+    cudaFree(ctx->d_keys); cudaFreeHost(ctx->h_keys); cudaFree(ctx->d_hit_values);
     cudaFree(ctx->d_scores);
     cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
     cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
@@ -292,19 +298,22 @@ bool is_capturing(b200slam_ctx *ctx)
     return st != cudaStreamCaptureStatusNone;
 }
 
-// Fills one slot of the pinned axis tables [ct | st | sxt | syt] and queues its upload.
-// The staging area is a ring of LAT_SLOTS slots, each guarded by an event recorded after
-// the last kernel that reads it, so back-to-back matches never wait on the host.
+// Computes the lattice axis tables [ct | st | sxt | syt] with the host libm and the
+// reference's float operations (main.c:424-437).  Small lattices (<= 960 floats) hand them
+// to the kernel as launch parameters: nothing is copied on the stream.  Larger ones go
+// through a ring of LAT_SLOTS pinned slots, each guarded by an event recorded after the
+// kernel that reads its device copy, so back-to-back matches never wait on the host.
 int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[3], const float step[3],
                   const int n[3], LatticeLaunch *L)
 {
     const int nth = n[0], ntx = n[1], nty = n[2];
     const size_t need = (size_t)2 * nth + ntx + nty;
     const bool capturing = is_capturing(ctx);
+    const bool by_param = need <= LATTICE_PARAM_FLOATS;
     if (need > ctx->lat_cap) {
-        if (capturing)
+        if (capturing && !by_param)
             return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "lattice larger than warmed-up scratch during graph capture");
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!capturing) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
         ctx->h_lat = ctx->d_lat = nullptr;
         ctx->lat_cap = 0;
@@ -316,10 +325,13 @@ int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[
                 CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->lat_event[i], cudaEventDisableTiming));
         ctx->lat_cap = cap;
     }
-    const int slot = ctx->lat_next;
-    ctx->lat_next = (slot + 1) % LAT_SLOTS;
-    ctx->lat_cur = slot;
-    if (!capturing) CUDA_TRY(ctx, cudaEventSynchronize(ctx->lat_event[slot]));
+    int slot = 0;
+    if (!by_param) {
+        slot = ctx->lat_next;
+        ctx->lat_next = (slot + 1) % LAT_SLOTS;
+        ctx->lat_cur = slot;
+        if (!capturing) CUDA_TRY(ctx, cudaEventSynchronize(ctx->lat_event[slot]));
+    }
     const float ipixel = 1 / map->pixel_size;                             // main.c:383
     float *ct = ctx->h_lat + (size_t)slot * ctx->lat_cap, *st = ct + nth, *sxt = st + nth, *syt = sxt + ntx;
     for (int i = 0; i < nth; ++i) {
@@ -337,11 +349,15 @@ int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[
         volatile float d = ty - map->top_left_y;
         syt[i] = d * ipixel;                                              // main.c:437
     }
-    float *dst = ctx->d_lat + (size_t)slot * ctx->lat_cap;
-    CUDA_TRY(ctx, cudaMemcpyAsync(dst, ct, sizeof(float) * need, cudaMemcpyHostToDevice, ctx->stream));
     L->map = map;
     L->nth = nth; L->ntx = ntx; L->nty = nty;
-    L->d_ct = dst; L->d_st = L->d_ct + nth; L->d_sxt = L->d_st + nth; L->d_syt = L->d_sxt + ntx;
+    L->h_tables = ct;
+    L->d_tables = nullptr;
+    if (!by_param) {
+        float *dst = ctx->d_lat + (size_t)slot * ctx->lat_cap;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, ct, sizeof(float) * need, cudaMemcpyHostToDevice, ctx->stream));
+        L->d_tables = dst;
+    }
     return B200SLAM_OK;
 }
 
@@ -389,15 +405,15 @@ int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], co
     if (rc) return rc;
     bool gathered = false;
     if (allreduce && ctx->nccl_comm && ctx->nranks > 1) {
-        rc = comm_allgather_u64(ctx, &ctx->d_match->key, ctx->d_keys, 1);
+        // {key, best_hits | last_hits} of every rank; b200slam_match_fetch merges them
+        rc = comm_allgather_u64(ctx, &ctx->d_match->key, ctx->d_keys, 2);
         if (rc) return rc;
         gathered = true;
     }
-    rc = trace_launch(ctx, L, gathered);
-    if (rc) return rc;
-    if (!is_capturing(ctx)) CUDA_TRY(ctx, cudaEventRecord(ctx->lat_event[ctx->lat_cur], ctx->stream));
+    if (L.d_tables && !is_capturing(ctx)) CUDA_TRY(ctx, cudaEventRecord(ctx->lat_event[ctx->lat_cur], ctx->stream));
     ctx->last.valid = true;
     ctx->last.is_poses = false;
+    ctx->last.gathered = gathered;
     for (int i = 0; i < 3; ++i) {
         ctx->last.n[i] = n[i];
         ctx->last.pose0[i] = pose0[i];
@@ -414,10 +430,26 @@ int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result)
 {
     if (!ctx || !result) return B200SLAM_ERR_ARG;
     if (!ctx->last.valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no match queued");
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_match, ctx->d_match, sizeof(MatchDev), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    const MatchDev &m = *ctx->h_match;
+    MatchDev m;
+    if (ctx->last.gathered) {
+        // merge the all-gathered per-rank results: lowest key wins; the last candidate of the
+        // whole lattice belongs to the last rank that scored anything
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_keys, ctx->d_keys, 16 * (size_t)ctx->nranks, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        m.key = ~0ull; m.best_hits = 0; m.last_hits = 0;
+        for (int r = 0; r < ctx->nranks; ++r) {
+            const unsigned long long k = ctx->h_keys[2 * r], h = ctx->h_keys[2 * r + 1];
+            if (k == ~0ull) continue;
+            if (k < m.key) { m.key = k; m.best_hits = (int)(h & 0xffffffffull); }
+            m.last_hits = (int)(h >> 32);
+        }
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_match, ctx->d_match, sizeof(MatchDev), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        m = *ctx->h_match;
+    }
     memset(result, 0, sizeof(*result));
     if (m.key == ~0ull) {               // empty shard
         result->best_index = -1;
@@ -558,6 +590,7 @@ int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *pose
     if (rc) return rc;
     ctx->last.valid = true;
     ctx->last.is_poses = true;
+    ctx->last.gathered = false;
     ctx->last_P = P;
     ctx->last_index_base = index_base;
     ctx->last_poses_host = poses;
@@ -566,21 +599,8 @@ int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *pose
     if (hits && P > 0)
         CUDA_TRY(ctx, cudaMemcpyAsync(hits, ctx->d_hits, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
     if (result) {
-        // best_hits of the winner comes from the per-pose hit counts
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_match, ctx->d_match, sizeof(MatchDev), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        rc = b200slam_match_fetch(ctx, result);
+        rc = b200slam_match_fetch(ctx, result);       // syncs; the kernel's last CTA published the hits
         if (rc) return rc;
-        result->best_hits = 0;
-        result->last_hits = 0;
-        if (result->best_index >= 0) {
-            int32_t h2[1];
-            const int64_t local = result->best_index - index_base;
-            CUDA_TRY(ctx, cudaMemcpy(h2, ctx->d_hits + local, sizeof(int32_t), cudaMemcpyDeviceToHost));
-            result->best_hits = h2[0];
-            CUDA_TRY(ctx, cudaMemcpy(h2, ctx->d_hits + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
-            result->last_hits = h2[0];
-        }
     } else {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }

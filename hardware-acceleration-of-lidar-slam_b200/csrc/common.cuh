@@ -25,9 +25,15 @@ struct b200slam_map {
     bool has_geometry = false;
 };
 
-// Device-side result block of a match (read back by b200slam_match_fetch).
+// Device-side state of a match.  work_key / tickets are the in-flight arg-min cell and the
+// finished-CTA counter; the last CTA of a scoring kernel publishes {key, best_hits,
+// last_hits} (what b200slam_match_fetch and the all-gather read) and resets the first two,
+// so between launches work_key == ~0 and tickets == 0.
 struct MatchDev {
-    unsigned long long key;     // (score bits << 32) | global linear index
+    unsigned long long work_key;
+    unsigned int tickets;
+    unsigned int pad;
+    unsigned long long key;     // (score bits << 32) | global linear index; ~0 = nothing scored
     int best_hits;
     int last_hits;
 };
@@ -53,7 +59,9 @@ struct b200slam_ctx {
     // match result
     MatchDev *d_match = nullptr;
     MatchDev *h_match = nullptr;            // pinned
-    unsigned long long *d_keys = nullptr;   // all-gather landing zone [nranks]
+    unsigned long long *d_keys = nullptr;   // all-gather landing zones: [0,128) {key, hits} per rank,
+                                            // [128,256) {weight sum, count} per rank
+    unsigned long long *h_keys = nullptr;   // pinned [128]
     float *d_hit_values = nullptr;          // [2][scan_cap]: best / last candidate
     // bookkeeping of the last queued lattice match (host side)
     struct {
@@ -62,6 +70,7 @@ struct b200slam_ctx {
         float pose0[3] = {0, 0, 0};
         float step[3] = {0, 0, 0};
         bool is_poses = false;
+        bool gathered = false;   // per-rank results were all-gathered into d_keys
     } last;
 
     // optional full score table
@@ -123,12 +132,15 @@ int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
 struct LatticeLaunch {
     const b200slam_map *map;
     int nth, ntx, nty;
-    const float *d_ct, *d_st, *d_sxt, *d_syt;
+    // axis tables ct[nth] | st[nth] | sxt[ntx] | syt[nty]: host copy (passed as kernel
+    // parameters when small enough) or, for large lattices, a device copy
+    const float *h_tables;
+    const float *d_tables;
     int64_t row_begin, row_end;
     float *d_scores;   // optional
 };
+constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
-int trace_launch(b200slam_ctx *ctx, const LatticeLaunch &L, bool use_gathered_keys);
 int poses_launch(b200slam_ctx *ctx, const b200slam_map *map, int64_t P, int64_t index_base,
                  float *d_scores, int32_t *d_hits);
 

@@ -216,7 +216,7 @@ int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_
         // d_wsum[1] = local N, so one 16-byte all-gather carries both
         unsigned long long nloc = (unsigned long long)N;
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_wsum + 1, &nloc, 8, cudaMemcpyHostToDevice, ctx->stream));
-        unsigned long long *d_all = ctx->d_keys + ctx->nranks;      // [nranks][2]
+        unsigned long long *d_all = ctx->d_keys + 128;              // [nranks][2]
         int rc = comm_allgather_u64(ctx, ctx->d_wsum, d_all, 2);
         if (rc) return rc;
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_wsum, d_all, 16 * ctx->nranks, cudaMemcpyDeviceToHost,

@@ -227,7 +227,7 @@ def test_graph_replay_matches_eager(ctx, oracle, synth):
         for _ in range(3):
             ctx.graph_launch(g)
         again = ctx.match_fetch()
-        assert ctx.launch_count() == before + 3 * 3        # EDT + lattice + trace per replay
+        assert ctx.launch_count() == before + 3 * 2        # EDT + lattice (arg-min and trace fused) per replay
         assert again.best_index == eager.best_index and again.best_hits == eager.best_hits
         ctx.graph_destroy(g)
     finally:

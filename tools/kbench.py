@@ -77,7 +77,7 @@ def bench_lattice(mod, synth, ctx, names):
         evals = n[0] * n[1] * n[2] * len(w["scan_x"])
         ms = time_loop(ctx, lambda i: ctx.score_lattice_async(m, w["pose0"], w["step"], n), 20 if evals > 1e9 else 100)
         r = ctx.match_fetch()
-        print(f"lattice {name} {n} x {len(w['scan_x'])} beams: {ms * 1e3:9.2f} us  {evals / ms / 1e9:8.2f} Gevals/s "
+        print(f"lattice {name} {n} x {len(w['scan_x'])} beams: {ms * 1e3:9.2f} us  {evals / ms / 1e9:8.3f} Tevals/s "
               f"best={r.best_index} score={r.best_score:.3f}", flush=True)
         m.close()
 
