@@ -32,6 +32,7 @@
 // for the next launch -- so a match is exactly ONE kernel: no memset, no table upload (the
 // lattice axis tables travel as kernel parameters), no separate reduction pass.
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -53,6 +54,15 @@ __device__ __forceinline__ int cell_index(float v, int n)
 {
     const int r = (int)roundf(v);
     return (r > 0 && r < n - 1) ? r : -1;
+}
+
+// Read-only gather whose position in the instruction stream the compiler must keep
+// (volatile asm statements are not reordered against each other).
+__device__ __forceinline__ float ldg_ordered(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 }
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
@@ -81,48 +91,69 @@ __device__ __forceinline__ bool cta_is_last(MatchDev *match, unsigned long long 
     return *flag_smem != 0;
 }
 
-// Replays candidate (ct, st, sxt, syt) with the whole CTA: in-bounds field values are
-// compacted in beam order into vals[] (main.c:515); returns the count in every thread.
-// red: shared scratch of NT/32 + 1 ints.
+// Replays two candidates at once with the whole CTA (the winner and the last one scored):
+// in-bounds field values are compacted in beam order into vals0 / vals1 (main.c:515);
+// the counts come back in every thread.  red: shared scratch of 2 * NT/32 ints.
+struct TraceCand {
+    float ct, st, sxt, syt;
+};
 template <int NT>
-__device__ int trace_candidate(const float *__restrict__ field, int pitch, int rows, int cols,
-                               const float *__restrict__ scan_x, const float *__restrict__ scan_y, int nbeams,
-                               float ipixel, float ct, float st, float sxt, float syt, float *vals, int *red)
+__device__ void trace_pair(const float *__restrict__ field, int pitch, int rows, int cols,
+                           const float *__restrict__ scan_x, const float *__restrict__ scan_y, int nbeams,
+                           float ipixel, const TraceCand (&cand)[2], float *vals0, float *vals1, int *red,
+                           int (&count)[2])
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int count = 0;
+    count[0] = count[1] = 0;
     for (int i0 = 0; i0 < nbeams; i0 += NT) {
         const int i = i0 + tid;
-        bool in = false;
-        float v = 0.0f;
+        bool in[2] = {false, false};
+        float v[2] = {0.0f, 0.0f};
         if (i < nbeams) {
             const float psx = __fmul_rn(scan_x[i], ipixel);
             const float psy = __fmul_rn(scan_y[i], ipixel);
-            const int c = cell_index(__fadd_rn(rot_x(psx, psy, ct, st), sxt), cols);
-            const int r = cell_index(__fadd_rn(rot_y(psx, psy, ct, st), syt), rows);
-            in = c >= 0 && r >= 0;
-            if (in) v = field[(long)r * pitch + c];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = cell_index(__fadd_rn(rot_x(psx, psy, cand[k].ct, cand[k].st), cand[k].sxt), cols);
+                const int r = cell_index(__fadd_rn(rot_y(psx, psy, cand[k].ct, cand[k].st), cand[k].syt), rows);
+                in[k] = c >= 0 && r >= 0;
+                v[k] = field[in[k] ? (long)r * pitch + c : -1];
+            }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, in);
+        const unsigned m0 = __ballot_sync(0xffffffffu, in[0]);
+        const unsigned m1 = __ballot_sync(0xffffffffu, in[1]);
         __syncthreads();                       // red[] free again
-        if (lane == 0) red[warp] = __popc(m);
+        if (lane == 0) { red[warp] = __popc(m0); red[NT / 32 + warp] = __popc(m1); }
         __syncthreads();
-        int before = 0, total = 0;
+        int before0 = 0, total0 = 0, before1 = 0, total1 = 0;
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w) {
-            const int c = red[w];
-            before += w < warp ? c : 0;
-            total += c;
+            const int c0 = red[w], c1 = red[NT / 32 + w];
+            before0 += w < warp ? c0 : 0; total0 += c0;
+            before1 += w < warp ? c1 : 0; total1 += c1;
         }
-        if (in && vals) vals[count + before + __popc(m & ((1u << lane) - 1u))] = v;
-        count += total;
+        const unsigned below = (1u << lane) - 1u;
+        if (in[0]) vals0[count[0] + before0 + __popc(m0 & below)] = v[0];
+        if (in[1]) vals1[count[1] + before1 + __popc(m1 & below)] = v[1];
+        count[0] += total0;
+        count[1] += total1;
     }
-    return count;
 }
 
 constexpr int LATTICE_TABLE_FLOATS = 960;      // ct | st | sxt | syt as kernel parameters
 struct LatticeTables {
     float v[LATTICE_TABLE_FLOATS];
+};
+
+// Gather pipeline shape: U beams per group, NBUF register buffers (NBUF - 1 groups in flight);
+// GUARD = table rows appended for padding (a multiple of NBUF*U) and for the prefetches that
+// run past the end.
+template <int TYPT>
+struct LatticePipe {
+    static constexpr int U = TYPT >= 16 ? 1 : 16 / TYPT;
+    static constexpr int NBUF = TYPT >= 16 ? 2 : 3;
+    static constexpr int PAD = NBUF * U;
+    static constexpr int GUARD = PAD - 1 + (NBUF - 1) * U;
 };
 
 struct LatticeArgs {
@@ -152,13 +183,16 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     constexpr int TXT = 32 * WX;
     constexpr int TYT = TYPT * WY;
     constexpr int NT = 32 * WX * WY;
+    using P = LatticePipe<TYPT>;
+    constexpr int U = P::U, NBUF = P::NBUF, GUARD = P::GUARD;
+    static_assert(NT % TXT == 0 && NT % TYT == 0, "tile shape");
     extern __shared__ __align__(16) int lat_smem[];
     int *colT = lat_smem;
-    int *rowT = colT + A.cb * TXT;
-    float *Sx_s = reinterpret_cast<float *>(rowT + A.cb * TYT);
+    int *rowT = colT + (A.cb + GUARD) * TXT;             // chunk rows + padding/guard rows
+    float *Sx_s = reinterpret_cast<float *>(rowT + (A.cb + GUARD) * TYT);
     float *Sy_s = Sx_s + A.cb;
     __shared__ unsigned long long red[WX * WY];
-    __shared__ int tail_red[NT / 32 + 1];
+    __shared__ int tail_red[2 * (NT / 32)];
     __shared__ int last_flag;
 
     const float *tab = A.tables ? A.tables : T.v;
@@ -193,49 +227,88 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                 Sy_s[i] = rot_y(psx, psy, ct, st);
             }
             __syncthreads();
-            for (int e = tid; e < cb * TXT; e += NT) {
-                const int i = e / TXT, t = e % TXT;
-                int v = INVALID_OFF;
-                if (tx0 + t < A.ntx) {
-                    const int c = cell_index(__fadd_rn(Sx_s[i], sxtT[tx0 + t]), A.cols);   // :483
-                    if (c >= 0) v = c;
+            const int cbp = (cb + P::PAD - 1) / P::PAD * P::PAD;             // padded with INVALID rows
+            const int cbg = cbp + (NBUF - 1) * U;                            // + guard rows for the prefetches
+            {
+                // column table: thread owns tile column t (its axis value is loop invariant)
+                // and walks the beams NT/TXT at a time
+                const int t = tid % TXT;
+                const bool tok = tx0 + t < A.ntx;
+                const float sx = tok ? sxtT[tx0 + t] : 0.0f;
+#pragma unroll 4
+                for (int i = tid / TXT; i < cbg; i += NT / TXT) {
+                    int v = INVALID_OFF;
+                    if (tok && i < cb) {
+                        const int c = cell_index(__fadd_rn(Sx_s[i], sx), A.cols);       // main.c:483
+                        if (c >= 0) v = c;
+                    }
+                    colT[i * TXT + t] = v;
                 }
-                colT[e] = v;
             }
-            for (int e = tid; e < cb * TYT; e += NT) {
-                const int i = e / TYT, t = e % TYT;
-                int v = INVALID_OFF;
-                if (ty0 + t < A.nty) {
-                    const int r = cell_index(__fadd_rn(Sy_s[i], sytT[ty0 + t]), A.rows);   // :501
-                    if (r >= 0) v = r * A.pitch;
+            {
+                const int t = tid % TYT;
+                const bool tok = ty0 + t < A.nty;
+                const float sy = tok ? sytT[ty0 + t] : 0.0f;
+#pragma unroll 4
+                for (int i = tid / TYT; i < cbg; i += NT / TYT) {
+                    int v = INVALID_OFF;
+                    if (tok && i < cb) {
+                        const int r = cell_index(__fadd_rn(Sy_s[i], sy), A.rows);       // main.c:501
+                        if (r >= 0) v = r * A.pitch;
+                    }
+                    rowT[i * TYT + t] = v;
                 }
-                rowT[e] = v;
             }
             __syncthreads();
+            // Software-pipelined gather: warps issue in order, so the loads of the next group
+            // of U beams are put in flight before the (sequential, in-order) additions of
+            // the current group.  Table rows [cb, cbp) are INVALID and add +0.0f.
             const int *cp = colT + txl;
             const int *rp = rowT + tyl;
-#pragma unroll 8
-            for (int i = 0; i < cb; ++i) {
-                const int c = cp[i * TXT];
-                int ro[TYPT];
-                if constexpr (TYPT % 4 == 0) {
+            auto gather = [&](int i0, float (&dst)[U][TYPT]) {
 #pragma unroll
-                    for (int j = 0; j < TYPT; j += 4) {
-                        const int4 q = *reinterpret_cast<const int4 *>(rp + i * TYT + j);
-                        ro[j] = q.x; ro[j + 1] = q.y; ro[j + 2] = q.z; ro[j + 3] = q.w;
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u;
+                    const int c = cp[i * TXT];
+                    int ro[TYPT];
+                    if constexpr (TYPT % 4 == 0) {
+#pragma unroll
+                        for (int j = 0; j < TYPT; j += 4) {
+                            const int4 q = *reinterpret_cast<const int4 *>(rp + i * TYT + j);
+                            ro[j] = q.x; ro[j + 1] = q.y; ro[j + 2] = q.z; ro[j + 3] = q.w;
+                        }
+                    } else if constexpr (TYPT == 2) {
+                        const int2 q = *reinterpret_cast<const int2 *>(rp + i * TYT);
+                        ro[0] = q.x; ro[1] = q.y;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TYPT; ++j) ro[j] = rp[i * TYT + j];
                     }
-                } else if constexpr (TYPT == 2) {
-                    const int2 q = *reinterpret_cast<const int2 *>(rp + i * TYT);
-                    ro[0] = q.x; ro[1] = q.y;
-                } else {
 #pragma unroll
-                    for (int j = 0; j < TYPT; ++j) ro[j] = rp[i * TYT + j];
+                    for (int j = 0; j < TYPT; ++j) dst[u][j] = ldg_ordered(A.field + __viaddmax_s32(c, ro[j], -1));
                 }
-                float v[TYPT];
+                // order fence for the compiler: the additions below stay behind these loads
 #pragma unroll
-                for (int j = 0; j < TYPT; ++j) v[j] = __ldg(A.field + __viaddmax_s32(c, ro[j], -1));
+                for (int j = 0; j < TYPT; ++j) asm volatile("" : "+f"(acc[j]));
+            };
+            auto accumulate = [&](const float (&src)[U][TYPT]) {
 #pragma unroll
-                for (int j = 0; j < TYPT; ++j) acc[j] = __fadd_rn(acc[j], v[j]);      // main.c:516
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < TYPT; ++j) acc[j] = __fadd_rn(acc[j], src[u][j]);      // main.c:516
+            };
+            {
+                // NBUF rotating register buffers: group g+NBUF-1 is requested before group g is added
+                float v[NBUF][U][TYPT];
+#pragma unroll
+                for (int b = 0; b < NBUF - 1; ++b) gather(b * U, v[b]);
+                for (int i0 = 0; i0 < cbp; i0 += NBUF * U) {
+#pragma unroll
+                    for (int b = 0; b < NBUF; ++b) {
+                        gather(i0 + (b + NBUF - 1) * U, v[(b + NBUF - 1) % NBUF]);   // past the end: guard rows
+                        accumulate(v[b]);
+                    }
+                }
             }
         }
 
@@ -265,19 +338,22 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     if (!cta_is_last(A.match, best, A.total_ctas, &last_flag)) return;
     __threadfence();
     const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&A.match->work_key);
-    int best_hits = 0, last_hits = 0;
+    int hits[2] = {0, 0};
     if (key != ~0ull) {
+        TraceCand cand[2];
+#pragma unroll
         for (int which = 0; which < 2; ++which) {
             const long long lin = which == 0 ? (long long)(key & 0xffffffffull) : A.row_end * A.nty - 1;
             const int ity = (int)(lin % A.nty);
             const long long row = lin / A.nty;
             const int itx = (int)(row % A.ntx), jth = (int)(row / A.ntx);
-            const int n = trace_candidate<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams,
-                                              A.ipixel, ctT[jth], stT[jth], sxtT[itx], sytT[ity],
-                                              A.hit_values + (size_t)which * A.hit_stride, tail_red);
-            if (which == 0) best_hits = n; else last_hits = n;
+            cand[which].ct = ctT[jth]; cand[which].st = stT[jth];
+            cand[which].sxt = sxtT[itx]; cand[which].syt = sytT[ity];
         }
+        trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand,
+                       A.hit_values, A.hit_values + A.hit_stride, tail_red, hits);
     }
+    const int best_hits = hits[0], last_hits = hits[1];
     if (tid == 0) {
         A.match->key = key;
         A.match->best_hits = best_hits;
@@ -330,17 +406,38 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
                                 __fmul_rn(A.scan_y[c0 + i], A.ipixel));
         __syncthreads();
         if (live) {
-#pragma unroll 8
-            for (int i = 0; i < cb; ++i) {
-                const float2 q = ps[i];
-                const float fx = __fadd_rn(__fadd_rn(__fmul_rn(q.x, ct), __fmul_rn(q.y, st)), sxt);
-                const float fy = __fadd_rn(__fadd_rn(__fmul_rn(q.x, nst), __fmul_rn(q.y, ct)), syt);
-                const int c = cell_index(fx, A.cols);
-                const int r = cell_index(fy, A.rows);
-                const bool in = (c >= 0) && (r >= 0);
-                const int off = in ? r * A.pitch + c : -1;
-                score = __fadd_rn(score, __ldg(A.field + off));
-                nh += in ? 1 : 0;
+            // software-pipelined like the lattice kernel: the gathers of the next 8 beams are
+            // in flight while the current 8 values are added in beam order
+            constexpr int U = 8;
+            auto gather = [&](int i0, float (&dst)[U]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = min(i0 + u, cb - 1);
+                    const float2 q = ps[i];
+                    const float fx = __fadd_rn(__fadd_rn(__fmul_rn(q.x, ct), __fmul_rn(q.y, st)), sxt);
+                    const float fy = __fadd_rn(__fadd_rn(__fmul_rn(q.x, nst), __fmul_rn(q.y, ct)), syt);
+                    const int c = cell_index(fx, A.cols);
+                    const int r = cell_index(fy, A.rows);
+                    const bool in = (c >= 0) && (r >= 0) && (i0 + u < cb);
+                    const int off = in ? r * A.pitch + c : -1;
+                    dst[u] = __ldg(A.field + off);
+                    nh += in ? 1 : 0;
+                }
+            };
+            auto accumulate = [&](const float (&src)[U]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) score = __fadd_rn(score, src[u]);   // +0.0f past the end
+            };
+            constexpr int NBUF = 3;
+            float v[NBUF][U];
+#pragma unroll
+            for (int b = 0; b < NBUF - 1; ++b) gather(b * U, v[b]);
+            for (int i0 = 0; i0 < cb; i0 += NBUF * U) {
+#pragma unroll
+                for (int b = 0; b < NBUF; ++b) {
+                    gather(i0 + (b + NBUF - 1) * U, v[(b + NBUF - 1) % NBUF]);
+                    accumulate(v[b]);
+                }
             }
         }
     }
@@ -379,21 +476,23 @@ int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T
 {
     constexpr int TXT = 32 * WX, TYT = TYPT * WY;
     auto kern = lattice_kernel<TYPT, WX, WY>;
-    // Beams per chunk: the whole scan when it fits ~60 KB of tables, else even chunks.
+    // Beams per chunk: the whole scan when its tables fit the budget, else even chunks.
+    constexpr int GUARD = LatticePipe<TYPT>::GUARD;
     const int per_beam = (TXT + TYT + 2) * 4;
+    const int budget = TYPT >= 16 ? 56 * 1024 : 100 * 1024;
     int cb = A.nbeams > 0 ? A.nbeams : 1;
-    const int cap = (60 * 1024) / per_beam;
+    const int cap = budget / per_beam - GUARD;
     if (cb > cap) {
         const int chunks = (cb + cap - 1) / cap;
         cb = (cb + chunks - 1) / chunks;
     }
     cb = (cb + 3) & ~3;                                   // keeps the int4 row loads aligned
     A.cb = cb;
-    const size_t smem = (size_t)cb * per_beam;
+    const size_t smem = (size_t)(cb + GUARD) * per_beam;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        smem_set = 64 * 1024;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+        smem_set = 104 * 1024;
     }
     dim3 grid((A.nty + TYT - 1) / TYT, (A.ntx + TXT - 1) / TXT, nth_cover);
     A.total_ctas = grid.x * grid.y * grid.z;
@@ -434,7 +533,8 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
 
     // Candidates per thread: as many as still leave ~16 warps per SM; big register tiles
     // amortise the per-chunk tables on large sweeps, small lattices need every thread.
-    const long long want_warps = 16LL * ctx->sm_count;
+    long long want_warps = 16LL * ctx->sm_count;
+    if (const char *e = getenv("B200SLAM_LATTICE_WARPS_PER_SM")) want_warps = (long long)atoi(e) * ctx->sm_count;
     if (cands >= want_warps * 32 * 16 && L.nty >= 64 && L.ntx >= 64)
         return launch_lattice_cfg<16, 2, 4>(ctx, A, T, nth_cover);       // 64 x 64 tile, 256 thr
     if (cands >= want_warps * 32 * 8 && L.nty >= 64)
