@@ -190,3 +190,66 @@ def make_workload(name: str, seed: int = SEED_GRID):
     pose0 = np.array([true_pose[i] + TRUE_POSE_OFFSET[i] for i in range(3)], np.float32)
     return dict(name=name, occ=occ, pixel=pixel, top_left=tl, scan_x=sx, scan_y=sy, pose0=pose0,
                 step=np.array(LATTICE_STEP, np.float32), n=tuple(w["n"]), true_pose=true_pose)
+
+
+# Synthetic stand-in for the reference's missing lidar_dataset.csv -------------------------
+REF_BEAMS = 1079                      # Subsystem_1/main.c:7  (#define column 1079)
+REF_ANGLE_MIN = -2.351831             # Subsystem_1/main.c:48
+REF_ANGLE_INC = 0.004363              # Subsystem_1/main.c:50
+
+
+def room_segments(width: float = 18.0, height: float = 12.0, pillars=((-3.0, 0.0), (3.5, 2.0), (-7.5, 4.0), (5.0, -3.0), (2.0, -4.5)),
+                  pillar_size: float = 0.8) -> np.ndarray:
+    """Axis-aligned wall segments [x0, y0, x1, y1] of a closed room with square pillars."""
+    hw, hh = width / 2, height / 2
+    segs = [(-hw, -hh, hw, -hh), (-hw, hh, hw, hh), (-hw, -hh, -hw, hh), (hw, -hh, hw, hh)]
+    for cx, cy in pillars:
+        h = pillar_size / 2
+        segs += [(cx - h, cy - h, cx + h, cy - h), (cx - h, cy + h, cx + h, cy + h),
+                 (cx - h, cy - h, cx - h, cy + h), (cx + h, cy - h, cx + h, cy + h)]
+    return np.array(segs, np.float64)
+
+
+def raycast_segments(segs: np.ndarray, px: float, py: float, ang: np.ndarray) -> np.ndarray:
+    """Range of each ray (origin (px, py), world angle ang[k]) to the nearest segment."""
+    dx, dy = np.cos(ang)[:, None], np.sin(ang)[:, None]
+    x0, y0, x1, y1 = (segs[None, :, i] for i in range(4))
+    vert = (x0 == x1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tv = (x0 - px) / dx                                   # vertical segments: x = x0
+        yv = py + tv * dy
+        okv = vert & (tv > 1e-9) & (yv >= np.minimum(y0, y1)) & (yv <= np.maximum(y0, y1))
+        th = (y0 - py) / dy                                   # horizontal segments: y = y0
+        xh = px + th * dx
+        okh = (~vert) & (th > 1e-9) & (xh >= np.minimum(x0, x1)) & (xh <= np.maximum(x0, x1))
+    t = np.where(okv, tv, np.where(okh, th, np.inf))
+    return t.min(axis=1)
+
+
+def lidar_dataset(nscans: int, radius: float = 3.0, loops: float = 1.0, seed: int = SEED_SCAN,
+                  noise: float = 0.004) -> np.ndarray:
+    """[nscans][1079] ranges of the reference's 270-degree lidar (Subsystem_1/main.c:45-58) carried
+    slowly around a circle inside room_segments(): a stand-in for the bundled lidar_dataset.csv,
+    which is not in the reference tree (.MISSING_LARGE_BLOBS).  Motion per scan stays far below
+    the +-1-step search window of FastMatch so the reference tracks it."""
+    segs = room_segments()
+    k = np.arange(REF_BEAMS, dtype=np.float64)
+    beam = REF_ANGLE_MIN + k * REF_ANGLE_INC
+    out = np.empty((nscans, REF_BEAMS), np.float32)
+    for s in range(nscans):
+        phi = 2.0 * np.pi * loops * s / max(nscans - 1, 1)
+        px, py = radius * np.cos(phi) - radius, radius * np.sin(phi)     # starts at the origin
+        heading = phi + np.pi / 2                                         # tangent to the circle
+        r = raycast_segments(segs, px, py, heading + beam)
+        if noise:
+            r = r + (hash_uniform(seed + s, np.arange(REF_BEAMS)) - 0.5) * 2.0 * noise
+        out[s] = r
+    return out
+
+
+def write_lidar_csv(path: str, ranges: np.ndarray) -> None:
+    """The reference reads `%f,` x 1079 per scan (Subsystem_1/main.c:22-30)."""
+    with open(path, "w") as f:
+        for row in ranges:
+            f.write(",".join("%.4f" % v for v in row))
+            f.write(",\n")

@@ -8,11 +8,13 @@
  *   B200SLAM_REF_MAPOUT    (anything opened for writing)
  * Nothing else about the reference is altered.
  */
+/* The reference objects are built with -Dfopen=orc_shim_fopen on one command line that also
+ * compiles this file: drop the macro BEFORE <stdio.h> so the real fopen is declared here. */
+#undef fopen
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
-#undef fopen
 FILE *orc_shim_fopen(const char *path, const char *mode)
 {
     const char *env = NULL;
