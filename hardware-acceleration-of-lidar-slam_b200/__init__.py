@@ -103,6 +103,8 @@ def load_library() -> C.CDLL:
         "b200slam_event_record": (i, [vp, i]),
         "b200slam_event_elapsed_ms": (i, [vp, i, i, c_float_p]),
         "b200slam_weights_resample": (i, [vp, f, C.c_uint32, vp, c_u64_p, vp, c_i64_p, c_i64_p]),
+        "b200slam_resample_owned_slots": (None, [C.c_uint64, C.c_int64, C.c_uint32, C.c_uint64, C.c_uint64,
+                                                 c_i64_p, c_i64_p]),
         "b200slam_pyramid_match": (i, [vp, C.POINTER(vp), i, c_float_p, c_float_p, c_int_p, C.POINTER(Match)]),
         "b200slam_comm_unique_id": (i, [vp]),
         "b200slam_comm_init": (i, [vp, i, i, vp]),
@@ -137,6 +139,13 @@ def shard_range(total: int, nranks: int, rank: int) -> tuple[int, int]:
     b, e = C.c_int64(0), C.c_int64(0)
     L.b200slam_shard_range(total, nranks, rank, C.byref(b), C.byref(e))
     return b.value, e.value
+
+
+def resample_owned_slots(w_global: int, n_global: int, u0_q32: int, rank_offset: int, w_local: int):
+    kb, kc = C.c_int64(0), C.c_int64(0)
+    load_library().b200slam_resample_owned_slots(w_global, n_global, u0_q32, rank_offset, w_local,
+                                                 C.byref(kb), C.byref(kc))
+    return kb.value, kc.value
 
 
 def pack_key(score: float, index: int) -> int:

@@ -244,10 +244,9 @@ int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_
     const unsigned long long Wd = Wglobal / (unsigned long long)Nglobal;
     const unsigned long long Wm = Wglobal % (unsigned long long)Nglobal;
     const unsigned long long U = (unsigned long long)(((unsigned __int128)Wd * u0_q32) >> 32);
-    // owned slots: rank_offset <= T_k < rank_offset + Wlocal
-    const long long k_begin = slots_below(rank_offset, U, Wd, Wm, Nglobal);
-    const long long k_end = slots_below(rank_offset + Wlocal, U, Wd, Wm, Nglobal);
-    const long long k_count = k_end - k_begin;
+    int64_t kb64 = 0, kc64 = 0;
+    b200slam_resample_owned_slots(Wglobal, Nglobal, u0_q32, rank_offset, Wlocal, &kb64, &kc64);
+    const long long k_begin = kb64, k_count = kc64;
     if (ancestors && k_count > 0) {
         if ((size_t)k_count > ctx->anc_cap) {
             if (ctx->d_ancestors) cudaFree(ctx->d_ancestors);
@@ -271,4 +270,22 @@ int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_
     if (k_begin_out) *k_begin_out = k_begin;
     if (k_count_out) *k_count_out = k_count;
     return B200SLAM_OK;
+}
+
+// Pure host arithmetic (no GPU): the slots k in [0, N) whose threshold T_k falls inside this
+// rank's stretch [rank_offset, rank_offset + w_local) of the global cumulative weight.
+extern "C" void b200slam_resample_owned_slots(uint64_t w_global, int64_t n_global, uint32_t u0_q32,
+                                              uint64_t rank_offset, uint64_t w_local, int64_t *k_begin,
+                                              int64_t *k_count)
+{
+    long long kb = 0, ke = 0;
+    if (n_global > 0 && w_global > 0) {
+        const unsigned long long Wd = w_global / (unsigned long long)n_global;
+        const unsigned long long Wm = w_global % (unsigned long long)n_global;
+        const unsigned long long U = (unsigned long long)(((unsigned __int128)Wd * u0_q32) >> 32);
+        kb = slots_below(rank_offset, U, Wd, Wm, n_global);
+        ke = slots_below(rank_offset + w_local, U, Wd, Wm, n_global);
+    }
+    if (k_begin) *k_begin = kb;
+    if (k_count) *k_count = ke - kb;
 }

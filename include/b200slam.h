@@ -205,6 +205,12 @@ int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id /
 int b200slam_comm_destroy(b200slam_ctx *ctx);
 /* Even split of `total` units over nranks (pure host arithmetic). */
 void b200slam_shard_range(int64_t total, int nranks, int rank, int64_t *begin, int64_t *end);
+/* Systematic-resampling slots owned by a rank (pure host): the k in [0, n_global) whose
+ * threshold T_k = U + floor(k * w_global / n_global) lies in [rank_offset, rank_offset +
+ * w_local), rank_offset being the sum of the lower ranks' integer weight sums. */
+void b200slam_resample_owned_slots(uint64_t w_global, int64_t n_global, uint32_t u0_q32,
+                                   uint64_t rank_offset, uint64_t w_local, int64_t *k_begin,
+                                   int64_t *k_count);
 /* Packed (score, index) key used for the arg-min exchange and its merge (pure host). */
 uint64_t b200slam_pack_key(float score, uint32_t index);
 void     b200slam_unpack_key(uint64_t key, float *score, uint32_t *index);

@@ -1,0 +1,173 @@
+"""Worker for tests/test_multirank.py: one process per rank, launched with torch.distributed.run.
+
+    --mode cpu : gloo only.  Checks the HOST side of the N > 1 path -- shard ranges, packed-key
+                 merge, integer-weight offsets and resampling-slot ownership (the pure-host C-ABI
+                 helpers) -- against the unsharded CPU oracle.  No GPU, no compute calls.
+    --mode gpu : one GPU per rank.  The C ABI's own NCCL communicator all-gathers the per-shard
+                 bests / weight sums; results must equal the unsharded CPU oracle bit for bit.
+Exits non-zero on the first mismatch.
+"""
+import argparse
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "hardware-acceleration-of-lidar-slam_b200"
+
+
+def check(cond, msg):
+    if not cond:
+        print(f"[rank {dist.get_rank()}] FAIL: {msg}", flush=True)
+        sys.exit(1)
+
+
+def gather_objects(obj):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def oracle_problem(mod, synth):
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    w = synth.make_workload("tiny")
+    field = orc.edt(w["occ"])
+    om = orc.make_map(field, w["pixel"], w["top_left"])
+    n = (6, 20, 12)
+    ores, oscores, _ = orc.score_lattice(om, w["scan_x"], w["scan_y"], w["pose0"], w["step"], n)
+    P = 5003
+    poses = synth.particles_gaussian(P, w["true_pose"])
+    _, pscores, _ = orc.score_poses(om, w["scan_x"], w["scan_y"], poses)
+    beta, u0 = 0.15, 0x40000000
+    ow, oq, oW, oanc = orc.weights_resample(pscores, beta, u0)
+    return dict(orc=orc, w=w, field=field, om=om, n=n, ores=ores, oscores=oscores, poses=poses, pscores=pscores,
+                beta=beta, u0=u0, ow=ow, oq=oq, oW=oW, oanc=oanc)
+
+
+def run_cpu(mod, synth):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pb = oracle_problem(mod, synth)
+    n, oscores = pb["n"], pb["oscores"]
+    # ---- lattice: rows sharded, per-rank packed key, all-gather, merge -----------------------
+    nrows = n[0] * n[1]
+    rb, re = mod.shard_range(nrows, world, rank)
+    idx = np.arange(rb * n[2], re * n[2], dtype=np.uint64)
+    local = oscores[rb * n[2]:re * n[2]]
+    keys = (local.view(np.uint32).astype(np.uint64) << np.uint64(32)) | idx
+    my_key = int(keys.min()) if len(keys) else (1 << 64) - 1
+    check(my_key == min(mod.pack_key(float(s), int(i)) for s, i in zip(local, idx)), "pack_key disagrees with numpy packing")
+    t = torch.tensor([my_key - (1 << 63)], dtype=torch.int64)          # order-preserving shift into int64
+    allk = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allk, t)
+    merged = mod.merge_keys(np.array([int(k.item()) + (1 << 63) for k in allk], np.uint64))
+    score, index = mod.unpack_key(int(merged))
+    check(index == pb["ores"].best_index and np.float32(score) == np.float32(pb["ores"].best_score),
+          f"merged winner ({index}, {score}) != oracle ({pb['ores'].best_index}, {pb['ores'].best_score})")
+    # ---- particles: integer weights, rank offsets, slot ownership ----------------------------
+    P = len(pb["pscores"])
+    pbeg, pend = mod.shard_range(P, world, rank)
+    mine = pb["pscores"][pbeg:pend]
+    smin = torch.tensor([float(mine.min())], dtype=torch.float32)
+    dist.all_reduce(smin, op=dist.ReduceOp.MIN)
+    ext = np.concatenate([mine, np.array([smin.item()], np.float32)])
+    _, q_ext, _, _ = pb["orc"].weights_resample(ext, pb["beta"], pb["u0"])
+    q = q_ext[:-1].astype(np.uint64)
+    check(np.array_equal(q, pb["oq"][pbeg:pend]), "per-shard integer weights differ from the unsharded oracle")
+    sums = gather_objects((int(q.sum(dtype=np.uint64)), len(q)))
+    W = sum(s for s, _ in sums)
+    N = sum(c for _, c in sums)
+    off = sum(s for s, _ in sums[:rank])
+    check(W == pb["oW"] and N == P, "global weight sum / count mismatch")
+    kb, kc = mod.resample_owned_slots(W, N, pb["u0"], off, int(q.sum(dtype=np.uint64)))
+    Wd, Wm = divmod(W, N)
+    U = (Wd * pb["u0"]) >> 32
+    C = off + np.cumsum(q.astype(object))                               # exact python ints
+    anc = []
+    for k in range(kb, kb + kc):
+        T = U + k * Wd + (k * Wm) // N
+        # first i with C[i] > T (bisect on exact python ints)
+        lo, hi = 0, len(C) - 1
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if C[mid] > T:
+                hi = mid
+            else:
+                lo = mid + 1
+        anc.append(lo + pbeg)
+    parts = gather_objects((kb, kc, anc))
+    check(parts[0][0] == 0 and sum(p[1] for p in parts) == N, "owned slot ranges do not tile [0, N)")
+    check(all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1)), "owned slot ranges not contiguous")
+    allanc = np.array([a for p in parts for a in p[2]], np.int32)
+    check(np.array_equal(allanc, pb["oanc"]), "sharded ancestors differ from the unsharded oracle")
+
+
+def run_gpu(mod, synth):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    pb = oracle_problem(mod, synth)
+    w, n = pb["w"], pb["n"]
+    ctx = mod.Context(local_rank)
+    uid = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(world, rank, uid[0])
+    rows, cols = w["occ"].shape
+    m = ctx.new_map(rows, cols)
+    m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+    check(np.array_equal(m.download_field().view(np.uint32), pb["field"].view(np.uint32)), "EDT differs")
+    ctx.scan_upload(w["scan_x"], w["scan_y"])
+    # ---- lattice, rows sharded, winner all-gathered over NCCL ----------------------------------
+    nrows = n[0] * n[1]
+    rb, re = mod.shard_range(nrows, world, rank)
+    res = ctx.score_lattice_rows(m, w["pose0"], w["step"], n, rb, re, allreduce=True)
+    o = pb["ores"]
+    check(res.best_index == o.best_index and res.best_hits == o.best_hits and res.last_hits == o.last_hits and
+          np.float32(res.best_score).tobytes() == np.float32(o.best_score).tobytes(),
+          f"global winner ({res.best_index}, {res.best_score}, {res.best_hits}, {res.last_hits}) != oracle "
+          f"({o.best_index}, {o.best_score}, {o.best_hits}, {o.last_hits})")
+    # an empty shard must not disturb the result
+    res2 = ctx.score_lattice_rows(m, w["pose0"], w["step"], n, 0 if rank == 0 else nrows, nrows, allreduce=True)
+    check(res2.best_index == o.best_index, "empty shard changed the winner")
+    # ---- 3-level pyramid through the communicator ----------------------------------------------
+    steps = np.array([[0.2, 0.2, 0.02], [0.1, 0.1, 0.01], [0.05, 0.05, 0.005]], np.float32)
+    ns = np.array([[5, 9, 9], [3, 5, 5], [3, 3, 3]], np.int32)
+    gres = ctx.pyramid_match([m, m, m], w["pose0"], steps, ns)
+    ores = pb["orc"].pyramid_match([pb["om"]] * 3, w["scan_x"], w["scan_y"], w["pose0"], steps, ns)
+    check(all(g.best_index == r.best_index for g, r in zip(gres, ores)), "pyramid winners differ from the oracle")
+    # ---- particles: poses sharded, weights normalised and resampled globally -------------------
+    P = len(pb["poses"])
+    pbeg, pend = mod.shard_range(P, world, rank)
+    _, pscores, _ = ctx.score_poses(m, pb["poses"][pbeg:pend], index_base=pbeg)
+    check(np.array_equal(pscores.view(np.uint32), pb["pscores"][pbeg:pend].view(np.uint32)), "particle scores differ")
+    wts, W, anc, kb, kc = ctx.weights_resample(P, pb["beta"], pb["u0"])
+    check(W == pb["oW"], f"global weight sum {W} != oracle {pb['oW']}")
+    check(np.array_equal(wts[:pend - pbeg].view(np.uint32), pb["ow"][pbeg:pend].view(np.uint32)), "weights differ")
+    parts = gather_objects((kb, kc, anc.tolist()))
+    check(parts[0][0] == 0 and sum(p[1] for p in parts) == P, "owned slot ranges do not tile [0, N)")
+    allanc = np.array([a for p in parts for a in p[2]], np.int32)
+    check(np.array_equal(allanc, pb["oanc"]), "sharded ancestors differ from the unsharded oracle")
+    m.close()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", choices=["cpu", "gpu"], required=True)
+    args = ap.parse_args()
+    dist.init_process_group("gloo")
+    mod = importlib.import_module(PKG)
+    synth = importlib.import_module(PKG + ".synth")
+    (run_cpu if args.mode == "cpu" else run_gpu)(mod, synth)
+    dist.barrier()
+    if dist.get_rank() == 0:
+        print(f"multirank {args.mode} ok on {dist.get_world_size()} ranks", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
