@@ -364,17 +364,17 @@ def run_b200_arm(args, synth):
         edt_bytes = 8.0 * cells                                              # 8 B / cell
         lat_bytes = 4.0 * evals_per_rank + 4.0 * nth * ntx * nty + 8.0 * nbeams   # 4 B / eval + 4 B / pose
         roofs = {
-            "edt_fused_kernel": {"bound": "hbm", "achieved": edt_bytes / (edt_ms_avg * 1e-3) / 1e9, "peak": peak,
+            "edt_tma_kernel": {"bound": "hbm", "achieved": edt_bytes / (edt_ms_avg * 1e-3) / 1e9, "peak": peak,
                                  "unit": "GB/s", "ms": edt_ms_avg, "algorithmic_bytes": edt_bytes,
-                                 "traffic": ncu_traffic(f"edt_fused_kernel:{args.workload}"),
+                                 "traffic": ncu_traffic(f"edt_tma_kernel:{args.workload}"),
                                  "mcells_per_s": cells / (edt_ms_avg * 1e-3) / 1e6},
             "lattice_kernel": {"bound": "hbm", "achieved": lat_bytes / (lat_ms_avg * 1e-3) / 1e9, "peak": peak,
                                "unit": "GB/s", "ms": lat_ms_avg, "algorithmic_bytes": lat_bytes,
                                "traffic": ncu_traffic(f"lattice_kernel:{args.workload}"),
                                "evals_per_s": evals_per_rank / (lat_ms_avg * 1e-3),
-                               "note": "gathers are served by L1/L2 (field is cache resident), so this "
-                                       "HBM-equivalent figure may exceed the DRAM peak; ms includes the "
-                                       "2-warp trace kernel"},
+                               "note": "4 B per pose x beam evaluation (SURVEY.md 8d); the gathers are served by "
+                                       "L1/L2 (the field is cache resident), so this HBM-equivalent figure may "
+                                       "exceed the DRAM peak"},
         }
         for r in roofs.values():
             r["frac"] = r["achieved"] / r["peak"]
