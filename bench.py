@@ -265,7 +265,7 @@ def run_b200_arm(args, synth):
     scan_x = ctx.pinned_empty((nbeams,), np.float32); scan_x[...] = w["scan_x"]
     scan_y = ctx.pinned_empty((nbeams,), np.float32); scan_y[...] = w["scan_y"]
     ctx.scan_upload(scan_x, scan_y)
-    allreduce = world > 1
+    allreduce = world > 1 and not args.no_allreduce
 
     def step_async(i):
         m = maps[i % ring]
@@ -421,6 +421,8 @@ def main():
     ap.add_argument("--workload", default="config1", choices=["config1", "config3", "tiny"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="diagnostic: N > 1 without the per-step exchange of bests (ranks run independently)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     synth = importlib.import_module(PKG + ".synth")

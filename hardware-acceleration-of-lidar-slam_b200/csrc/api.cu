@@ -60,7 +60,7 @@ int b200slam_create(b200slam_ctx **out, int device)
     CREATE_TRY(cudaHostAlloc(&ctx->h_match, sizeof(MatchDev), cudaHostAllocDefault));
     {
         MatchDev init;
-        init.work_key = ~0ull; init.tickets = 0; init.pad = 0; init.key = ~0ull;
+        init.work_key = ~0ull; init.tickets = 0; init.epoch = 0; init.key = ~0ull;
         init.best_hits = 0; init.last_hits = 0;
         CREATE_TRY(cudaMemcpy(ctx->d_match, &init, sizeof init, cudaMemcpyHostToDevice));
     }
@@ -387,6 +387,8 @@ int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], co
     L.row_begin = row_begin;
     L.row_end = row_end;
     L.d_scores = nullptr;
+    const bool multi = allreduce && ctx->nccl_comm && ctx->nranks > 1;
+    L.exchange = multi && ctx->p2p_ready;      // merged inside the kernel over NVLink peer memory
     if (want_scores) {
         const size_t need = (size_t)nrows * n[2];
         if (need > ctx->scores_cap) {
@@ -404,7 +406,7 @@ int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], co
     rc = lattice_launch(ctx, L);
     if (rc) return rc;
     bool gathered = false;
-    if (allreduce && ctx->nccl_comm && ctx->nranks > 1) {
+    if (multi && !L.exchange) {
         // {key, best_hits | last_hits} of every rank; b200slam_match_fetch merges them
         rc = comm_allgather_u64(ctx, &ctx->d_match->key, ctx->d_keys, 2);
         if (rc) return rc;

@@ -7,6 +7,7 @@
 // NCCL at all, and a process that already loaded a libnccl.so.2 (e.g. torch's bundled one)
 // shares it instead of loading a second copy.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <nccl.h>
 
 #include "common.cuh"
@@ -71,6 +72,79 @@ int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send, unsi
     return B200SLAM_OK;
 }
 
+namespace {
+
+void teardown_peer_exchange(b200slam_ctx *ctx)
+{
+    for (int r = 0; r < XCHG_MAX_RANKS; ++r) {
+        if (ctx->peer_ptrs[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_ptrs[r]);
+        ctx->peer_ptrs[r] = nullptr;
+    }
+    cudaFree(ctx->d_xchg); ctx->d_xchg = nullptr;
+    cudaFree(ctx->d_peers); ctx->d_peers = nullptr;
+    ctx->p2p_ready = false;
+}
+
+// Allocates this rank's exchange buffer, trades CUDA IPC handles with the other ranks (one
+// NCCL all-gather at init time) and maps every peer's buffer.  All ranks must agree on the
+// outcome, so the per-rank success flags are all-gathered too.
+void setup_peer_exchange(b200slam_ctx *ctx)
+{
+    const int n = ctx->nranks;
+    if (n > XCHG_MAX_RANKS) return;
+    bool ok = cudaMalloc(&ctx->d_xchg, sizeof(XchgBuf)) == cudaSuccess &&
+              cudaMemset(ctx->d_xchg, 0, sizeof(XchgBuf)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_peers, sizeof(XchgBuf *) * n) == cudaSuccess &&
+              cudaMemset(&ctx->d_match->epoch, 0, sizeof(unsigned int)) == cudaSuccess;
+    // handle record: 64-byte IPC handle + 8-byte ok flag, padded to 80 bytes (10 x u64)
+    constexpr int REC = 10;
+    unsigned long long rec[REC] = {0};
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    if (ok) ok = cudaIpcGetMemHandle(&h, ctx->d_xchg) == cudaSuccess;
+    if (ok) memcpy(rec, &h, sizeof h);
+    rec[8] = ok ? 1 : 0;
+    unsigned long long *d_send = nullptr, *d_recv = nullptr;
+    unsigned long long all[XCHG_MAX_RANKS * REC];
+    bool gathered = cudaMalloc(&d_send, sizeof rec) == cudaSuccess &&
+                    cudaMalloc(&d_recv, sizeof(rec) * n) == cudaSuccess &&
+                    cudaMemcpyAsync(d_send, rec, sizeof rec, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                    comm_allgather_u64(ctx, d_send, d_recv, REC) == B200SLAM_OK &&
+                    cudaMemcpyAsync(all, d_recv, sizeof(rec) * n, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+                    cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    cudaFree(d_send); cudaFree(d_recv);
+    if (gathered)
+        for (int r = 0; r < n; ++r) ok = ok && all[r * REC + 8] == 1;
+    else
+        ok = false;
+    if (ok) {
+        for (int r = 0; r < n && ok; ++r) {
+            if (r == ctx->rank) { ctx->peer_ptrs[r] = ctx->d_xchg; continue; }
+            cudaIpcMemHandle_t ph;
+            memcpy(&ph, &all[r * REC], sizeof ph);
+            void *p = nullptr;
+            ok = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            ctx->peer_ptrs[r] = static_cast<XchgBuf *>(p);
+        }
+        if (ok) ok = cudaMemcpy(ctx->d_peers, ctx->peer_ptrs, sizeof(XchgBuf *) * n, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    cudaGetLastError();               // failures here only mean "use the NCCL path"
+    // second agreement round: mapping may have failed on one rank only
+    unsigned long long mine = ok ? 1 : 0, *d_f = nullptr, *d_all = nullptr, flags[XCHG_MAX_RANKS] = {0};
+    bool agree = cudaMalloc(&d_f, 8) == cudaSuccess && cudaMalloc(&d_all, 8 * n) == cudaSuccess &&
+                 cudaMemcpyAsync(d_f, &mine, 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                 comm_allgather_u64(ctx, d_f, d_all, 1) == B200SLAM_OK &&
+                 cudaMemcpyAsync(flags, d_all, 8 * n, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+                 cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    cudaFree(d_f); cudaFree(d_all);
+    for (int r = 0; r < n && agree; ++r) agree = flags[r] == 1;
+    if (agree) ctx->p2p_ready = true;
+    else teardown_peer_exchange(ctx);
+    cudaGetLastError();
+}
+
+}  // namespace
+
 extern "C" {
 
 int b200slam_comm_unique_id(void *id_out)
@@ -103,6 +177,9 @@ int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id_i
     ctx->nccl_comm = comm;
     ctx->nranks = nranks;
     ctx->rank = rank;
+    // NVLink peer exchange: best effort.  When CUDA IPC / P2P is unavailable the match results
+    // are all-gathered with NCCL instead (same answers, ~20 us more latency per match).
+    if (nranks > 1 && !getenv("B200SLAM_NO_P2P")) setup_peer_exchange(ctx);
     return B200SLAM_OK;
 }
 
@@ -112,6 +189,7 @@ int b200slam_comm_destroy(b200slam_ctx *ctx)
     if (ctx->nccl_comm) {
         NcclApi *api = nccl_api();
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        teardown_peer_exchange(ctx);
         if (api->handle) api->CommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }

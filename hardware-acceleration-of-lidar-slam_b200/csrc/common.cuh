@@ -32,10 +32,30 @@ struct b200slam_map {
 struct MatchDev {
     unsigned long long work_key;
     unsigned int tickets;
-    unsigned int pad;
+    unsigned int epoch;         // number of peer exchanges this context has taken part in
     unsigned long long key;     // (score bits << 32) | global linear index; ~0 = nothing scored
     int best_hits;
     int last_hits;
+};
+
+// Peer-memory exchange of per-rank match results (multi-GPU): every context owns one
+// XchgBuf; the last CTA of a scoring kernel stores its {key, best_hits, last_hits} into
+// EVERY peer's buffer over NVLink (P2P mapped through CUDA IPC), waits until all ranks'
+// words of that epoch have landed in its own buffer, and merges.  The four 32-bit payload
+// words travel as 8-byte stores {data, epoch} (each store is atomic and carries its own
+// validity flag, like NCCL's LL protocol), so no fence and no separate flag are needed.
+// 4 epochs of slots: a rank can run at most two posts ahead of the slowest reader.
+constexpr int XCHG_MAX_RANKS = 64;
+constexpr int XCHG_EPOCHS = 4;
+struct XchgSlot {
+    unsigned long long w[4];          // {key lo, key hi, best_hits, last_hits}, each | (epoch << 32)
+};
+struct XchgBuf {
+    XchgSlot slot[XCHG_EPOCHS][XCHG_MAX_RANKS];
+};
+struct XchgArgs {                     // kernel-side view; peers == nullptr: no exchange
+    XchgBuf *const *peers;            // [nranks] device pointers (own buffer at [rank])
+    int nranks, rank;
 };
 
 struct b200slam_ctx {
@@ -107,6 +127,11 @@ struct b200slam_ctx {
     // NCCL (dlopen'ed lazily; see comm.cu)
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    // NVLink peer exchange (set up by b200slam_comm_init when P2P + CUDA IPC work)
+    XchgBuf *d_xchg = nullptr;            // this rank's buffer
+    XchgBuf **d_peers = nullptr;          // device array [nranks]
+    XchgBuf *peer_ptrs[XCHG_MAX_RANKS] = {};   // host copy (for closing the IPC mappings)
+    bool p2p_ready = false;
 };
 
 int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
@@ -138,6 +163,7 @@ struct LatticeLaunch {
     const float *d_tables;
     int64_t row_begin, row_end;
     float *d_scores;   // optional
+    bool exchange;     // merge with the other ranks through peer memory inside the kernel
 };
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);

@@ -91,6 +91,68 @@ __device__ __forceinline__ bool cta_is_last(MatchDev *match, unsigned long long 
     return *flag_smem != 0;
 }
 
+// ---- multi-GPU: merge this rank's result with its peers' through NVLink peer memory ------
+// Called by the whole last CTA (>= 64 threads).  `epoch` is this exchange's number (> 0,
+// identical on every rank).  On return (thread 0) key / best_hits / last_hits are the GLOBAL
+// result: lowest key wins; the last candidate of the whole lattice belongs to the highest
+// rank that scored anything.
+__device__ __forceinline__ void exchange_and_merge(const XchgArgs &X, unsigned int epoch, unsigned long long &key,
+                                                   int &best_hits, int &last_hits, unsigned int *words_smem)
+{
+    const int tid = threadIdx.x;
+    const int ring = (int)(epoch % XCHG_EPOCHS);
+    if (tid == 0) {
+        words_smem[0] = (unsigned int)key; words_smem[1] = (unsigned int)(key >> 32);
+        words_smem[2] = (unsigned int)best_hits; words_smem[3] = (unsigned int)last_hits;
+    }
+    __syncthreads();
+    const unsigned long long tag = (unsigned long long)epoch << 32;
+    for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
+        const int r = i >> 2, w = i & 3;
+        // post word w to rank r ...
+        *reinterpret_cast<volatile unsigned long long *>(&X.peers[r]->slot[ring][X.rank].w[w]) = tag | words_smem[w];
+    }
+    __shared__ unsigned int got[4 * XCHG_MAX_RANKS];
+    for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
+        const int r = i >> 2, w = i & 3;
+        // ... and wait for rank r's word w of this epoch in OUR buffer
+        const volatile unsigned long long *src = &X.peers[X.rank]->slot[ring][r].w[w];
+        unsigned long long v;
+        do { v = *src; } while ((unsigned int)(v >> 32) != epoch);
+        got[i] = (unsigned int)v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long k = ~0ull;
+        int bh = 0, lh = 0;
+        for (int r = 0; r < X.nranks; ++r) {
+            const unsigned long long kr = (unsigned long long)got[4 * r] | ((unsigned long long)got[4 * r + 1] << 32);
+            if (kr == ~0ull) continue;
+            if (kr < k) { k = kr; bh = (int)got[4 * r + 2]; }
+            lh = (int)got[4 * r + 3];
+        }
+        key = k; best_hits = bh; last_hits = lh;
+    }
+}
+
+// Empty shard of a multi-GPU match: nothing to score, but the exchange still needs this rank.
+__global__ void __launch_bounds__(64) exchange_only_kernel(MatchDev *match, const XchgArgs X)
+{
+    __shared__ unsigned int words_s[4];
+    __shared__ unsigned int epoch_s;
+    if (threadIdx.x == 0) epoch_s = match->epoch + 1;
+    __syncthreads();
+    unsigned long long key = ~0ull;
+    int bh = 0, lh = 0;
+    exchange_and_merge(X, epoch_s, key, bh, lh, words_s);
+    if (threadIdx.x == 0) {
+        match->key = key;
+        match->best_hits = bh;
+        match->last_hits = lh;
+        match->epoch = epoch_s;
+    }
+}
+
 // Replays two candidates at once with the whole CTA (the winner and the last one scored):
 // in-bounds field values are compacted in beam order into vals0 / vals1 (main.c:515);
 // the counts come back in every thread.  red: shared scratch of 2 * NT/32 ints.
@@ -172,6 +234,7 @@ struct LatticeArgs {
     int hit_stride;
     int cb;                   // beams per shared-memory chunk
     unsigned total_ctas;
+    XchgArgs xchg;            // peers == nullptr: single GPU / no exchange
 };
 
 // TYPT candidates (consecutive ty) per thread, WX warps along tx, WY warps along ty.
@@ -194,6 +257,8 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     __shared__ unsigned long long red[WX * WY];
     __shared__ int tail_red[2 * (NT / 32)];
     __shared__ int last_flag;
+    __shared__ unsigned int xchg_words[4];
+    __shared__ unsigned int epoch_s;
 
     const float *tab = A.tables ? A.tables : T.v;
     const float *ctT = tab, *stT = tab + A.nth, *sxtT = tab + 2 * A.nth, *sytT = sxtT + A.ntx;
@@ -338,6 +403,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     if (!cta_is_last(A.match, best, A.total_ctas, &last_flag)) return;
     __threadfence();
     const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&A.match->work_key);
+    if (tid == 0) epoch_s = *reinterpret_cast<volatile unsigned int *>(&A.match->epoch) + 1;
     int hits[2] = {0, 0};
     if (key != ~0ull) {
         TraceCand cand[2];
@@ -353,13 +419,19 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
         trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand,
                        A.hit_values, A.hit_values + A.hit_stride, tail_red, hits);
     }
-    const int best_hits = hits[0], last_hits = hits[1];
+    int best_hits = hits[0], last_hits = hits[1];
+    unsigned long long out_key = key;
+    if (A.xchg.peers) {
+        __syncthreads();
+        exchange_and_merge(A.xchg, epoch_s, out_key, best_hits, last_hits, xchg_words);
+    }
     if (tid == 0) {
-        A.match->key = key;
+        A.match->key = out_key;
         A.match->best_hits = best_hits;
         A.match->last_hits = last_hits;
         A.match->work_key = ~0ull;
         A.match->tickets = 0u;
+        if (A.xchg.peers) A.match->epoch = epoch_s;
     }
 }
 
@@ -517,9 +589,19 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     A.hit_values = ctx->d_hit_values;
     A.hit_stride = ctx->scan_cap;
     A.tables = L.d_tables;
+    A.xchg.peers = nullptr; A.xchg.nranks = 1; A.xchg.rank = 0;
+    if (L.exchange && ctx->p2p_ready) {
+        A.xchg.peers = ctx->d_peers;
+        A.xchg.nranks = ctx->nranks; A.xchg.rank = ctx->rank;
+    }
     LatticeTables T;                     // parameter block (copied at launch)
     if (!L.d_tables) memcpy(T.v, L.h_tables, sizeof(float) * (2 * (size_t)L.nth + L.ntx + L.nty));
     if (L.row_end <= L.row_begin) {
+        if (A.xchg.peers) {             // nothing to score, but the peers wait for this rank's post
+            exchange_only_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, A.xchg);
+            LAUNCH_CHECK(ctx);
+            return B200SLAM_OK;
+        }
         // empty shard: publish "nothing scored"
         CUDA_TRY(ctx, cudaMemsetAsync(&ctx->d_match->key, 0xff, sizeof(unsigned long long), ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(&ctx->d_match->best_hits, 0, 2 * sizeof(int), ctx->stream));
