@@ -297,8 +297,10 @@ def run_b200_arm(args, synth):
     lat_ms = [ctx.event_elapsed_ms(3 * i + 1, 3 * i + 2) for i in range(KA)]
     edt_ms_avg, lat_ms_avg = sum(edt_ms) / KA, sum(lat_ms) / KA
 
-    # ---- pass B: the timed region.  One CUDA graph per ring slot, K replays --------------
-    graphs = []
+    # ---- pass B: the timed region.  The step is two microsecond-scale kernels, so steps are
+    # captured as CUDA graphs: one graph holding a whole turn of the ring (`ring` consecutive
+    # steps) for the bulk, single-step graphs for the remainder; K steps are replayed exactly.
+    graphs, turn = [], None
     use_graph = not args.no_graph
     if use_graph:
         try:
@@ -306,19 +308,32 @@ def run_b200_arm(args, synth):
                 ctx.graph_begin()
                 step_async(i)
                 graphs.append(ctx.graph_end())
+            ctx.graph_begin()
+            for i in range(ring):
+                step_async(i)
+            turn = ctx.graph_end()
         except mod.B200SlamError as e:
             if rank == 0:
                 print(f"[bench] graph capture unavailable ({e}); timing eager launches", file=sys.stderr)
             use_graph = False
-            graphs = []
-    for i in range(W):
-        ctx.graph_launch(graphs[i % ring]) if use_graph else step_async(i)
+            graphs, turn = [], None
+
+    def run_steps(n):
+        if not use_graph:
+            for i in range(n):
+                step_async(i)
+            return
+        for _ in range(n // ring):
+            ctx.graph_launch(turn)
+        for i in range(n % ring):
+            ctx.graph_launch(graphs[i])
+
+    run_steps(max(W, ring))
     launches0 = ctx.launch_count()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.event_record(4000)
-    for i in range(K):
-        ctx.graph_launch(graphs[i % ring]) if use_graph else step_async(i)
+    run_steps(K)
     ctx.event_record(4001)
     barrier()
     dev_ms = ctx.event_elapsed_ms(4000, 4001)
@@ -387,7 +402,7 @@ def run_b200_arm(args, synth):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(w, args, world), ring_maps=ring,
-                           timing="cuda-graph replay" if use_graph else "eager launches"),
+                           timing=f"cuda-graph replay ({ring} steps per graph)" if use_graph else "eager launches"),
             "edt_mcells_per_s": cells / (edt_ms_avg * 1e-3) / 1e6,
             "match_evals_per_s_per_gpu": evals_per_rank / (lat_ms_avg * 1e-3),
             "roofline": roofline, "rooflines": roofs,
@@ -402,7 +417,7 @@ def run_b200_arm(args, synth):
             line["cpu_baseline"] = cpu_sample(w, synth, budget_s=args.cpu_seconds)
         print(json.dumps(line), flush=True)
 
-    for g in graphs:
+    for g in graphs + ([turn] if turn is not None else []):
         ctx.graph_destroy(g)
     for m in maps:
         m.close()
