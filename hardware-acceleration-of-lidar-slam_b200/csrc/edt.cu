@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -340,14 +341,18 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<int32_t *>(d_occ), gdim, gstr, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      getenv("B200SLAM_EDT_L2P") ? (CUtensorMapL2promotion)atoi(getenv("B200SLAM_EDT_L2P"))
+                                                 : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS)
         return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "cuTensorMapEncodeTiled -> %d (pitch %d)", (int)cr,
                                   occ_pitch);
 
-    // Rows per CTA: a chunk of `cb` batches of R rows costs cb + ~2.5 batch times (two halo
-    // stages that only run pass 1, plus the pipeline fill); pick the cb that minimises
-    // waves x cost for the number of CTAs the GPU holds at once.
+    // Rows per CTA.  Big grids: chunks of 14 batches -- several waves of CTAs balance better
+    // than one wave of long ones (measured at 8192^2: 103 us vs 111 us) and the halo costs
+    // 2/16.  Small grids: a chunk of `cb` batches costs cb + ~2.5 batch times (two halo stages
+    // that only run pass 1, plus the pipeline fill); pick the cb that minimises waves x cost
+    // for the number of CTAs the GPU holds at once.
     const int gx = (cols + 64 * NW - 1) / (64 * NW);
     const int nbatch = (rows + R - 1) / R;
     const long resident = (long)ctx->sm_count * occupancy;
@@ -359,6 +364,8 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
         const double cost = (double)waves * (cb + 2.5);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_cb = cb; }
     }
+    if (nbatch >= 14 && (long)gx * ((nbatch + 13) / 14) * 2 >= 5 * resident) best_cb = 14;
+    if (const char *e = getenv("B200SLAM_EDT_CB")) best_cb = max(1, min(atoi(e), nbatch));   // tuning knob
     const int gy = (nbatch + best_cb - 1) / best_cb;
     kern<<<dim3(gx, gy), C::THREADS, smem, ctx->stream>>>(tmap, d_field, (uint32_t)field_pitch * 4u, rows, cols, best_cb, t2,
                                                          max_dist);
@@ -370,6 +377,10 @@ template <int R>
 int launch_fused(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field, int field_pitch,
                  int rows, int cols, int t2, float max_dist)
 {
+    if (const char *e = getenv("B200SLAM_EDT_NST")) {
+        if (atoi(e) == 2) return launch_tma<R, 3, 2>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
+        if (atoi(e) == 4) return launch_tma<R, 3, 4>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
+    }
     return launch_tma<R, 3, 3>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
 }
 
