@@ -83,6 +83,9 @@ def load_library() -> C.CDLL:
         "b200slam_map_destroy": (None, [vp, vp]),
         "b200slam_map_set_geometry": (i, [vp, f, f, f]),
         "b200slam_map_upload_occupancy": (i, [vp, vp, vp, i]),
+        "b200slam_map_resize": (i, [vp, i, i]),
+        "b200slam_map_rasterise": (i, [vp, vp, vp, vp, i, f, c_int_p, c_int_p, c_float_p]),
+        "b200slam_map_download_occupancy": (i, [vp, vp, vp, i]),
         "b200slam_map_edt": (i, [vp, vp, f]),
         "b200slam_map_download_field": (i, [vp, vp, vp, i]),
         "b200slam_map_upload_field": (i, [vp, vp, vp, i]),
@@ -199,6 +202,23 @@ class Map:
         self.ctx._check(self.ctx.L.b200slam_map_upload_occupancy(self.ctx.h, self.h, occ.ctypes.data,
                                                                  occ.strides[0] // 4))
         return self
+
+    def rasterise(self, x, y, pixel_size: float):
+        """Map points -> occupancy on the device (one level of OccupationalGrid, main.c:271-354);
+        the map takes the rasterised grid's size and geometry.  -> (rows, cols, (min_x, min_y))"""
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.ascontiguousarray(y, np.float32)
+        r, c = C.c_int32(0), C.c_int32(0)
+        tl = (C.c_float * 2)()
+        self.ctx._check(self.ctx.L.b200slam_map_rasterise(self.ctx.h, self.h, x.ctypes.data, y.ctypes.data, len(x),
+                                                          pixel_size, C.byref(r), C.byref(c), tl))
+        self.rows, self.cols = r.value, c.value
+        return r.value, c.value, (np.float32(tl[0]), np.float32(tl[1]))
+
+    def download_occupancy(self) -> np.ndarray:
+        out = np.empty((self.rows, self.cols), np.int32)
+        self.ctx._check(self.ctx.L.b200slam_map_download_occupancy(self.ctx.h, self.h, out.ctypes.data, self.cols))
+        return out
 
     def edt(self, max_dist: float = 10.0):
         self.ctx._check(self.ctx.L.b200slam_map_edt(self.ctx.h, self.h, max_dist))

@@ -89,6 +89,7 @@ void b200slam_destroy(b200slam_ctx *ctx)
     cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
     cudaFree(ctx->d_ancestors); cudaFree(ctx->d_wsum); cudaFreeHost(ctx->h_wsum);
     cudaFree(ctx->d_edt_scratch);
+    cudaFree(ctx->d_points); cudaFreeHost(ctx->h_points);
     for (int i = 0; i < LAT_SLOTS; ++i)
         if (ctx->lat_event[i]) cudaEventDestroy(ctx->lat_event[i]);
     for (int i = 0; i < 4096; ++i)
@@ -147,8 +148,8 @@ int b200slam_map_create(b200slam_ctx *ctx, int rows, int cols, b200slam_map **ou
                                   rows, cols);
     b200slam_map *m = new (std::nothrow) b200slam_map();
     if (!m) return B200SLAM_ERR_NOMEM;
-    m->rows = rows;
-    m->cols = cols;
+    m->rows = m->cap_rows = rows;
+    m->cols = m->cap_cols = cols;
     m->occ_pitch = (cols + 31) & ~31;        // rows start on 128-byte lines
     m->field_pitch = (cols + 31) & ~31;
     cudaError_t e = cudaMalloc(&m->d_occ, sizeof(int32_t) * (size_t)m->occ_pitch * rows);
@@ -178,6 +179,14 @@ void b200slam_map_destroy(b200slam_ctx *ctx, b200slam_map *map)
     delete map;
 }
 
+int b200slam_map_resize(b200slam_map *map, int rows, int cols)
+{
+    if (!map || rows <= 0 || cols <= 0 || rows > map->cap_rows || cols > map->cap_cols) return B200SLAM_ERR_ARG;
+    map->rows = rows;
+    map->cols = cols;
+    return B200SLAM_OK;
+}
+
 int b200slam_map_set_geometry(b200slam_map *map, float pixel_size, float top_left_x, float top_left_y)
 {
     if (!map || !(pixel_size > 0.0f)) return B200SLAM_ERR_ARG;
@@ -197,6 +206,61 @@ int b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const in
     return B200SLAM_OK;
 }
 
+int b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x, const float *y, int npoints,
+                           float pixel_size, int *rows_out, int *cols_out, float top_left_out[2])
+{
+    if (!ctx || !map || !x || !y || npoints <= 0 || !(pixel_size > 0.0f)) return B200SLAM_ERR_ARG;
+    // main.c:272-289: bounding box, strict compares, seeded with point 0
+    float minXY[2] = {x[0], y[0]}, maxXY[2] = {x[0], y[0]};
+    for (int a = 0; a < npoints; ++a) {
+        if (x[a] < minXY[0]) minXY[0] = x[a];
+        if (x[a] > maxXY[0]) maxXY[0] = x[a];
+        if (y[a] < minXY[1]) minXY[1] = y[a];
+        if (y[a] > maxXY[1]) maxXY[1] = y[a];
+    }
+    // main.c:296-305: 3-pixel margin; size = (int)roundf(extent / pixel) + 1, every step rounded to float
+    int S[2];
+    for (int a = 0; a < 2; ++a) {
+        volatile float margin = 3 * pixel_size;
+        volatile float lo = minXY[a] - margin, hi = maxXY[a] + margin;
+        volatile float ext = hi - lo;
+        volatile float q = ext / pixel_size;
+        minXY[a] = lo;
+        S[a] = (int)roundf(q) + 1;
+    }
+    const int cols = S[0], rows = S[1];                                    // main.c:313-314
+    if (rows_out) *rows_out = rows;
+    if (cols_out) *cols_out = cols;
+    if (top_left_out) { top_left_out[0] = minXY[0]; top_left_out[1] = minXY[1]; }
+    if (rows > map->cap_rows || cols > map->cap_cols || rows <= 0 || cols <= 0)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "rasterised grid %d x %d exceeds the map capacity %d x %d",
+                                  rows, cols, map->cap_rows, map->cap_cols);
+    if ((size_t)npoints > ctx->points_cap) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_points); cudaFreeHost(ctx->h_points);
+        ctx->d_points = ctx->h_points = nullptr;
+        ctx->points_cap = 0;
+        const size_t cap = ((size_t)npoints + 4095) & ~(size_t)4095;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_points, sizeof(float) * 2 * cap));
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_points, sizeof(float) * 2 * cap, cudaHostAllocDefault));
+        ctx->points_cap = cap;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));          // pinned staging buffer free again
+    memcpy(ctx->h_points, x, sizeof(float) * npoints);
+    memcpy(ctx->h_points + ctx->points_cap, y, sizeof(float) * npoints);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points, ctx->h_points, sizeof(float) * npoints, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points + ctx->points_cap, ctx->h_points + ctx->points_cap,
+                                  sizeof(float) * npoints, cudaMemcpyHostToDevice, ctx->stream));
+    map->rows = rows;
+    map->cols = cols;
+    map->pixel_size = pixel_size;                                          // main.c:357-362
+    map->top_left_x = minXY[0];
+    map->top_left_y = minXY[1];
+    map->has_geometry = true;
+    return rasterise_launch(ctx, map, npoints, minXY[0], minXY[1], pixel_size);
+}
+
 int b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist)
 {
     if (!ctx || !map) return B200SLAM_ERR_ARG;
@@ -211,6 +275,16 @@ int b200slam_map_download_field(b200slam_ctx *ctx, b200slam_map *map, float *out
                                     sizeof(float) * (size_t)map->field_pitch,
                                     sizeof(float) * (size_t)map->cols, map->rows,
                                     cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200SLAM_OK;
+}
+
+int b200slam_map_download_occupancy(b200slam_ctx *ctx, b200slam_map *map, int32_t *out, int stride)
+{
+    if (!ctx || !map || !out || stride < map->cols) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(out, sizeof(int32_t) * (size_t)stride, map->d_occ,
+                                    sizeof(int32_t) * (size_t)map->occ_pitch, sizeof(int32_t) * (size_t)map->cols,
+                                    map->rows, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return B200SLAM_OK;
 }

@@ -15,7 +15,8 @@
 #define LAT_SLOTS 4
 
 struct b200slam_map {
-    int rows = 0, cols = 0;
+    int rows = 0, cols = 0;          // current size (<= capacity; changed by b200slam_map_rasterise)
+    int cap_rows = 0, cap_cols = 0;  // allocated size
     int occ_pitch = 0;       // elements
     int field_pitch = 0;     // elements
     int32_t *d_occ = nullptr;
@@ -115,6 +116,10 @@ struct b200slam_ctx {
     unsigned long long *d_wsum = nullptr;     // [4] scratch scalars
     unsigned long long *h_wsum = nullptr;     // pinned [4]
 
+    // map points staged for rasterisation: x | y
+    float *d_points = nullptr, *h_points = nullptr;   // device / pinned
+    size_t points_cap = 0;
+
     // generic EDT scratch (u16 column distances)
     uint16_t *d_edt_scratch = nullptr;
     size_t edt_scratch_cap = 0;
@@ -173,6 +178,9 @@ int poses_launch(b200slam_ctx *ctx, const b200slam_map *map, int64_t P, int64_t 
 int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32,
                                float *weights, uint64_t *wsum, int32_t *ancestors,
                                int64_t *k_begin, int64_t *k_count);
+
+int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float min_x, float min_y,
+                     float pixel_size);
 
 int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send,
                        unsigned long long *d_recv, int count_per_rank);

@@ -1,0 +1,47 @@
+// raster.cu -- map points -> occupancy grid on the device: the scatter loop of
+// OccupationalGrid (Subsystem_1/main.c:332-353), one level.  The bounding box, margin and
+// grid size (main.c:272-305) are computed by the caller on the host with the reference's
+// float operations (api.cu: b200slam_map_rasterise); the per-point arithmetic here is
+//     hits = (int)roundf((p - min) / PIXELSIZE) + 1          (IEEE division, roundf)
+//     idx  = (hits_y - 1) * Sgrid_x + hits_x - 1 ;  row = idx / Sgrid_x ; col = idx % Sgrid_x
+// exactly as the reference, including its index wrap when hits_x runs past the row.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+raster_clear_kernel(int4 *__restrict__ occ, long n4)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) occ[i] = make_int4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(256)
+raster_scatter_kernel(const float *__restrict__ px, const float *__restrict__ py, int n, float min_x,
+                      float min_y, float pixel, int sgrid_x, int rows, int32_t *__restrict__ occ, int pitch)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const float dx = __fsub_rn(px[a], min_x);                               // main.c:333
+    const float dy = __fsub_rn(py[a], min_y);                               // main.c:334
+    const int hx = (int)roundf(__fdiv_rn(dx, pixel)) + 1;                   // main.c:339
+    const int hy = (int)roundf(__fdiv_rn(dy, pixel)) + 1;                   // main.c:340
+    const int idx = (((hy - 1) * sgrid_x) + hx) - 1;                        // main.c:345
+    const int row = idx / sgrid_x, col = idx % sgrid_x;                     // main.c:348-349
+    if (row >= 0 && row < rows && col >= 0) occ[(long)row * pitch + col] = 1;   // main.c:355
+}
+
+}  // namespace
+
+int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float min_x, float min_y, float pixel_size)
+{
+    // main.c:319 clears the whole array; the rows x pitch region in use is what anyone reads
+    const long n4 = (long)map->rows * map->occ_pitch / 4;
+    raster_clear_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<int4 *>(map->d_occ), n4);
+    LAUNCH_CHECK(ctx);
+    raster_scatter_kernel<<<(npoints + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->d_points, ctx->d_points + ctx->points_cap, npoints, min_x, min_y, pixel_size, map->cols, map->rows,
+        map->d_occ, map->occ_pitch);
+    LAUNCH_CHECK(ctx);
+    return B200SLAM_OK;
+}

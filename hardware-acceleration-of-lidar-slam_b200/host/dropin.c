@@ -9,6 +9,10 @@
  *     void FastMatch (const float POSE[3], const float searchResolution[3])
  *     void FastMatch2(const float POSE[3], const float searchResolution[3])
  *         (Subsystem_1/main.c:381,598)
+ *     void OccupationalGrid(const float PIXELSIZE, const float PIXELSIZE2)
+ *         (Subsystem_1/main.c:271 -- the step in front of the transform: map points are
+ *          rasterised and transformed on the device, 8 bytes per point cross PCIe instead of
+ *          4 bytes per cell)
  * so that the unmodified reference program, built as a shared object, calls the GPU path
  * when this library precedes it in the link order (ELF symbol interposition, see
  * INTEGRATION.md).  FastMatch* read the reference's globals `scan` and `occ_grid` and write
@@ -20,6 +24,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "b200slam.h"
 
@@ -46,6 +51,12 @@ typedef struct {                              /* main.c:200-212 */
     float top_left_corner2[2];
 } MyGrid;
 
+typedef struct {                              /* main.c:147-151 */
+    float x[25000];
+    float y[25000];
+    int size;
+} myLocalMap;
+
 typedef struct {                              /* main.c:374-378 */
     float pose[3];
     float bestHits[2500];
@@ -56,6 +67,7 @@ typedef struct {                              /* main.c:374-378 */
 extern ScanData scan __attribute__((weak));
 extern MyGrid occ_grid __attribute__((weak));
 extern MyFastMatchParameters FastMatchParameters __attribute__((weak));
+extern myLocalMap local_map __attribute__((weak));
 
 static b200slam_ctx *g_ctx;
 /* Device-resident twins of metric_grid / metric_grid2, kept from the last transform so
@@ -82,13 +94,23 @@ static b200slam_ctx *ctx(void)
     return g_ctx;
 }
 
+/* One device map per reference grid, created at the reference's fixed capacity
+ * (200 x 200 / 400 x 400, main.c:201-209) and resized to the current grid_size. */
 static b200slam_map *slot_map(int slot, int rows, int cols)
 {
-    if (!g_maps[slot].map || g_maps[slot].rows != rows || g_maps[slot].cols != cols) {
-        if (g_maps[slot].map) b200slam_map_destroy(ctx(), g_maps[slot].map);
-        g_maps[slot].map = NULL;
-        int rc = b200slam_map_create(ctx(), rows, cols, &g_maps[slot].map);
+    const int cap = slot ? 400 : 200;
+    if (rows > cap || cols > cap) {
+        fprintf(stderr, "libb200slam_dropin: grid %d x %d exceeds the reference capacity %d x %d\n", rows, cols, cap, cap);
+        abort();
+    }
+    if (!g_maps[slot].map) {
+        int rc = b200slam_map_create(ctx(), cap, cap, &g_maps[slot].map);
         if (rc) die("b200slam_map_create", rc);
+        g_maps[slot].host_field = NULL;
+    }
+    if (g_maps[slot].rows != rows || g_maps[slot].cols != cols) {
+        int rc = b200slam_map_resize(g_maps[slot].map, rows, cols);
+        if (rc) die("b200slam_map_resize", rc);
         g_maps[slot].rows = rows;
         g_maps[slot].cols = cols;
         g_maps[slot].host_field = NULL;
@@ -159,6 +181,51 @@ void FastMatch(const float POSE[3], const float searchResolution[3])
 void FastMatch2(const float POSE[3], const float searchResolution[3])
 {
     fastmatch_common(1, POSE, searchResolution);
+}
+
+/* main.c:271-363: both levels rasterised and transformed on the device.  Everything the
+ * reference function leaves behind is reproduced: grid / grid2 (zeroed, then the 1s),
+ * grid_size, metric grids, pixel sizes, top-left corners. */
+static void occgrid_level(int slot, float pixel)
+{
+    const int S = slot ? 400 : 200;
+    int rows = 0, cols = 0;
+    float tl[2];
+    if (!g_maps[slot].map) slot_map(slot, S, S);
+    int rc = b200slam_map_rasterise(ctx(), g_maps[slot].map, local_map.x, local_map.y, local_map.size, pixel,
+                                    &rows, &cols, tl);
+    if (rc) die("b200slam_map_rasterise", rc);
+    g_maps[slot].rows = rows;
+    g_maps[slot].cols = cols;
+    rc = b200slam_map_edt(ctx(), g_maps[slot].map, 10.0f);                  /* main.c:355-356 */
+    if (rc) die("b200slam_map_edt", rc);
+    int *grid = slot ? &occ_grid.grid2[0][0] : &occ_grid.grid[0][0];
+    float *field = slot ? &occ_grid.metric_grid2[0][0] : &occ_grid.metric_grid[0][0];
+    memset(grid, 0, sizeof(int) * (size_t)S * S);                            /* main.c:319-320 */
+    rc = b200slam_map_download_occupancy(ctx(), g_maps[slot].map, grid, S);
+    if (rc) die("b200slam_map_download_occupancy", rc);
+    rc = b200slam_map_download_field(ctx(), g_maps[slot].map, field, S);
+    if (rc) die("b200slam_map_download_field", rc);
+    g_maps[slot].host_field = field;
+    if (slot) {
+        occ_grid.grid_size2[0] = rows; occ_grid.grid_size2[1] = cols;       /* main.c:316-317 */
+        occ_grid.pixel_size2 = pixel;
+        occ_grid.top_left_corner2[0] = tl[0]; occ_grid.top_left_corner2[1] = tl[1];
+    } else {
+        occ_grid.grid_size[0] = rows; occ_grid.grid_size[1] = cols;         /* main.c:313-314 */
+        occ_grid.pixel_size = pixel;
+        occ_grid.top_left_corner[0] = tl[0]; occ_grid.top_left_corner[1] = tl[1];
+    }
+}
+
+void OccupationalGrid(const float PIXELSIZE, const float PIXELSIZE2)
+{
+    if (!&local_map || !&occ_grid) {
+        fprintf(stderr, "libb200slam_dropin: OccupationalGrid needs the reference globals local_map / occ_grid\n");
+        abort();
+    }
+    occgrid_level(0, PIXELSIZE);
+    occgrid_level(1, PIXELSIZE2);
 }
 
 /* The host field array may be rewritten by someone other than our transform (tests do);

@@ -91,14 +91,31 @@ int b200slam_edt(b200slam_ctx *ctx, const int32_t *occ, int occ_stride, float *o
  * grid_size + pixel_size + top_left_corner). */
 int  b200slam_map_create(b200slam_ctx *ctx, int rows, int cols, b200slam_map **out);
 void b200slam_map_destroy(b200slam_ctx *ctx, b200slam_map *map);
+/* Changes the current size within the capacity the map was created with (the reference keeps
+ * fixed 200 x 200 / 400 x 400 arrays and a varying grid_size, main.c:200-213). */
+int  b200slam_map_resize(b200slam_map *map, int rows, int cols);
 /* pixel_size / top_left_corner = {minX, minY} (main.c:357-362). */
 int  b200slam_map_set_geometry(b200slam_map *map, float pixel_size, float top_left_x,
                                float top_left_y);
 int  b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const int32_t *occ,
                                    int stride);
+/* Rasterises map points into the occupancy grid ON THE DEVICE: one level of OccupationalGrid
+ * (Subsystem_1/main.c:271-354) -- bounding box of the points, 3-pixel margin, grid size
+ * round(extent / pixel) + 1, a 1 in every cell a point rounds into -- with the reference's float
+ * arithmetic (the bounding box and sizes are computed on the host exactly as main.c:272-305,
+ * the per-point cell indices on the GPU with IEEE division and roundf, main.c:332-353).
+ * The map was created with capacity rows x cols (200 x 200 / 400 x 400 in the reference); its
+ * current size, pixel size and top-left corner become those of the rasterised grid
+ * (grid_size, pixel_size, top_left_corner: main.c:313-314, 357-362), returned through
+ * rows / cols / top_left (each optional).  B200SLAM_ERR_ARG when the grid exceeds the capacity.
+ * Only 8 bytes per point cross PCIe instead of 4 bytes per cell.  x, y: host arrays. */
+int  b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x, const float *y,
+                            int npoints, float pixel_size, int *rows, int *cols, float top_left[2]);
 /* occ -> field entirely on the device (async on the context's stream). */
 int  b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist);
 int  b200slam_map_download_field(b200slam_ctx *ctx, b200slam_map *map, float *out, int stride);
+/* The int32 occupancy of the current rows x cols (e.g. after b200slam_map_rasterise). */
+int  b200slam_map_download_occupancy(b200slam_ctx *ctx, b200slam_map *map, int32_t *out, int stride);
 /* Install a precomputed distance field (e.g. one produced by another GPU). */
 int  b200slam_map_upload_field(b200slam_ctx *ctx, b200slam_map *map, const float *field,
                                int stride);

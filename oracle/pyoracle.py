@@ -92,6 +92,21 @@ class Oracle:
         fn(_ip(occ), cols, _fp(out), cols, rows, cols, C.c_float(max_dist))
         return out
 
+    def occupational_grid(self, x, y, pixel_size: float, cap_rows: int, cap_cols: int):
+        """-> (grid[rows][cols] int32, (min_x, min_y)) per Subsystem_1/main.c:271-354 (one level)."""
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.ascontiguousarray(y, np.float32)
+        grid = np.empty((cap_rows, cap_cols), np.int32)
+        rows, cols = C.c_int(0), C.c_int(0)
+        mx, my = C.c_float(0), C.c_float(0)
+        self.lib.orc_occupational_grid.restype = C.c_int
+        rc = self.lib.orc_occupational_grid(_fp(x), _fp(y), len(x), C.c_float(pixel_size), _ip(grid), cap_cols,
+                                            cap_rows, cap_cols, C.byref(rows), C.byref(cols), C.byref(mx),
+                                            C.byref(my))
+        if rc != 0:
+            raise ValueError(f"grid {rows.value} x {cols.value} exceeds capacity {cap_rows} x {cap_cols}")
+        return grid[:rows.value, :cols.value].copy(), (np.float32(mx.value), np.float32(my.value))
+
     # -- scoring -----------------------------------------------------------
     @staticmethod
     def make_map(field: np.ndarray, pixel_size: float, top_left, rows=None, cols=None):
@@ -194,6 +209,10 @@ class RefFastMatchParameters(C.Structure):  # main.c:374-378
     _fields_ = [("pose", C.c_float * 3), ("bestHits", C.c_float * 2500), ("bestHits_size", C.c_int)]
 
 
+class RefLocalMap(C.Structure):  # main.c:147-151
+    _fields_ = [("x", C.c_float * 25000), ("y", C.c_float * 25000), ("size", C.c_int)]
+
+
 def reference_available() -> bool:
     return all(os.path.exists(os.path.join(REF_DIR, f))
                for f in ("libref_main.so", "libref_accel.so", "libref_edtfrag.so"))
@@ -251,6 +270,32 @@ class Reference:
             g.grid_size[0], g.grid_size[1] = rows, cols
             g.pixel_size = pixel_size
             g.top_left_corner[0], g.top_left_corner[1] = top_left
+
+    def occupational_grid(self, x, y, pixel_size: float, pixel_size2: float):
+        """Runs the reference OccupationalGrid (main.c:271-363) on its own globals: local_map <- (x, y).
+        Returns [(grid, field, (min_x, min_y)), (grid2, field2, (min_x2, min_y2))]."""
+        n = len(x)
+        assert n <= 25000
+        lm = RefLocalMap.in_dll(self.lib, "local_map")
+        xs = np.zeros(25000, np.float32); xs[:n] = x
+        ys = np.zeros(25000, np.float32); ys[:n] = y
+        C.memmove(lm.x, xs.ctypes.data, xs.nbytes)
+        C.memmove(lm.y, ys.ctypes.data, ys.nbytes)
+        lm.size = n
+        f = self.lib.OccupationalGrid
+        f.restype = None
+        f.argtypes = [C.c_float, C.c_float]
+        f(C.c_float(pixel_size), C.c_float(pixel_size2))
+        g = self.occ_grid
+        out = []
+        for fine in (False, True):
+            S = 400 if fine else 200
+            rows, cols = (g.grid_size2[0], g.grid_size2[1]) if fine else (g.grid_size[0], g.grid_size[1])
+            grid = np.ctypeslib.as_array(g.grid2 if fine else g.grid).reshape(S, S)[:rows, :cols].copy()
+            field = np.ctypeslib.as_array(g.metric_grid2 if fine else g.metric_grid).reshape(S, S)[:rows, :cols].copy()
+            tl = g.top_left_corner2 if fine else g.top_left_corner
+            out.append((grid, field, (np.float32(tl[0]), np.float32(tl[1]))))
+        return out
 
     def set_scan(self, x, y):
         n = len(x)

@@ -402,3 +402,48 @@ void orc_pyramid_match(const orc_map *maps, int levels, const float *scan_x,
         seed[2] = results[l].best_pose[2];
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* Occupancy-grid rasterisation                                               */
+/* ------------------------------------------------------------------------- */
+
+int orc_occupational_grid(const float *x, const float *y, int n, float pixel_size, int32_t *grid,
+                          int stride, int cap_rows, int cap_cols, int *rows, int *cols,
+                          float *min_x, float *min_y)
+{
+    /* main.c:272-289: bounding box (strict compares, seeded with point 0) */
+    float minXY[2] = {x[0], y[0]};
+    float maxXY[2] = {x[0], y[0]};
+    for (int a = 0; a < n; a++) {
+        if (x[a] < minXY[0]) minXY[0] = x[a];
+        if (x[a] > maxXY[0]) maxXY[0] = x[a];
+        if (y[a] < minXY[1]) minXY[1] = y[a];
+        if (y[a] > maxXY[1]) maxXY[1] = y[a];
+    }
+    /* main.c:296-305: 3-pixel margin, size = round(extent / pixel) + 1 */
+    int Sgrid[2];
+    for (int a = 0; a < 2; a++) {
+        minXY[a] -= (3 * pixel_size);
+        maxXY[a] += (3 * pixel_size);
+        Sgrid[a] = (int)roundf((maxXY[a] - minXY[a]) / pixel_size) + 1;
+    }
+    *cols = Sgrid[0];                       /* grid_size[1] = Sgrid[0], main.c:313-314 */
+    *rows = Sgrid[1];
+    *min_x = minXY[0];                      /* top_left_corner, main.c:359-360 */
+    *min_y = minXY[1];
+    if (Sgrid[0] > cap_cols || Sgrid[1] > cap_rows) return -1;
+    for (int r = 0; r < cap_rows; ++r)      /* main.c:319 memset of the whole array */
+        for (int c = 0; c < cap_cols; ++c) grid[(size_t)r * stride + c] = 0;
+    /* main.c:332-353 */
+    for (int a = 0; a < n; a++) {
+        float x_minus_minX = x[a] - minXY[0];
+        float y_minus_minY = y[a] - minXY[1];
+        int hx = (int)roundf(x_minus_minX / pixel_size) + 1;
+        int hy = (int)roundf(y_minus_minY / pixel_size) + 1;
+        int idx = (((hy - 1) * Sgrid[0]) + hx) - 1;
+        int idx_row = idx / Sgrid[0];
+        int idx_col = idx % Sgrid[0];
+        grid[(size_t)idx_row * stride + idx_col] = 1;
+    }
+    return 0;
+}

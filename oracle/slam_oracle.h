@@ -16,6 +16,8 @@
  *     reference's own functions compiled unmodified into oracle/_ref/ (see
  *     oracle/Makefile) and against fixtures under tests/golden/ generated from
  *     those same objects (tests/golden/make_golden.py).
+ *   - orc_occupational_grid is PINNED the same way (reference OccupationalGrid run on its own
+ *     globals, both pixel sizes).
  *   - orc_score_poses restates the same per-beam arithmetic for an arbitrary pose
  *     list; it is pinned through the lattice (a lattice expanded to a pose list
  *     must give identical scores).
@@ -34,6 +36,16 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* ---- occupancy-grid rasterisation ---------- */
+
+/* One level of OccupationalGrid, Subsystem_1/main.c:271-354: bounding box of the points,
+ * 3-pixel margin, grid size, and a 1 in every cell a point rounds into.  `grid` is
+ * [cap_rows][stride]; the whole capacity is zeroed first (main.c:319).  Returns 0, or -1 when
+ * the grid does not fit the capacity (the reference would overflow its fixed arrays). */
+int orc_occupational_grid(const float *x, const float *y, int n, float pixel_size, int32_t *grid,
+                          int stride, int cap_rows, int cap_cols, int *rows, int *cols,
+                          float *min_x, float *min_y);
 
 /* ---- distance transform ------------------------------------------------- */
 

@@ -232,3 +232,47 @@ def test_graph_replay_matches_eager(ctx, oracle, synth):
         ctx.graph_destroy(g)
     finally:
         m.close()
+
+
+@pytest.mark.gpu
+def test_config3_full_size_4m_x_1080_properties(ctx, oracle, synth, b200slam):
+    """BASELINE configs[3] at full size (8192^2 map, 256 x 128 x 128 = 4 194 304 poses x 1080 beams):
+    4.5 G evaluations are out of the oracle's reach, so parity is checked through properties --
+    (1) the oracle's own score of the winning pose equals the GPU's best score bit for bit,
+    (2) the full GPU score table is consistent with the winner (min, lowest index among equals),
+    (3) two oracle-scored theta slices (32 768 candidates each) match the table bit for bit,
+    (4) eight row shards merge to the same winner (the multi-GPU partition, run on one GPU)."""
+    w = synth.make_workload("config3")
+    rows, cols = w["occ"].shape
+    n = w["n"]
+    m = ctx.new_map(rows, cols)
+    try:
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+        field = m.download_field()
+        ctx.scan_upload(w["scan_x"], w["scan_y"])
+        res, scores, _ = ctx.score_lattice(m, w["pose0"], w["step"], n, want_scores=True)
+        om = oracle.make_map(field, w["pixel"], w["top_left"])
+        # (1) winner re-scored by the oracle as a single pose
+        _, oscore, ohits = oracle.score_poses(om, w["scan_x"], w["scan_y"], res.pose().reshape(1, 3))
+        assert bits(oscore)[0] == bits(np.float32(res.best_score)) and int(ohits[0]) == res.best_hits
+        # (2) table vs winner
+        assert bits(scores[res.best_index]) == bits(np.float32(res.best_score))
+        assert res.best_index == int(np.flatnonzero(scores == scores.min())[0])
+        # (3) oracle on two theta slices: lattice of one theta centred on that slice's angle
+        per_theta = n[1] * n[2]
+        for ith in (0, 173):
+            th = b200slam.lattice_value(float(w["pose0"][2]), float(w["step"][2]), ith, n[0])
+            pose_slice = np.array([w["pose0"][0], w["pose0"][1], th], np.float32)
+            _, oslice, _ = oracle.score_lattice(om, w["scan_x"], w["scan_y"], pose_slice, w["step"], (1, n[1], n[2]))
+            assert np.array_equal(bits(oslice), bits(scores[ith * per_theta:(ith + 1) * per_theta]))
+        # (4) shards
+        nrows = n[0] * n[1]
+        keys = []
+        for r in range(8):
+            rb, re = b200slam.shard_range(nrows, 8, r)
+            part = ctx.score_lattice_rows(m, w["pose0"], w["step"], n, rb, re)
+            keys.append(b200slam.pack_key(part.best_score, part.best_index))
+        score, index = b200slam.unpack_key(b200slam.merge_keys(np.array(keys, np.uint64)))
+        assert index == res.best_index and np.float32(score) == np.float32(res.best_score)
+    finally:
+        m.close()
