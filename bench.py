@@ -118,12 +118,55 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
-def cpu_sample(w, synth, budget_s: float = 12.0, want_kind: str | None = None) -> dict:
-    """Times the reference CPU path on a bounded sample of workload `w` (1 core: the reference
-    is single-threaded).  kind "reference": the reference's own euclidean_distance_transform2
-    and FastMatch2, compiled unmodified (oracle/_ref); kind "port": the oracle restatement."""
+def _cpu_worker(job):
+    """One host core: the reference's own euclidean_distance_transform2 + FastMatch2 (or the oracle
+    port) on the sample `job` describes.  Runs in its own process: the reference keeps its state in
+    globals.  -> (cells, t_edt, evals, t_match, kind)"""
+    crop, pixel, tl, sx, sy, pose0, step, n, budget_s, use_ref = job
     from oracle import pyoracle
+    S = crop.shape[0]
+    nb = len(sx)
+    res3 = np.array([step[0], step[1], step[2]], np.float32)
+    if use_ref:
+        ref = pyoracle.Reference("accel")
+        t0 = time.perf_counter()
+        field = ref.edt(crop, fine=True)                      # reference EDT2, <= 400 x 400
+        t_edt = time.perf_counter() - t0
+        ref.set_map(field, pixel, tl, fine=True)
+        ref.set_scan(sx, sy)
+        calls, t0 = 0, time.perf_counter()
+        while True:
+            ref.fastmatch(pose0, res3, fine=True)             # 5 sweeps x 27 candidates
+            calls += 1
+            t_fm = time.perf_counter() - t0
+            if t_fm > max(1.0, budget_s - t_edt) or calls >= 20000:
+                break
+        return S * S, t_edt, calls * 135 * nb, t_fm, "reference"
     orc = pyoracle.Oracle()
+    t0 = time.perf_counter()
+    field = orc.edt(crop, variant="scatter")                  # the reference's scatter-form loop nest
+    t_edt = time.perf_counter() - t0
+    om = orc.make_map(field, pixel, tl)
+    nn = (min(n[0], 16), n[1], n[2])
+    t0 = time.perf_counter()
+    orc.score_lattice(om, sx, sy, pose0, step, nn, want_scores=False)
+    t_fm = time.perf_counter() - t0
+    return S * S, t_edt, nn[0] * nn[1] * nn[2] * nb, t_fm, "port"
+
+
+def host_cores() -> int:
+    return max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+
+
+def cpu_sample(w, synth, budget_s: float = 12.0, want_kind: str | None = None, cores: int | None = None,
+               pool=None) -> dict:
+    """Times the reference CPU path on a bounded sample of workload `w`.  The reference is a
+    single-threaded program, so "all host threads" means one independent copy per core (separate
+    processes; the work is embarrassingly parallel over candidates / grid tiles) and the rates add.
+    kind "reference": the reference's own euclidean_distance_transform2 and FastMatch2, compiled
+    unmodified (oracle/_ref); kind "port": the oracle restatement."""
+    import multiprocessing as mp
+    from oracle import pyoracle
     rows, cols = w["occ"].shape
     n = w["n"]
     nb_full = len(w["scan_x"])
@@ -136,46 +179,32 @@ def cpu_sample(w, synth, budget_s: float = 12.0, want_kind: str | None = None) -
     pixel = float(w["pixel"])
     tl = (np.float32(w["top_left"][0] + c0 * pixel), np.float32(w["top_left"][1] + r0 * pixel))
     nb = min(nb_full, 1079)
-    sx, sy = w["scan_x"][:nb], w["scan_y"][:nb]
-    res3 = np.array([w["step"][0], w["step"][1], w["step"][2]], np.float32)
-    if use_ref:
-        ref = pyoracle.Reference("accel")
-        t0 = time.perf_counter()
-        field = ref.edt(crop, fine=True)                      # reference EDT2, <= 400 x 400
-        t_edt = time.perf_counter() - t0
-        ref.set_map(field, pixel, tl, fine=True)
-        ref.set_scan(sx, sy)
-        calls, t0 = 0, time.perf_counter()
-        while True:
-            ref.fastmatch(w["pose0"], res3, fine=True)        # 5 sweeps x 27 candidates
-            calls += 1
-            t_fm = time.perf_counter() - t0
-            if t_fm > max(1.0, budget_s - t_edt) or calls >= 20000:
-                break
-        evals = calls * 135 * nb
-        kind = "reference"
-        what = (f"reference euclidean_distance_transform2 on a {S}x{S} crop ({t_edt:.3f} s) + {calls} x "
-                f"reference FastMatch2 (135 candidate evals x {nb} beams each, {t_fm:.3f} s)")
+    sx, sy = np.array(w["scan_x"][:nb]), np.array(w["scan_y"][:nb])
+    if cores is None:
+        cores = host_cores()
+    job = (crop, pixel, tl, sx, sy, np.array(w["pose0"]), np.array(w["step"]), tuple(n), budget_s, use_ref)
+    if pool is not None:
+        results = pool.map(_cpu_worker, [job] * cores)
+    elif cores == 1:
+        results = [_cpu_worker(job)]
     else:
-        t0 = time.perf_counter()
-        field = orc.edt(crop, variant="scatter")              # the reference's scatter-form loop nest
-        t_edt = time.perf_counter() - t0
-        om = orc.make_map(field, pixel, tl)
-        nn = (min(n[0], 16), n[1], n[2])
-        t0 = time.perf_counter()
-        orc.score_lattice(om, sx, sy, w["pose0"], w["step"], nn, want_scores=False)
-        t_fm = time.perf_counter() - t0
-        evals = nn[0] * nn[1] * nn[2] * nb
-        kind = "port"
-        what = (f"oracle scatter-form EDT on a {S}x{S} crop ({t_edt:.3f} s) + oracle lattice "
-                f"{nn[0]}x{nn[1]}x{nn[2]} x {nb} beams ({t_fm:.3f} s)")
-    evals_per_s = evals / t_fm
-    cells_per_s = S * S / t_edt
+        with mp.get_context("spawn").Pool(cores) as own:
+            results = own.map(_cpu_worker, [job] * cores)
+    kind = results[0][4]
+    cells_per_s = sum(c / t for c, t, _, _, _ in results)
+    evals_per_s = sum(e / t for _, _, e, t, _ in results)
+    t_edt = max(r[1] for r in results)
+    t_fm = max(r[3] for r in results)
+    calls = results[0][2] // (135 * nb) if use_ref else 0
+    what = (f"per core: reference euclidean_distance_transform2 on a {S}x{S} crop ({t_edt:.3f} s) + ~{calls} x reference "
+            f"FastMatch2 (135 candidate evals x {nb} beams each, {t_fm:.3f} s)") if use_ref else (
+            f"per core: oracle scatter-form EDT on a {S}x{S} crop ({t_edt:.3f} s) + oracle lattice x {nb} beams ({t_fm:.3f} s)")
     # one full step on this CPU at the sampled rates (the EDT term is generous to the
     # reference: its loop nest is O(occupied x cells), so it slows down with area)
     t_step = cells_full / cells_per_s + evals_full / evals_per_s
-    return {"value": evals_full / t_step, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": what + "; value = full-step evals / (cells/rate_edt + evals/rate_match), extrapolated",
+    return {"value": evals_full / t_step, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": what + f"; {cores} independent copies, rates summed; value = full-step evals / "
+                             "(cells/rate_edt + evals/rate_match), extrapolated",
             "match_evals_per_s": evals_per_s, "edt_mcells_per_s": cells_per_s / 1e6,
             "host_cpus": os.cpu_count()}
 
@@ -186,16 +215,19 @@ def run_reference_arm(args, synth):
         return
     w = synth.make_workload(args.workload)
     K, W = args.steps, args.warmup
+    import multiprocessing as mp
     per = max(0.4, min(4.0, 150.0 / max(K + W, 1)))
     vals, last = [], None
+    cores = host_cores()
     t_all = time.perf_counter()
-    for i in range(W + K):
-        s = cpu_sample(w, synth, budget_s=per)
-        if i >= W:
-            vals.append(s["value"])
-        last = s
-        if time.perf_counter() - t_all > 240 and len(vals) >= 3:
-            break
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for i in range(W + K):
+            s = cpu_sample(w, synth, budget_s=per, cores=cores, pool=pool)
+            if i >= W:
+                vals.append(s["value"])
+            last = s
+            if time.perf_counter() - t_all > 240 and len(vals) >= 3:
+                break
     v = statistics.median(vals)
     n = w["n"]
     evals_full = n[0] * n[1] * n[2] * len(w["scan_x"])
