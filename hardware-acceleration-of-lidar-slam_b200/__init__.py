@@ -106,6 +106,10 @@ def load_library() -> C.CDLL:
         "b200slam_event_record": (i, [vp, i]),
         "b200slam_event_elapsed_ms": (i, [vp, i, i, c_float_p]),
         "b200slam_weights_resample": (i, [vp, f, C.c_uint32, vp, c_u64_p, vp, c_i64_p, c_i64_p]),
+        "b200slam_particles_upload": (i, [vp, vp, vp, vp, C.c_int64]),
+        "b200slam_particles_score_async": (i, [vp, vp]),
+        "b200slam_particles_resample_async": (i, [vp, f, C.c_uint32]),
+        "b200slam_particles_download": (i, [vp, vp, vp, vp, vp]),
         "b200slam_resample_owned_slots": (None, [C.c_uint64, C.c_int64, C.c_uint32, C.c_uint64, C.c_uint64,
                                                  c_i64_p, c_i64_p]),
         "b200slam_pyramid_match": (i, [vp, C.POINTER(vp), i, c_float_p, c_float_p, c_int_p, C.POINTER(Match)]),
@@ -381,6 +385,34 @@ class Context:
         self._check(self.L.b200slam_weights_resample(self.h, beta, u0_q32, w.ctypes.data if want_weights else None,
                                                      C.byref(W), anc.ctypes.data, C.byref(kb), C.byref(kc)))
         return w, int(W.value), anc[:kc.value], kb.value, kc.value
+
+    # -- device-resident particle set (single GPU) ----------------------------------------
+    def particles_upload(self, poses, ct=None, st=None):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 3)
+        ctp = np.ascontiguousarray(ct, np.float32) if ct is not None else None
+        stp = np.ascontiguousarray(st, np.float32) if st is not None else None
+        self._check(self.L.b200slam_particles_upload(self.h, poses.ctypes.data,
+                                                     ctp.ctypes.data if ctp is not None else None,
+                                                     stp.ctypes.data if stp is not None else None, poses.shape[0]))
+        self._P = poses.shape[0]
+
+    def particles_score_async(self, m: Map):
+        self._check(self.L.b200slam_particles_score_async(self.h, m.h))
+
+    def particles_resample_async(self, beta: float, u0_q32: int):
+        self._check(self.L.b200slam_particles_resample_async(self.h, beta, u0_q32))
+
+    def particles_download(self, want_scores=True, want_weights=True, want_ancestors=True):
+        P = self._P
+        poses = np.empty((P, 3), np.float32)
+        sc = np.empty(P, np.float32) if want_scores else None
+        w = np.empty(P, np.float32) if want_weights else None
+        a = np.empty(P, np.int32) if want_ancestors else None
+        self._check(self.L.b200slam_particles_download(self.h, poses.ctypes.data,
+                                                       sc.ctypes.data if want_scores else None,
+                                                       w.ctypes.data if want_weights else None,
+                                                       a.ctypes.data if want_ancestors else None))
+        return poses, sc, w, a
 
     def pyramid_match(self, maps, pose0, steps, ns):
         Ln = len(maps)

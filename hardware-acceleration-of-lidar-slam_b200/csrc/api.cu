@@ -85,7 +85,7 @@ void b200slam_destroy(b200slam_ctx *ctx)
     cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match);
     cudaFree(ctx->d_keys); cudaFreeHost(ctx->h_keys); cudaFree(ctx->d_hit_values);
     cudaFree(ctx->d_scores);
-    cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
+    cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_pose_alt); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
     cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
     cudaFree(ctx->d_ancestors); cudaFree(ctx->d_wsum); cudaFreeHost(ctx->h_wsum);
     cudaFree(ctx->d_edt_scratch);
@@ -617,25 +617,22 @@ int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3]
 
 /* ---- pose lists / particles ---------------------------------------------------- */
 
-int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *poses, const float *ct,
-                         const float *st, int64_t P, int64_t index_base, float *scores, int32_t *hits,
-                         b200slam_match *result)
+// Sizes the particle buffers for P poses and stages poses (+ cos/sin from the host libm when not
+// given, main.c:434-435) into the device SoA x | y | ct | st | theta.
+static int stage_poses(b200slam_ctx *ctx, const float *poses, const float *ct, const float *st, int64_t P)
 {
-    if (!ctx || !map || P < 0 || (P > 0 && !poses)) return B200SLAM_ERR_ARG;
-    if (!map->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
-    if (!ctx->d_scan_x) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan uploaded");
-    if (P + index_base > 0xffffffffll) return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "too many poses");
     if ((size_t)P > ctx->pose_cap) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
+        cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_pose_alt); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
         cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
-        ctx->d_pose_soa = nullptr; ctx->d_hits = nullptr; ctx->h_pose_stage = nullptr;
+        ctx->d_pose_soa = nullptr; ctx->d_pose_alt = nullptr; ctx->d_hits = nullptr; ctx->h_pose_stage = nullptr;
         ctx->d_q = nullptr; ctx->d_block_sums = nullptr; ctx->d_weights = nullptr;
         ctx->pose_cap = 0;
         const size_t cap = ((size_t)P + 4095) & ~(size_t)4095;
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_pose_soa, sizeof(float) * 4 * cap));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_pose_soa, sizeof(float) * 5 * cap));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_pose_alt, sizeof(float) * 5 * cap));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_hits, sizeof(int32_t) * cap));
-        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_pose_stage, sizeof(float) * 4 * cap, cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_pose_stage, sizeof(float) * 5 * cap, cudaHostAllocDefault));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_q, sizeof(unsigned long long) * cap));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_block_sums, sizeof(unsigned long long) * (cap / 1024 + 2)));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_weights, sizeof(float) * cap));
@@ -650,19 +647,42 @@ int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *pose
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_scores, sizeof(float) * cap));
         ctx->scores_cap = cap;
     }
+    if ((size_t)P > ctx->anc_cap) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_ancestors);
+        ctx->d_ancestors = nullptr;
+        ctx->anc_cap = 0;
+        const size_t cap = ((size_t)P + 4095) & ~(size_t)4095;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_ancestors, sizeof(int32_t) * cap));
+        ctx->anc_cap = cap;
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // staging buffer free again
     const size_t cap = ctx->pose_cap;
-    float *hx = ctx->h_pose_stage, *hy = hx + cap, *hct = hy + cap, *hst = hct + cap;
+    float *hx = ctx->h_pose_stage, *hy = hx + cap, *hct = hy + cap, *hst = hct + cap, *hth = hst + cap;
     for (int64_t p = 0; p < P; ++p) {
         hx[p] = poses[3 * p + 0];
         hy[p] = poses[3 * p + 1];
+        hth[p] = poses[3 * p + 2];
         hct[p] = ct ? ct[p] : cosf(poses[3 * p + 2]);                     // main.c:434
         hst[p] = st ? st[p] : sinf(poses[3 * p + 2]);                     // main.c:435
     }
     if (P > 0)
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pose_soa, ctx->h_pose_stage, sizeof(float) * 4 * cap,
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pose_soa, ctx->h_pose_stage, sizeof(float) * 5 * cap,
                                       cudaMemcpyHostToDevice, ctx->stream));
-    int rc = poses_launch(ctx, map, P, index_base, ctx->d_scores, ctx->d_hits);
+    return B200SLAM_OK;
+}
+
+int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *poses, const float *ct,
+                         const float *st, int64_t P, int64_t index_base, float *scores, int32_t *hits,
+                         b200slam_match *result)
+{
+    if (!ctx || !map || P < 0 || (P > 0 && !poses)) return B200SLAM_ERR_ARG;
+    if (!map->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
+    if (!ctx->d_scan_x) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan uploaded");
+    if (P + index_base > 0xffffffffll) return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "too many poses");
+    int rc = stage_poses(ctx, poses, ct, st, P);
+    if (rc) return rc;
+    rc = poses_launch(ctx, map, P, index_base, ctx->d_scores, ctx->d_hits);
     if (rc) return rc;
     ctx->last.valid = true;
     ctx->last.is_poses = true;
@@ -681,6 +701,72 @@ int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *pose
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     ctx->last_poses_host = nullptr;      // caller's buffer is only borrowed during this call
+    return B200SLAM_OK;
+}
+
+/* ---- device-resident particle set ------------------------------------------------------- */
+
+int b200slam_particles_upload(b200slam_ctx *ctx, const float *poses, const float *ct, const float *st, int64_t P)
+{
+    if (!ctx || P <= 0 || !poses || P > 0x7fffffffll) return B200SLAM_ERR_ARG;
+    int rc = stage_poses(ctx, poses, ct, st, P);
+    if (rc) return rc;
+    ctx->last_P = P;
+    ctx->last_index_base = 0;
+    ctx->last_poses_host = nullptr;
+    ctx->last.valid = false;
+    return B200SLAM_OK;
+}
+
+int b200slam_particles_score_async(b200slam_ctx *ctx, b200slam_map *map)
+{
+    if (!ctx || !map) return B200SLAM_ERR_ARG;
+    if (!map->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
+    if (!ctx->d_scan_x) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan uploaded");
+    if (ctx->last_P <= 0 || !ctx->d_pose_soa) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no particles uploaded");
+    int rc = poses_launch(ctx, map, ctx->last_P, 0, ctx->d_scores, ctx->d_hits);
+    if (rc) return rc;
+    ctx->last.valid = true;
+    ctx->last.is_poses = true;
+    ctx->last.gathered = false;
+    ctx->last_index_base = 0;
+    return B200SLAM_OK;
+}
+
+int b200slam_particles_resample_async(b200slam_ctx *ctx, float beta, uint32_t u0_q32)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    if (!ctx->last.valid || !ctx->last.is_poses)
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_particles_score_async must run first");
+    if (ctx->nccl_comm && ctx->nranks > 1)
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE,
+                                  "the resident particle set is single-GPU; use b200slam_weights_resample with a communicator");
+    return particles_resample_resident(ctx, ctx->last_P, beta, u0_q32);
+}
+
+int b200slam_particles_download(b200slam_ctx *ctx, float *poses, float *scores, float *weights, int32_t *ancestors)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    const int64_t P = ctx->last_P;
+    if (P <= 0 || !ctx->d_pose_soa) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no particles uploaded");
+    const size_t cap = ctx->pose_cap;
+    if (poses) {
+        float *h = ctx->h_pose_stage;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_pose_soa, sizeof(float) * 2 * cap, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(h + 4 * cap, ctx->d_pose_soa + 4 * cap, sizeof(float) * (size_t)P,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t p = 0; p < P; ++p) {
+            poses[3 * p + 0] = h[p];
+            poses[3 * p + 1] = h[cap + p];
+            poses[3 * p + 2] = h[4 * cap + p];
+        }
+    }
+    if (scores) CUDA_TRY(ctx, cudaMemcpyAsync(scores, ctx->d_scores, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weights) CUDA_TRY(ctx, cudaMemcpyAsync(weights, ctx->d_weights, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ancestors) CUDA_TRY(ctx, cudaMemcpyAsync(ancestors, ctx->d_ancestors, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return B200SLAM_OK;
 }
 

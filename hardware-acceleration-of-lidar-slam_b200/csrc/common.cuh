@@ -99,7 +99,8 @@ struct b200slam_ctx {
     size_t scores_cap = 0;       // floats
 
     // pose-list scoring (particles)
-    float *d_pose_soa = nullptr;  // x | y | ct | st, each [pose_cap]
+    float *d_pose_soa = nullptr;  // x | y | ct | st | theta, each [pose_cap]
+    float *d_pose_alt = nullptr;  // same layout: target of the resampling gather (buffers swap)
     size_t pose_cap = 0;
     int32_t *d_hits = nullptr;
     float *h_pose_stage = nullptr;   // pinned staging [4][pose_cap]
@@ -175,6 +176,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
 int poses_launch(b200slam_ctx *ctx, const b200slam_map *map, int64_t P, int64_t index_base,
                  float *d_scores, int32_t *d_hits);
 
+int particles_resample_resident(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32);
 int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32,
                                float *weights, uint64_t *wsum, int32_t *ancestors,
                                int64_t *k_begin, int64_t *k_count);

@@ -113,7 +113,7 @@ block_sums_scan_kernel(unsigned long long *__restrict__ block_sums, int nb,
         if (threadIdx.x == 1023) carry = before + inc;
         __syncthreads();
     }
-    if (threadIdx.x == 0) out_total[0] = carry;
+    if (threadIdx.x == 0) { out_total[0] = carry; out_total[1] = carry; }   // [1]: global W (one GPU: the same)
 }
 
 // In-place inclusive prefix C_i (local to this rank) and normalised weights.
@@ -172,6 +172,36 @@ resample_kernel(const unsigned long long *__restrict__ C, long long N_local, lon
     ancestors[s] = (int)(lo + index_base);
 }
 
+// Single-GPU variant for the device-resident particle set: the weight sum is read on the device
+// (no host round trip), every slot belongs to this rank, and the offspring is gathered right
+// away: particle k of `dst` <- particle ancestors[k] of `src` (SoA x | y | ct | st | theta).
+__global__ void __launch_bounds__(256)
+resample_gather_kernel(const unsigned long long *__restrict__ C, long long N,
+                       const unsigned long long *__restrict__ totals, unsigned int u0_q32,
+                       int *__restrict__ ancestors, const float *__restrict__ src, float *__restrict__ dst,
+                       size_t cap)
+{
+    __shared__ unsigned long long sWd, sWm, sU;
+    if (threadIdx.x == 0) {
+        const unsigned long long W = totals[0];
+        sWd = W / (unsigned long long)N;
+        sWm = W % (unsigned long long)N;
+        sU = (sWd >> 32) * u0_q32 + (((sWd & 0xffffffffull) * u0_q32) >> 32);    // (Wd * u0) >> 32, exact
+    }
+    __syncthreads();
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const unsigned long long T = sU + (unsigned long long)k * sWd + ((unsigned long long)k * sWm) / (unsigned long long)N;
+    long long lo = 0, hi = N - 1;                      // first i with C[i] > T
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (C[mid] > T) hi = mid; else lo = mid + 1;
+    }
+    ancestors[k] = (int)lo;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) dst[f * cap + k] = src[f * cap + lo];
+}
+
 // number of slots k in [0, N) with T_k < c  (T_k is non-decreasing in k)
 long long slots_below(unsigned long long c, unsigned long long U, unsigned long long Wd,
                       unsigned long long Wm, long long N)
@@ -187,6 +217,26 @@ long long slots_below(unsigned long long c, unsigned long long U, unsigned long 
 }
 
 }  // namespace
+
+int particles_resample_resident(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32)
+{
+    if (N <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scored poses");
+    const int nb = (int)((N + PT_BLOCK - 1) / PT_BLOCK);
+    weights_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_scores, N, beta, &ctx->d_match->key, 1, ctx->d_q,
+                                                       ctx->d_block_sums);
+    LAUNCH_CHECK(ctx);
+    block_sums_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums, nb, ctx->d_wsum);
+    LAUNCH_CHECK(ctx);
+    prefix_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_q, N, ctx->d_block_sums, ctx->d_wsum, ctx->d_weights);
+    LAUNCH_CHECK(ctx);
+    resample_gather_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->d_q, N, ctx->d_wsum, u0_q32, ctx->d_ancestors, ctx->d_pose_soa, ctx->d_pose_alt, ctx->pose_cap);
+    LAUNCH_CHECK(ctx);
+    float *t = ctx->d_pose_soa;          // the offspring is the resident set now
+    ctx->d_pose_soa = ctx->d_pose_alt;
+    ctx->d_pose_alt = t;
+    return B200SLAM_OK;
+}
 
 int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32,
                                float *weights, uint64_t *wsum, int32_t *ancestors,

@@ -209,6 +209,23 @@ int b200slam_weights_resample(b200slam_ctx *ctx, float beta, uint32_t u0_q32, fl
                               uint64_t *wsum, int32_t *ancestors, int64_t *k_begin,
                               int64_t *k_count);
 
+/* Device-resident particle set (single GPU): the particles stay in HBM across filter steps,
+ * nothing crosses PCIe per step, and every call below only queues kernels on the context's
+ * stream (capturable in a CUDA graph).
+ *   upload            poses[P][3] (+ optional ct/st, else host libm) -> device SoA
+ *   score_async       scores / hit counts of the resident particles against `map`; the arg-min
+ *                     is available through b200slam_match_fetch
+ *   resample_async    weights, normalisation, systematic resampling (same definition as
+ *                     b200slam_weights_resample) and the gather: the resident set is REPLACED by
+ *                     its resampled offspring (particle k <- old particle ancestors[k])
+ *   download          current poses and, optionally, the weights / ancestors of the last resample */
+int b200slam_particles_upload(b200slam_ctx *ctx, const float *poses, const float *ct, const float *st,
+                              int64_t P);
+int b200slam_particles_score_async(b200slam_ctx *ctx, b200slam_map *map);
+int b200slam_particles_resample_async(b200slam_ctx *ctx, float beta, uint32_t u0_q32);
+int b200slam_particles_download(b200slam_ctx *ctx, float *poses, float *scores, float *weights,
+                                int32_t *ancestors);
+
 /* ---- multi-resolution match (generalises the 2-level schedule of main.c:901-918) ---- */
 int b200slam_pyramid_match(b200slam_ctx *ctx, b200slam_map *const *maps, int levels,
                            const float pose0[3], const float *steps /*[levels][3]*/,

@@ -53,3 +53,38 @@ def test_resample_is_sorted_and_proportional(ctx, oracle, synth):
         assert abs(float(gw.astype(np.float64).sum()) - 1.0) < 1e-5
     finally:
         m.close()
+
+
+@pytest.mark.gpu
+def test_resident_particle_set_matches_oracle(ctx, oracle, synth):
+    """BASELINE configs[2] at full size, device resident: 100 000 particles x 720 beams scored,
+    weighted, normalised, resampled and gathered without leaving HBM; two consecutive filter
+    steps against the oracle (scores, weights, ancestors, offspring poses, arg-min)."""
+    w = synth.make_workload("config1")
+    rows, cols = w["occ"].shape
+    m = ctx.new_map(rows, cols)
+    try:
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+        field = m.download_field()
+        om = oracle.make_map(field, w["pixel"], w["top_left"])
+        sx, sy = synth.scan_fixed_count(w["occ"], float(w["pixel"]), w["top_left"], w["true_pose"], 720)
+        ctx.scan_upload(sx, sy)
+        P, beta = 100000, 0.05
+        poses = synth.particles_gaussian(P, w["true_pose"])
+        ctx.particles_upload(poses)
+        cur = poses
+        for step, u0 in enumerate((0x80000000, 0x12345678)):
+            ctx.particles_score_async(m)
+            best = ctx.match_fetch()
+            ctx.particles_resample_async(beta, u0)
+            gposes, gscores, gw, ganc = ctx.particles_download()
+            ores, oscores, _ = oracle.score_poses(om, sx, sy, cur)
+            ow, _, _, oanc = oracle.weights_resample(oscores, beta, u0)
+            assert np.array_equal(bits(gscores), bits(oscores)), f"step {step}: scores"
+            assert best.best_index == ores.best_index
+            assert np.array_equal(ganc, oanc), f"step {step}: ancestors"
+            assert np.array_equal(bits(gw), bits(ow)), f"step {step}: weights"
+            cur = cur[oanc]
+            assert np.array_equal(bits(gposes), bits(cur)), f"step {step}: offspring poses"
+    finally:
+        m.close()

@@ -101,6 +101,21 @@ def bench_poses(mod, synth, ctx):
     for _ in range(10):
         ctx.weights_resample(P, 0.05, 0x80000000, want_weights=True)
     t2 = time.perf_counter()
+    # device-resident filter step: score + weights + normalise + resample + gather, two steps per graph
+    ctx.particles_upload(poses)
+    for _ in range(2):
+        ctx.particles_score_async(m); ctx.particles_resample_async(0.05, 0x80000000)
+    ctx.sync()
+    ctx.graph_begin()
+    for _ in range(2):
+        ctx.particles_score_async(m); ctx.particles_resample_async(0.05, 0x80000000)
+    g = ctx.graph_end()
+    ms = time_loop(ctx, lambda i: ctx.graph_launch(g), 20) / 2
+    ctx.event_record(10); ctx.particles_score_async(m); ctx.event_record(11); ctx.particles_resample_async(0.05, 0x80000000)
+    ctx.event_record(12); ctx.sync()
+    print(f"particles 100k x 720 device-resident step: {ms * 1e3:.1f} us  {P * 720 / ms / 1e9:.3f} Tevals/s "
+          f"(eager: score {ctx.event_elapsed_ms(10, 11) * 1e3:.1f} us, weights+resample+gather {ctx.event_elapsed_ms(11, 12) * 1e3:.1f} us)", flush=True)
+    ctx.graph_destroy(g)
     print(f"poses 100k x 720 (host call incl. H2D/D2H): {(t1 - t0) / 10 * 1e3:.3f} ms  "
           f"{P * 720 / ((t1 - t0) / 10) / 1e9:.2f} Gevals/s; weights+resample {(t2 - t1) / 10 * 1e3:.3f} ms", flush=True)
     m.close()
