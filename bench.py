@@ -459,13 +459,119 @@ def run_b200_arm(args, synth):
         dist.destroy_process_group()
 
 
+def run_particles_arm(args, synth):
+    """--workload config2 (BASELINE.json configs[2]): FastSLAM-style 100 000 particles x 720 beams;
+    a step = score every particle against the distance field + weights + normalise + systematic
+    resample + gather, device resident (single GPU; under torchrun every rank runs an independent
+    replica -- the resident particle set does not shard)."""
+    mod = importlib.import_module(PKG)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps + (args.steps & 1), max(args.warmup, 3)      # even: two steps per graph (buffers swap)
+    w = synth.make_workload("config1")
+    rows, cols = w["occ"].shape
+    P, nbeams, beta, u0 = 100000, 720, 0.05, 0x80000000
+    ctx = mod.Context(local_rank)
+    m = ctx.new_map(rows, cols)
+    m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+    sx, sy = synth.scan_fixed_count(w["occ"], float(w["pixel"]), w["top_left"], w["true_pose"], nbeams)
+    ctx.scan_upload(sx, sy)
+    poses = synth.particles_gaussian(P, w["true_pose"])
+    ctx.particles_upload(poses)
+
+    def step():
+        ctx.particles_score_async(m)
+        ctx.particles_resample_async(beta, u0)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(2 * ((W + 1) // 2)):
+        step()
+    ctx.sync()
+    # per-kernel split, eager
+    KA = 20
+    for i in range(KA):
+        ctx.event_record(3 * i); ctx.particles_score_async(m)
+        ctx.event_record(3 * i + 1); ctx.particles_resample_async(beta, u0)
+        ctx.event_record(3 * i + 2)
+    ctx.sync()
+    sc_ms = sum(ctx.event_elapsed_ms(3 * i, 3 * i + 1) for i in range(KA)) / KA
+    rs_ms = sum(ctx.event_elapsed_ms(3 * i + 1, 3 * i + 2) for i in range(KA)) / KA
+    ctx.graph_begin(); step(); step(); g = ctx.graph_end()
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.event_record(4000)
+    for _ in range(K // 2):
+        ctx.graph_launch(g)
+    ctx.event_record(4001)
+    barrier()
+    dev_ms = ctx.event_elapsed_ms(4000, 4001)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    best = ctx.match_fetch()
+    # e2e: particles from host memory every step, weights + ancestors back
+    KE = 10
+    t0 = time.perf_counter()
+    for _ in range(KE):
+        res, _, _ = ctx.score_poses(m, poses, want_hits=False)
+        ctx.weights_resample(P, beta, u0)
+    e2e_s = (time.perf_counter() - t0) / KE
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_s, sc_ms, rs_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, sc_ms, rs_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        evals = P * nbeams
+        ms_per_step = dev_ms / K
+        peak, peak_src = measured_peak_gbs()
+        sc_bytes = 4.0 * evals + 16.0 * P + 8.0 * nbeams            # SURVEY 8d: 4 B / eval + 16 B / pose
+        line = {
+            "metric": METRIC, "value": evals * world / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"config2: FastSLAM-style {P} particles x {nbeams} beams on a {rows}x{cols} map: score + "
+                                   "weights + normalise + systematic resample + gather, device resident",
+                       "particles": P, "beams": nbeams, "beta": beta, "parallelism": f"{world} independent replica(s)",
+                       "l2": "the 16.8 MB distance field is L2 resident by design (gather workload)",
+                       "timing": "cuda-graph replay (2 steps per graph)"},
+            "roofline": {"bound": "hbm", "kernel": "poses_kernel", "achieved": sc_bytes / (sc_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": sc_bytes / (sc_ms * 1e-3) / 1e9 / peak, "ms": sc_ms,
+                         "algorithmic_bytes": sc_bytes, "traffic": ncu_traffic("poses_kernel:config2"),
+                         "peak_source": peak_src, "resample_ms": rs_ms,
+                         "note": "4 B per pose x beam evaluation; gathers are served by L1/L2"},
+            "e2e": {"value": evals * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 12 * P + 8 * nbeams,
+                    "d2h_bytes_per_step": 12 * P + 16, "ms_per_step": e2e_s * 1e3, "steps": KE},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "result": {"best_index": int(best.best_index), "best_score": float(best.best_score)},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.graph_destroy(g)
+    m.close()
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config1", choices=["config1", "config3", "tiny"])
+    ap.add_argument("--workload", default="config1", choices=["config1", "config2", "config3", "tiny"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-allreduce", action="store_true",
@@ -474,7 +580,11 @@ def main():
     args = ap.parse_args()
     synth = importlib.import_module(PKG + ".synth")
     if args.impl == "reference":
+        if args.workload == "config2":
+            args.workload = "config1"       # the reference has no particle filter: its matcher on the same map
         run_reference_arm(args, synth)
+    elif args.workload == "config2":
+        run_particles_arm(args, synth)
     else:
         run_b200_arm(args, synth)
 
