@@ -80,7 +80,8 @@ void b200slam_destroy(b200slam_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     b200slam_comm_destroy(ctx);
     if (ctx->edt_map) b200slam_map_destroy(ctx, ctx->edt_map);
-    cudaFree(ctx->d_scan_x); cudaFree(ctx->d_scan_y);
+    cudaFree(ctx->d_scan_x); cudaFreeHost(ctx->h_scan); cudaFreeHost(ctx->h_hit_values);
+    if (ctx->scan_event) cudaEventDestroy(ctx->scan_event);
     cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
     cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match);
     cudaFree(ctx->d_keys); cudaFreeHost(ctx->h_keys); cudaFree(ctx->d_hit_values);
@@ -336,20 +337,28 @@ int b200slam_edt(b200slam_ctx *ctx, const int32_t *occ, int occ_stride, float *o
 int b200slam_scan_upload(b200slam_ctx *ctx, const float *x, const float *y, int nbeams)
 {
     if (!ctx || nbeams < 0 || (nbeams > 0 && (!x || !y))) return B200SLAM_ERR_ARG;
-    if (nbeams > ctx->scan_cap) {
+    if (nbeams > ctx->scan_cap || !ctx->d_scan_x) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_scan_x); cudaFree(ctx->d_scan_y); cudaFree(ctx->d_hit_values);
-        ctx->d_scan_x = ctx->d_scan_y = ctx->d_hit_values = nullptr;
+        cudaFree(ctx->d_scan_x); cudaFree(ctx->d_hit_values); cudaFreeHost(ctx->h_scan); cudaFreeHost(ctx->h_hit_values);
+        ctx->d_scan_x = ctx->d_scan_y = ctx->d_hit_values = ctx->h_scan = ctx->h_hit_values = nullptr;
         ctx->scan_cap = 0;
-        const int cap = (nbeams + 255) & ~255;
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_scan_x, sizeof(float) * cap));
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_scan_y, sizeof(float) * cap));
+        const int cap = ((nbeams > 0 ? nbeams : 1) + 255) & ~255;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_scan_x, sizeof(float) * 2 * cap));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_hit_values, sizeof(float) * 2 * cap));
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_scan, sizeof(float) * 2 * cap, cudaHostAllocDefault));
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_hit_values, sizeof(float) * cap, cudaHostAllocDefault));
+        if (!ctx->scan_event) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->scan_event, cudaEventDisableTiming));
+        ctx->d_scan_y = ctx->d_scan_x + cap;
         ctx->scan_cap = cap;
     }
     if (nbeams > 0) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scan_x, x, sizeof(float) * nbeams, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scan_y, y, sizeof(float) * nbeams, cudaMemcpyHostToDevice, ctx->stream));
+        // one pinned, truly asynchronous copy of x | y (callers hand in pageable arrays)
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->scan_event));
+        memcpy(ctx->h_scan, x, sizeof(float) * nbeams);
+        memcpy(ctx->h_scan + ctx->scan_cap, y, sizeof(float) * nbeams);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scan_x, ctx->h_scan, sizeof(float) * ((size_t)ctx->scan_cap + nbeams),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->scan_event, ctx->stream));
     }
     ctx->nbeams = nbeams;
     return B200SLAM_OK;
@@ -581,16 +590,16 @@ int b200slam_score_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pos
     if (scores)
         CUDA_TRY(ctx, cudaMemcpyAsync(scores, ctx->d_scores, sizeof(float) * (size_t)nrows * n[2],
                                       cudaMemcpyDeviceToHost, ctx->stream));
+    // the last candidate's hit values ride along with the result: one synchronisation per match
+    if (last_hit_values && ctx->nbeams > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_hit_values, ctx->d_hit_values + ctx->scan_cap,
+                                      sizeof(float) * (size_t)ctx->nbeams, cudaMemcpyDeviceToHost, ctx->stream));
     b200slam_match tmp;
-    rc = b200slam_match_fetch(ctx, result ? result : &tmp);
+    rc = b200slam_match_fetch(ctx, result ? result : &tmp);       // copies the result block and synchronises
     if (rc) return rc;
     const b200slam_match *m = result ? result : &tmp;
-    if (last_hit_values && m->last_hits > 0) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(last_hit_values, ctx->d_hit_values + ctx->scan_cap,
-                                      sizeof(float) * (size_t)m->last_hits, cudaMemcpyDeviceToHost,
-                                      ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if (last_hit_values && m->last_hits > 0)
+        memcpy(last_hit_values, ctx->h_hit_values, sizeof(float) * (size_t)m->last_hits);
     return B200SLAM_OK;
 }
 

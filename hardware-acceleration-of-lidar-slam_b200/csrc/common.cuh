@@ -67,7 +67,10 @@ struct b200slam_ctx {
     uint64_t launches = 0;
 
     // scan (sensor frame), device resident
-    float *d_scan_x = nullptr, *d_scan_y = nullptr;
+    float *d_scan_x = nullptr, *d_scan_y = nullptr;   // one allocation: x[scan_cap] | y[scan_cap]
+    float *h_scan = nullptr;                          // pinned staging, same layout
+    float *h_hit_values = nullptr;                    // pinned landing zone for the last candidate's hits
+    cudaEvent_t scan_event = nullptr;                 // staging buffer free again
     int nbeams = 0, scan_cap = 0;
 
     // lattice axis tables: host-pinned staging + device copy

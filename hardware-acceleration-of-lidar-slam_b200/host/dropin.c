@@ -70,6 +70,8 @@ extern MyFastMatchParameters FastMatchParameters __attribute__((weak));
 extern myLocalMap local_map __attribute__((weak));
 
 static b200slam_ctx *g_ctx;
+static float g_scan_x[REF_COLUMN], g_scan_y[REF_COLUMN];   /* the scan the device currently holds */
+static int g_scan_size = -1;
 /* Device-resident twins of metric_grid / metric_grid2, kept from the last transform so
  * FastMatch does not re-upload the field it was just handed. */
 static struct {
@@ -166,8 +168,15 @@ static void fastmatch_common(int slot, const float POSE[3], const float searchRe
                                    slot ? occ_grid.top_left_corner2[0] : occ_grid.top_left_corner[0],
                                    slot ? occ_grid.top_left_corner2[1] : occ_grid.top_left_corner[1]);
     if (rc) die("b200slam_map_set_geometry", rc);
-    rc = b200slam_scan_upload(ctx(), scan.x, scan.y, scan.size);                 /* main.c:417-421 */
-    if (rc) die("b200slam_scan_upload", rc);
+    /* main.c:417-421.  FastMatch and FastMatch2 of one iteration see the same scan: upload once. */
+    if (g_scan_size != scan.size || memcmp(g_scan_x, scan.x, sizeof(float) * (size_t)scan.size) ||
+        memcmp(g_scan_y, scan.y, sizeof(float) * (size_t)scan.size)) {
+        rc = b200slam_scan_upload(ctx(), scan.x, scan.y, scan.size);
+        if (rc) die("b200slam_scan_upload", rc);
+        memcpy(g_scan_x, scan.x, sizeof(float) * (size_t)scan.size);
+        memcpy(g_scan_y, scan.y, sizeof(float) * (size_t)scan.size);
+        g_scan_size = scan.size;
+    }
     rc = b200slam_fastmatch(ctx(), m, POSE, searchResolution, FastMatchParameters.pose,
                             FastMatchParameters.bestHits, &FastMatchParameters.bestHits_size);
     if (rc) die("b200slam_fastmatch", rc);
