@@ -387,9 +387,13 @@ bool is_capturing(b200slam_ctx *ctx)
 // through a ring of LAT_SLOTS pinned slots, each guarded by an event recorded after the
 // kernel that reads its device copy, so back-to-back matches never wait on the host.
 int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[3], const float step[3],
-                  const int n[3], LatticeLaunch *L)
+                  const int n[3], int64_t row_begin, int64_t row_end, LatticeLaunch *L)
 {
-    const int nth = n[0], ntx = n[1], nty = n[2];
+    const int nth_all = n[0], ntx = n[1], nty = n[2];
+    // only the angles this launch's (theta, tx) rows touch (a shard of a big lattice stays small)
+    const int th_first = row_end > row_begin ? (int)(row_begin / ntx) : 0;
+    const int th_last = row_end > row_begin ? (int)((row_end - 1) / ntx) : 0;
+    const int nth = th_last - th_first + 1;
     const size_t need = (size_t)2 * nth + ntx + nty;
     const bool capturing = is_capturing(ctx);
     const bool by_param = need <= LATTICE_PARAM_FLOATS;
@@ -418,7 +422,7 @@ int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[
     const float ipixel = 1 / map->pixel_size;                             // main.c:383
     float *ct = ctx->h_lat + (size_t)slot * ctx->lat_cap, *st = ct + nth, *sxt = st + nth, *syt = sxt + ntx;
     for (int i = 0; i < nth; ++i) {
-        const float th = b200slam_lattice_value(pose0[2], step[2], i, nth);   // main.c:424
+        const float th = b200slam_lattice_value(pose0[2], step[2], th_first + i, nth_all);   // main.c:424
         ct[i] = cosf(th);                                                 // main.c:434
         st[i] = sinf(th);                                                 // main.c:435
     }
@@ -433,7 +437,8 @@ int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[
         syt[i] = d * ipixel;                                              // main.c:437
     }
     L->map = map;
-    L->nth = nth; L->ntx = ntx; L->nty = nty;
+    L->nth = nth_all; L->ntx = ntx; L->nty = nty;
+    L->th_first = th_first; L->nth_tab = nth;
     L->h_tables = ct;
     L->d_tables = nullptr;
     if (!by_param) {
@@ -465,7 +470,7 @@ int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], co
         return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "row range [%lld,%lld) outside [0,%lld)",
                                   (long long)row_begin, (long long)row_end, (long long)nrows);
     LatticeLaunch L;
-    rc = stage_lattice(ctx, map, pose0, step, n, &L);
+    rc = stage_lattice(ctx, map, pose0, step, n, row_begin, row_end, &L);
     if (rc) return rc;
     L.row_begin = row_begin;
     L.row_end = row_end;

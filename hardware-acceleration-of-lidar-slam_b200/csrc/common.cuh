@@ -166,10 +166,12 @@ int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
 struct LatticeLaunch {
     const b200slam_map *map;
     int nth, ntx, nty;
-    // axis tables ct[nth] | st[nth] | sxt[ntx] | syt[nty]: host copy (passed as kernel
-    // parameters when small enough) or, for large lattices, a device copy
+    // axis tables ct[nth_tab] | st[nth_tab] | sxt[ntx] | syt[nty], theta entries only for the
+    // nth_tab angles [th_first, th_first + nth_tab) this launch's rows touch: host copy (passed
+    // as kernel parameters when small enough) or, for large lattices, a device copy
     const float *h_tables;
     const float *d_tables;
+    int th_first, nth_tab;
     int64_t row_begin, row_end;
     float *d_scores;   // optional
     bool exchange;     // merge with the other ranks through peer memory inside the kernel

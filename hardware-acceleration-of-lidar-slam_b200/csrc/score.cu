@@ -226,7 +226,8 @@ struct LatticeArgs {
     float ipixel;
     const float *tables;      // device copy of ct|st|sxt|syt, or nullptr: use the parameter block
     int nth, ntx, nty;
-    int th_first;             // first theta index covered by blockIdx.z
+    int th_first;             // first theta index covered by blockIdx.z == first entry of ct / st
+    int nth_tab;              // number of theta entries in the tables
     long long row_begin, row_end;
     MatchDev *match;
     float *scores;            // optional
@@ -261,7 +262,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     __shared__ unsigned int epoch_s;
 
     const float *tab = A.tables ? A.tables : T.v;
-    const float *ctT = tab, *stT = tab + A.nth, *sxtT = tab + 2 * A.nth, *sytT = sxtT + A.ntx;
+    const float *ctT = tab, *stT = tab + A.nth_tab, *sxtT = tab + 2 * A.nth_tab, *sytT = sxtT + A.ntx;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -274,7 +275,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     const long long r_lo = (long long)ith * A.ntx + tx0;
     const long long r_hi = r_lo + min(TXT, A.ntx - tx0);
     if (r_hi > A.row_begin && r_lo < A.row_end) {
-        const float ct = ctT[ith], st = stT[ith];
+        const float ct = ctT[blockIdx.z], st = stT[blockIdx.z];
         const int txl = wx * 32 + lane;          // tile-local tx of this thread
         const int tyl = wy * TYPT;               // first tile-local ty of this thread
 
@@ -413,7 +414,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
             const int ity = (int)(lin % A.nty);
             const long long row = lin / A.nty;
             const int itx = (int)(row % A.ntx), jth = (int)(row / A.ntx);
-            cand[which].ct = ctT[jth]; cand[which].st = stT[jth];
+            cand[which].ct = ctT[jth - A.th_first]; cand[which].st = stT[jth - A.th_first];
             cand[which].sxt = sxtT[itx]; cand[which].syt = sytT[ity];
         }
         trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand,
@@ -595,7 +596,8 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
         A.xchg.nranks = ctx->nranks; A.xchg.rank = ctx->rank;
     }
     LatticeTables T;                     // parameter block (copied at launch)
-    if (!L.d_tables) memcpy(T.v, L.h_tables, sizeof(float) * (2 * (size_t)L.nth + L.ntx + L.nty));
+    A.nth_tab = L.nth_tab;
+    if (!L.d_tables) memcpy(T.v, L.h_tables, sizeof(float) * (2 * (size_t)L.nth_tab + L.ntx + L.nty));
     if (L.row_end <= L.row_begin) {
         if (A.xchg.peers) {             // nothing to score, but the peers wait for this rank's post
             exchange_only_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, A.xchg);
@@ -607,10 +609,8 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
         CUDA_TRY(ctx, cudaMemsetAsync(&ctx->d_match->best_hits, 0, 2 * sizeof(int), ctx->stream));
         return B200SLAM_OK;
     }
-    const int th_first = (int)(L.row_begin / L.ntx);
-    const int th_last = (int)((L.row_end - 1) / L.ntx);
-    A.th_first = th_first;
-    const int nth_cover = th_last - th_first + 1;
+    A.th_first = L.th_first;
+    const int nth_cover = L.nth_tab;
     const long long cands = (long long)(L.row_end - L.row_begin) * L.nty;
 
     // Candidates per thread: as many as still leave ~16 warps per SM; big register tiles
