@@ -100,3 +100,37 @@ def test_edt_8192_properties_and_tiles(ctx, oracle, synth):
 def test_edt_empty_shapes(ctx):
     out = ctx.edt(np.zeros((0, 5), np.int32))
     assert out.shape == (0, 5)
+
+
+@pytest.mark.gpu
+def test_bad_arguments_are_reported_not_fatal(ctx, b200slam, synth):
+    """Every entry point answers bad input with an error code and a message (the new
+    generic API returns int status and never throws or crashes)."""
+    L = ctx.L
+    occ = np.zeros((8, 8), np.int32)
+    out = np.zeros((8, 8), np.float32)
+    assert L.b200slam_edt(ctx.h, None, 8, out.ctypes.data, 8, 8, 8, 10.0) == b200slam.ERR_ARG
+    assert L.b200slam_edt(ctx.h, occ.ctypes.data, 4, out.ctypes.data, 8, 8, 8, 10.0) == b200slam.ERR_ARG   # stride < cols
+    assert L.b200slam_edt(ctx.h, occ.ctypes.data, 8, out.ctypes.data, 8, 8, 8, -1.0) == b200slam.ERR_ARG
+    assert L.b200slam_edt(ctx.h, occ.ctypes.data, 8, out.ctypes.data, 8, 8, 8, 300.0) == b200slam.ERR_ARG
+    assert b"max_dist" in L.b200slam_last_error(ctx.h)
+    with pytest.raises(b200slam.B200SlamError):
+        ctx.new_map(0, 5)
+    m = ctx.new_map(16, 16)
+    try:
+        with pytest.raises(b200slam.B200SlamError) as e:            # geometry not set
+            ctx.score_lattice(m, (0, 0, 0), (0.05, 0.05, 0.01), (3, 3, 3))
+        assert e.value.code == b200slam.ERR_STATE
+        m.set_geometry(0.1, (0.0, 0.0))
+        with pytest.raises(b200slam.B200SlamError):                 # zero-sized lattice
+            ctx.score_lattice(m, (0, 0, 0), (0.05, 0.05, 0.01), (0, 3, 3))
+        with pytest.raises(b200slam.B200SlamError):                 # row range outside the lattice
+            ctx.score_lattice_rows(m, (0, 0, 0), (0.05, 0.05, 0.01), (3, 3, 3), 0, 10)
+        assert L.b200slam_map_resize(m.h, 17, 4) == b200slam.ERR_ARG
+        x = np.array([0.0, 100.0], np.float32)
+        with pytest.raises(b200slam.B200SlamError):                 # rasterised grid exceeds the capacity
+            m.rasterise(x, x, 0.1)
+        # the context is still usable afterwards
+        assert np.array_equal(ctx.edt(occ), np.full((8, 8), 10.0, np.float32))
+    finally:
+        m.close()
