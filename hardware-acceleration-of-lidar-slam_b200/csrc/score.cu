@@ -48,12 +48,20 @@ __device__ __forceinline__ float rot_y(float psx, float psy, float ct, float st)
 {
     return __fadd_rn(__fmul_rn(psx, -st), __fmul_rn(psy, ct));           // main.c:463
 }
+// (int)roundf(v) for every v whose result can pass the validity test below: for v >= 0 adding 0.5
+// with round-toward-zero and truncating IS round-half-away-from-zero (exhaustively equal to glibc
+// roundf); for v < 0, NaN and out-of-range values both this and roundf give something <= 0 or
+// saturated, i.e. an invalid cell either way.
+__device__ __forceinline__ int round_cell(float v)
+{
+    return __float2int_rz(__fadd_rz(v, 0.5f));
+}
 // 0-based cell index of (int)roundf(v) + 1 - 1, or -1 when the 1-based index fails
 // `1 < S < n` (main.c:512).
 __device__ __forceinline__ int cell_index(float v, int n)
 {
-    const int r = (int)roundf(v);
-    return (r > 0 && r < n - 1) ? r : -1;
+    const int r = round_cell(v);
+    return ((unsigned)(r - 1) < (unsigned)(n - 2)) ? r : -1;
 }
 
 // Read-only gather whose position in the instruction stream the compiler must keep
@@ -456,7 +464,7 @@ constexpr int POSES_CB = 1024;
 
 __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_constant__ PosesArgs A)
 {
-    __shared__ float2 ps[POSES_CB];
+    __shared__ float2 ps[POSES_CB + 64];
     __shared__ unsigned long long red[POSES_THREADS / 32];
     __shared__ int last_flag;
     const long long p = (long long)blockIdx.x * POSES_THREADS + threadIdx.x;
@@ -471,27 +479,29 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
     const float nst = -st;
     float score = 0.0f;
     int nh = 0;
+    const unsigned cols_m2 = (unsigned)(A.cols - 2), rows_m2 = (unsigned)(A.rows - 2);
     for (int c0 = 0; c0 < A.nbeams; c0 += POSES_CB) {
         const int cb = min(POSES_CB, A.nbeams - c0);
+        constexpr int U = 8, NBUF = 3;
+        const int cbp = (cb + NBUF * U - 1) / (NBUF * U) * (NBUF * U);
         __syncthreads();
-        for (int i = threadIdx.x; i < cb; i += POSES_THREADS)
-            ps[i] = make_float2(__fmul_rn(A.scan_x[c0 + i], A.ipixel),
-                                __fmul_rn(A.scan_y[c0 + i], A.ipixel));
+        // beams [cb, cbp + (NBUF-1)*U) are padding: points that land outside every grid and add +0.0f
+        for (int i = threadIdx.x; i < cbp + (NBUF - 1) * U; i += POSES_THREADS)
+            ps[i] = i < cb ? make_float2(__fmul_rn(A.scan_x[c0 + i], A.ipixel), __fmul_rn(A.scan_y[c0 + i], A.ipixel))
+                           : make_float2(-1.0e30f, -1.0e30f);
         __syncthreads();
         if (live) {
-            // software-pipelined like the lattice kernel: the gathers of the next 8 beams are
-            // in flight while the current 8 values are added in beam order
-            constexpr int U = 8;
+            // software-pipelined like the lattice kernel: the gathers of the next beams are in
+            // flight while the current ones are added in beam order (main.c:516)
             auto gather = [&](int i0, float (&dst)[U]) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int i = min(i0 + u, cb - 1);
-                    const float2 q = ps[i];
+                    const float2 q = ps[i0 + u];
                     const float fx = __fadd_rn(__fadd_rn(__fmul_rn(q.x, ct), __fmul_rn(q.y, st)), sxt);
                     const float fy = __fadd_rn(__fadd_rn(__fmul_rn(q.x, nst), __fmul_rn(q.y, ct)), syt);
-                    const int c = cell_index(fx, A.cols);
-                    const int r = cell_index(fy, A.rows);
-                    const bool in = (c >= 0) && (r >= 0) && (i0 + u < cb);
+                    const int c = round_cell(fx);                                   // main.c:483
+                    const int r = round_cell(fy);                                   // main.c:501
+                    const bool in = ((unsigned)(c - 1) < cols_m2) & ((unsigned)(r - 1) < rows_m2);   // main.c:512
                     const int off = in ? r * A.pitch + c : -1;
                     dst[u] = __ldg(A.field + off);
                     nh += in ? 1 : 0;
@@ -499,13 +509,12 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
             };
             auto accumulate = [&](const float (&src)[U]) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) score = __fadd_rn(score, src[u]);   // +0.0f past the end
+                for (int u = 0; u < U; ++u) score = __fadd_rn(score, src[u]);
             };
-            constexpr int NBUF = 3;
             float v[NBUF][U];
 #pragma unroll
             for (int b = 0; b < NBUF - 1; ++b) gather(b * U, v[b]);
-            for (int i0 = 0; i0 < cb; i0 += NBUF * U) {
+            for (int i0 = 0; i0 < cbp; i0 += NBUF * U) {
 #pragma unroll
                 for (int b = 0; b < NBUF; ++b) {
                     gather(i0 + (b + NBUF - 1) * U, v[(b + NBUF - 1) % NBUF]);
