@@ -332,7 +332,10 @@ def run_b200_arm(args, synth):
     # ---- pass B: the timed region.  The step is two microsecond-scale kernels, so steps are
     # captured as CUDA graphs: one graph holding a whole turn of the ring (`ring` consecutive
     # steps) for the bulk, single-step graphs for the remainder; K steps are replayed exactly.
-    graphs, turn = [], None
+    # Consecutive steps are independent (each has its own map), so inside a turn the transforms
+    # run on a second stream (a second context on the same GPU): the EDT of step i+1 executes
+    # under the match of step i.  The un-pipelined graph is timed too (`serial_ms_per_step`).
+    graphs, turn, turn_serial, ctx_e = [], None, None, None
     use_graph = not args.no_graph
     if use_graph:
         try:
@@ -340,36 +343,70 @@ def run_b200_arm(args, synth):
                 ctx.graph_begin()
                 step_async(i)
                 graphs.append(ctx.graph_end())
+            # inside a turn every match POSTS its per-rank best to the peers and merges the PREVIOUS
+            # step's posts in the same kernel tail (allreduce = 2), so ranks are not held in
+            # lockstep; one collect at the end of the turn merges the last step
+            post = 2 if allreduce else 0
             ctx.graph_begin()
             for i in range(ring):
-                step_async(i)
-            turn = ctx.graph_end()
+                maps[i].edt(10.0)
+                ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n_global, row_b, row_e, post)
+            if allreduce:
+                ctx.exchange_collect_async()
+            turn_serial = ctx.graph_end()
+            turn = turn_serial
+            if not args.no_pipeline:
+                ctx_e = mod.Context(local_rank)
+                for i in range(ring):                         # warm the second context's kernels
+                    ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
+                ctx_e.sync()
+                ctx.graph_begin()
+                ctx.event_record(3000)
+                ctx_e.event_wait(ctx, 3000)                   # fork: the transform stream joins the capture
+                for i in range(ring):
+                    ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
+                    ctx_e.event_record(3100 + i)
+                    ctx.event_wait(ctx_e, 3100 + i)
+                    ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n_global, row_b, row_e, post)
+                if allreduce:
+                    ctx.exchange_collect_async()
+                ctx_e.event_record(3200)
+                ctx.event_wait(ctx_e, 3200)                   # join
+                turn = ctx.graph_end()
         except mod.B200SlamError as e:
             if rank == 0:
                 print(f"[bench] graph capture unavailable ({e}); timing eager launches", file=sys.stderr)
             use_graph = False
-            graphs, turn = [], None
+            graphs, turn, turn_serial = [], None, None
 
-    def run_steps(n):
+    def run_steps(n, turn_graph):
         if not use_graph:
             for i in range(n):
                 step_async(i)
             return
         for _ in range(n // ring):
-            ctx.graph_launch(turn)
+            ctx.graph_launch(turn_graph)
         for i in range(n % ring):
             ctx.graph_launch(graphs[i])
 
-    run_steps(max(W, ring))
-    launches0 = ctx.launch_count()
+    serial_ms = None
+    if use_graph and turn is not turn_serial:
+        run_steps(max(W, ring), turn_serial)
+        barrier()
+        ctx.event_record(4002)
+        run_steps(K, turn_serial)
+        ctx.event_record(4003)
+        barrier()
+        serial_ms = ctx.event_elapsed_ms(4002, 4003) / K
+    run_steps(max(W, ring), turn)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.event_record(4000)
-    run_steps(K)
+    run_steps(K, turn)
     ctx.event_record(4001)
     barrier()
+    launches = 2 * K + (K // ring if allreduce else 0)   # EDT + scan-matching kernel per step (+ one collect per turn when N > 1)
     dev_ms = ctx.event_elapsed_ms(4000, 4001)
-    launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     last = ctx.match_fetch()
 
@@ -399,9 +436,10 @@ def run_b200_arm(args, synth):
     # ---- max over ranks ---------------------------------------------------------------
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_s, edt_ms_avg, lat_ms_avg], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, edt_ms_avg, lat_ms_avg, serial_ms or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, edt_ms_avg, lat_ms_avg = [float(x) for x in t.tolist()]
+        dev_ms, e2e_s, edt_ms_avg, lat_ms_avg, smax = [float(x) for x in t.tolist()]
+        serial_ms = smax if serial_ms is not None else None
 
     if rank == 0:
         ms_per_step = dev_ms / K
@@ -434,7 +472,10 @@ def run_b200_arm(args, synth):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(w, args, world), ring_maps=ring,
-                           timing=f"cuda-graph replay ({ring} steps per graph)" if use_graph else "eager launches"),
+                           timing=(f"cuda-graph replay ({ring} steps per graph"
+                                   + (", EDT of step i+1 on a second stream under the match of step i)" if ctx_e else ")"))
+                           if use_graph else "eager launches"),
+            "serial_ms_per_step": serial_ms,
             "edt_mcells_per_s": cells / (edt_ms_avg * 1e-3) / 1e6,
             "match_evals_per_s_per_gpu": evals_per_rank / (lat_ms_avg * 1e-3),
             "roofline": roofline, "rooflines": roofs,
@@ -449,8 +490,10 @@ def run_b200_arm(args, synth):
             line["cpu_baseline"] = cpu_sample(w, synth, budget_s=args.cpu_seconds)
         print(json.dumps(line), flush=True)
 
-    for g in graphs + ([turn] if turn is not None else []):
+    for g in graphs + [g for g in {id(turn): turn, id(turn_serial): turn_serial}.values() if g is not None]:
         ctx.graph_destroy(g)
+    if ctx_e is not None:
+        ctx_e.close()
     for m in maps:
         m.close()
     ctx.close()
@@ -517,7 +560,6 @@ def run_particles_arm(args, synth):
     ctx.event_record(4001)
     barrier()
     dev_ms = ctx.event_elapsed_ms(4000, 4001)
-    launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     best = ctx.match_fetch()
     # e2e: particles from host memory every step, weights + ancestors back
@@ -573,6 +615,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config1", choices=["config1", "config2", "config3", "tiny"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="keep every step's EDT and match strictly back to back (no second stream)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-allreduce", action="store_true",
                     help="diagnostic: N > 1 without the per-step exchange of bests (ranks run independently)")

@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
         "b200slam_score_lattice_rows": (i, [vp, vp, c_float_p, c_float_p, c_int_p, C.c_int64, C.c_int64, i,
                                             C.POINTER(Match)]),
         "b200slam_score_lattice_async": (i, [vp, vp, c_float_p, c_float_p, c_int_p, C.c_int64, C.c_int64, i]),
+        "b200slam_exchange_collect_async": (i, [vp]),
         "b200slam_match_fetch": (i, [vp, C.POINTER(Match)]),
         "b200slam_score_poses": (i, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.POINTER(Match)]),
         "b200slam_fastmatch": (i, [vp, vp, c_float_p, c_float_p, c_float_p, vp, c_int_p]),
@@ -104,6 +105,7 @@ def load_library() -> C.CDLL:
         "b200slam_graph_launch": (i, [vp, vp]),
         "b200slam_graph_destroy": (None, [vp, vp]),
         "b200slam_event_record": (i, [vp, i]),
+        "b200slam_event_wait": (i, [vp, vp, i]),
         "b200slam_event_elapsed_ms": (i, [vp, i, i, c_float_p]),
         "b200slam_weights_resample": (i, [vp, f, C.c_uint32, vp, c_u64_p, vp, c_i64_p, c_i64_p]),
         "b200slam_particles_upload": (i, [vp, vp, vp, vp, C.c_int64]),
@@ -347,7 +349,10 @@ class Context:
         if row_begin is None:
             row_begin, row_end = 0, int(n[0]) * int(n[1])
         self._check(self.L.b200slam_score_lattice_async(self.h, m.h, _f3(pose0), _f3(step), _i3(n), row_begin,
-                                                        row_end, 1 if allreduce else 0))
+                                                        row_end, int(allreduce)))
+
+    def exchange_collect_async(self):
+        self._check(self.L.b200slam_exchange_collect_async(self.h))
 
     def match_fetch(self) -> Match:
         res = Match()
@@ -442,6 +447,9 @@ class Context:
     # -- timing ----------------------------------------------------------------------
     def event_record(self, slot: int):
         self._check(self.L.b200slam_event_record(self.h, slot))
+
+    def event_wait(self, other: "Context", slot: int):
+        self._check(self.L.b200slam_event_wait(self.h, other.h, slot))
 
     def event_elapsed_ms(self, a: int, b: int) -> float:
         ms = C.c_float(0)

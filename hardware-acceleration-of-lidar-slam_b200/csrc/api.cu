@@ -61,7 +61,7 @@ int b200slam_create(b200slam_ctx **out, int device)
     {
         MatchDev init;
         init.work_key = ~0ull; init.tickets = 0; init.epoch = 0; init.key = ~0ull;
-        init.best_hits = 0; init.last_hits = 0;
+        init.best_hits = 0; init.last_hits = 0; init.collected = 0; init.pad = 0; init.gkey = ~0ull; init.gbest_hits = 0; init.glast_hits = 0;
         CREATE_TRY(cudaMemcpy(ctx->d_match, &init, sizeof init, cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaMalloc(&ctx->d_keys, sizeof(unsigned long long) * 256));
@@ -460,8 +460,10 @@ int check_lattice_args(b200slam_ctx *ctx, const b200slam_map *map, const float *
     return B200SLAM_OK;
 }
 
+// allreduce: 0 = this rank only; 1 = exchange the per-rank results and merge; 2 = post this
+// rank's result to its peers but leave the merge to a later b200slam_exchange_collect_async.
 int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], const float step[3],
-                  const int n[3], int64_t row_begin, int64_t row_end, bool want_scores, bool allreduce)
+                  const int n[3], int64_t row_begin, int64_t row_end, bool want_scores, int allreduce)
 {
     int rc = check_lattice_args(ctx, map, pose0, step, n);
     if (rc) return rc;
@@ -475,8 +477,9 @@ int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], co
     L.row_begin = row_begin;
     L.row_end = row_end;
     L.d_scores = nullptr;
-    const bool multi = allreduce && ctx->nccl_comm && ctx->nranks > 1;
-    L.exchange = multi && ctx->p2p_ready;      // merged inside the kernel over NVLink peer memory
+    const bool multi = allreduce != 0 && ctx->nccl_comm && ctx->nranks > 1;
+    L.exchange = multi && ctx->p2p_ready;      // posted from the kernel's tail over NVLink peer memory
+    L.collect_prev = L.exchange && allreduce == 2;
     if (want_scores) {
         const size_t need = (size_t)nrows * n[2];
         if (need > ctx->scores_cap) {
@@ -500,10 +503,15 @@ int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], co
         if (rc) return rc;
         gathered = true;
     }
+    if (L.exchange && allreduce == 1) {
+        rc = exchange_collect_launch(ctx);
+        if (rc) return rc;
+    }
     if (L.d_tables && !is_capturing(ctx)) CUDA_TRY(ctx, cudaEventRecord(ctx->lat_event[ctx->lat_cur], ctx->stream));
     ctx->last.valid = true;
     ctx->last.is_poses = false;
     ctx->last.gathered = gathered;
+    ctx->last.exchanged = L.exchange;
     for (int i = 0; i < 3; ++i) {
         ctx->last.n[i] = n[i];
         ctx->last.pose0[i] = pose0[i];
@@ -539,6 +547,9 @@ int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result)
                                       ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         m = *ctx->h_match;
+        if (ctx->last.exchanged && !ctx->last.is_poses) {     // the merged, global result
+            m.key = m.gkey; m.best_hits = m.gbest_hits; m.last_hits = m.glast_hits;
+        }
     }
     memset(result, 0, sizeof(*result));
     if (m.key == ~0ull) {               // empty shard
@@ -572,14 +583,21 @@ int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const flo
                                  const float step[3], const int n[3], int64_t row_begin, int64_t row_end,
                                  int allreduce)
 {
-    return queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, allreduce != 0);
+    return queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, allreduce);
+}
+
+int b200slam_exchange_collect_async(b200slam_ctx *ctx)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    if (!(ctx->nccl_comm && ctx->nranks > 1 && ctx->p2p_ready)) return B200SLAM_OK;   // nothing was deferred
+    return exchange_collect_launch(ctx);
 }
 
 int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
                                 const float step[3], const int n[3], int64_t row_begin, int64_t row_end,
                                 int allreduce, b200slam_match *result)
 {
-    int rc = queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, allreduce != 0);
+    int rc = queue_lattice(ctx, map, pose0, step, n, row_begin, row_end, false, allreduce != 0 ? 1 : 0);
     if (rc) return rc;
     return b200slam_match_fetch(ctx, result);
 }
@@ -590,7 +608,7 @@ int b200slam_score_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pos
 {
     if (!n) return B200SLAM_ERR_ARG;
     const int64_t nrows = (int64_t)n[0] * n[1];
-    int rc = queue_lattice(ctx, map, pose0, step, n, 0, nrows, scores != nullptr, false);
+    int rc = queue_lattice(ctx, map, pose0, step, n, 0, nrows, scores != nullptr, 0);
     if (rc) return rc;
     if (scores)
         CUDA_TRY(ctx, cudaMemcpyAsync(scores, ctx->d_scores, sizeof(float) * (size_t)nrows * n[2],
@@ -701,6 +719,7 @@ int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *pose
     ctx->last.valid = true;
     ctx->last.is_poses = true;
     ctx->last.gathered = false;
+    ctx->last.exchanged = false;
     ctx->last_P = P;
     ctx->last_index_base = index_base;
     ctx->last_poses_host = poses;
@@ -743,6 +762,7 @@ int b200slam_particles_score_async(b200slam_ctx *ctx, b200slam_map *map)
     ctx->last.valid = true;
     ctx->last.is_poses = true;
     ctx->last.gathered = false;
+    ctx->last.exchanged = false;
     ctx->last_index_base = 0;
     return B200SLAM_OK;
 }
@@ -876,6 +896,13 @@ int b200slam_event_record(b200slam_ctx *ctx, int slot)
     if (!ctx || slot < 0 || slot >= 4096) return B200SLAM_ERR_ARG;
     if (!ctx->timing[slot]) CUDA_TRY(ctx, cudaEventCreate(&ctx->timing[slot]));
     CUDA_TRY(ctx, cudaEventRecord(ctx->timing[slot], ctx->stream));
+    return B200SLAM_OK;
+}
+
+int b200slam_event_wait(b200slam_ctx *ctx, b200slam_ctx *other, int slot)
+{
+    if (!ctx || !other || slot < 0 || slot >= 4096 || !other->timing[slot]) return B200SLAM_ERR_ARG;
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, other->timing[slot], 0));
     return B200SLAM_OK;
 }
 

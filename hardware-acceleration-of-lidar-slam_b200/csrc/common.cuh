@@ -33,10 +33,15 @@ struct b200slam_map {
 struct MatchDev {
     unsigned long long work_key;
     unsigned int tickets;
-    unsigned int epoch;         // number of peer exchanges this context has taken part in
+    unsigned int epoch;         // peer exchanges this context has POSTED
     unsigned long long key;     // (score bits << 32) | global linear index; ~0 = nothing scored
     int best_hits;
     int last_hits;
+    unsigned int collected;     // peer exchanges this context has COLLECTED (merged)
+    unsigned int pad;
+    unsigned long long gkey;    // GLOBAL result of the last collected exchange (all ranks merged)
+    int gbest_hits;
+    int glast_hits;
 };
 
 // Peer-memory exchange of per-rank match results (multi-GPU): every context owns one
@@ -95,6 +100,7 @@ struct b200slam_ctx {
         float step[3] = {0, 0, 0};
         bool is_poses = false;
         bool gathered = false;   // per-rank results were all-gathered into d_keys
+        bool exchanged = false;  // per-rank results were exchanged through peer memory: read MatchDev::g*
     } last;
 
     // optional full score table
@@ -174,10 +180,12 @@ struct LatticeLaunch {
     int th_first, nth_tab;
     int64_t row_begin, row_end;
     float *d_scores;   // optional
-    bool exchange;     // merge with the other ranks through peer memory inside the kernel
+    bool exchange;     // post the result to the other ranks through peer memory from the kernel's tail
+    bool collect_prev; // ... and merge the previous, deferred exchange in the same tail
 };
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
+int exchange_collect_launch(b200slam_ctx *ctx);
 int poses_launch(b200slam_ctx *ctx, const b200slam_map *map, int64_t P, int64_t index_base,
                  float *d_scores, int32_t *d_hits);
 

@@ -99,13 +99,12 @@ __device__ __forceinline__ bool cta_is_last(MatchDev *match, unsigned long long 
     return *flag_smem != 0;
 }
 
-// ---- multi-GPU: merge this rank's result with its peers' through NVLink peer memory ------
-// Called by the whole last CTA (>= 64 threads).  `epoch` is this exchange's number (> 0,
-// identical on every rank).  On return (thread 0) key / best_hits / last_hits are the GLOBAL
-// result: lowest key wins; the last candidate of the whole lattice belongs to the highest
-// rank that scored anything.
-__device__ __forceinline__ void exchange_and_merge(const XchgArgs &X, unsigned int epoch, unsigned long long &key,
-                                                   int &best_hits, int &last_hits, unsigned int *words_smem)
+// ---- multi-GPU: per-rank results travel through NVLink peer memory ----------------------
+// POST (tail of a scoring kernel): this rank's {key, best_hits, last_hits} of exchange number
+// `epoch` is stored into EVERY peer's buffer.  Fire and forget: nobody waits here, so ranks
+// are not forced into lockstep.
+__device__ __forceinline__ void exchange_post(const XchgArgs &X, unsigned int epoch, unsigned long long key,
+                                              int best_hits, int last_hits, unsigned int *words_smem)
 {
     const int tid = threadIdx.x;
     const int ring = (int)(epoch % XCHG_EPOCHS);
@@ -117,13 +116,25 @@ __device__ __forceinline__ void exchange_and_merge(const XchgArgs &X, unsigned i
     const unsigned long long tag = (unsigned long long)epoch << 32;
     for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
         const int r = i >> 2, w = i & 3;
-        // post word w to rank r ...
         *reinterpret_cast<volatile unsigned long long *>(&X.peers[r]->slot[ring][X.rank].w[w]) = tag | words_smem[w];
     }
-    __shared__ unsigned int got[4 * XCHG_MAX_RANKS];
+}
+
+// COLLECT: waits until every rank's words of the oldest uncollected exchange have landed in OUR
+// buffer and publishes the GLOBAL result (lowest key wins; the last candidate of the whole
+// lattice belongs to the highest rank that scored anything) in match->g*.  Runs either as its
+// own one-CTA kernel or in the tail of the NEXT scoring kernel (a step after the posts, when they
+// have long arrived), so ranks drift by up to a step instead of running in lockstep.  Four
+// epochs of slots are enough: a rank posts exchange k only after collecting k-2, which needed
+// every peer's post of k-2, which those peers issued after collecting k-4.
+// Called by a whole CTA (>= 64 threads); got: shared scratch of 4 * XCHG_MAX_RANKS words.
+__device__ __forceinline__ void exchange_collect(const XchgArgs &X, MatchDev *match, unsigned int epoch,
+                                                 unsigned int *got)
+{
+    const int tid = threadIdx.x;
+    const int ring = (int)(epoch % XCHG_EPOCHS);
     for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
         const int r = i >> 2, w = i & 3;
-        // ... and wait for rank r's word w of this epoch in OUR buffer
         const volatile unsigned long long *src = &X.peers[X.rank]->slot[ring][r].w[w];
         unsigned long long v;
         do { v = *src; } while ((unsigned int)(v >> 32) != epoch);
@@ -139,24 +150,40 @@ __device__ __forceinline__ void exchange_and_merge(const XchgArgs &X, unsigned i
             if (kr < k) { k = kr; bh = (int)got[4 * r + 2]; }
             lh = (int)got[4 * r + 3];
         }
-        key = k; best_hits = bh; last_hits = lh;
+        match->gkey = k;
+        match->gbest_hits = bh;
+        match->glast_hits = lh;
+        match->collected = epoch;
     }
 }
 
-// Empty shard of a multi-GPU match: nothing to score, but the exchange still needs this rank.
+__global__ void __launch_bounds__(64) exchange_collect_kernel(MatchDev *match, const XchgArgs X)
+{
+    __shared__ unsigned int got[4 * XCHG_MAX_RANKS];
+    __shared__ unsigned int todo[2];
+    if (threadIdx.x == 0) {
+        todo[0] = *reinterpret_cast<volatile unsigned int *>(&match->collected);
+        todo[1] = *reinterpret_cast<volatile unsigned int *>(&match->epoch);
+    }
+    __syncthreads();
+    for (unsigned int e = todo[0] + 1; e <= todo[1]; ++e) {      // everything posted so far
+        exchange_collect(X, match, e, got);
+        __syncthreads();
+    }
+}
+
+// Empty shard of a multi-GPU match: nothing to score, but the peers expect this rank's post.
 __global__ void __launch_bounds__(64) exchange_only_kernel(MatchDev *match, const XchgArgs X)
 {
     __shared__ unsigned int words_s[4];
     __shared__ unsigned int epoch_s;
     if (threadIdx.x == 0) epoch_s = match->epoch + 1;
     __syncthreads();
-    unsigned long long key = ~0ull;
-    int bh = 0, lh = 0;
-    exchange_and_merge(X, epoch_s, key, bh, lh, words_s);
+    exchange_post(X, epoch_s, ~0ull, 0, 0, words_s);
     if (threadIdx.x == 0) {
-        match->key = key;
-        match->best_hits = bh;
-        match->last_hits = lh;
+        match->key = ~0ull;
+        match->best_hits = 0;
+        match->last_hits = 0;
         match->epoch = epoch_s;
     }
 }
@@ -243,6 +270,7 @@ struct LatticeArgs {
     int hit_stride;
     int cb;                   // beams per shared-memory chunk
     unsigned total_ctas;
+    int collect_prev;         // exchange: also merge the previous, still uncollected exchange in this tail
     XchgArgs xchg;            // peers == nullptr: single GPU / no exchange
 };
 
@@ -428,11 +456,19 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
         trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand,
                        A.hit_values, A.hit_values + A.hit_stride, tail_red, hits);
     }
-    int best_hits = hits[0], last_hits = hits[1];
-    unsigned long long out_key = key;
+    const int best_hits = hits[0], last_hits = hits[1];
+    const unsigned long long out_key = key;
     if (A.xchg.peers) {
         __syncthreads();
-        exchange_and_merge(A.xchg, epoch_s, out_key, best_hits, last_hits, xchg_words);
+        exchange_post(A.xchg, epoch_s, key, best_hits, last_hits, xchg_words);
+        // merge the PREVIOUS exchange here (posted a whole step ago) when the caller deferred it
+        if (A.collect_prev) {
+            __shared__ unsigned int got[4 * XCHG_MAX_RANKS];
+            __shared__ unsigned int done_s;
+            if (tid == 0) done_s = *reinterpret_cast<volatile unsigned int *>(&A.match->collected);
+            __syncthreads();
+            if (done_s + 1 < epoch_s) exchange_collect(A.xchg, A.match, done_s + 1, got);
+        }
     }
     if (tid == 0) {
         A.match->key = out_key;
@@ -600,6 +636,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     A.hit_stride = ctx->scan_cap;
     A.tables = L.d_tables;
     A.xchg.peers = nullptr; A.xchg.nranks = 1; A.xchg.rank = 0;
+    A.collect_prev = L.collect_prev ? 1 : 0;
     if (L.exchange && ctx->p2p_ready) {
         A.xchg.peers = ctx->d_peers;
         A.xchg.nranks = ctx->nranks; A.xchg.rank = ctx->rank;
@@ -637,6 +674,15 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     if (L.nty > 4)
         return launch_lattice_cfg<1, 1, 8>(ctx, A, T, nth_cover);        // 32 x 8 tile
     return launch_lattice_cfg<1, 1, 4>(ctx, A, T, nth_cover);            // 32 x 4 tile, 128 thr
+}
+
+int exchange_collect_launch(b200slam_ctx *ctx)
+{
+    XchgArgs X;
+    X.peers = ctx->d_peers; X.nranks = ctx->nranks; X.rank = ctx->rank;
+    exchange_collect_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, X);
+    LAUNCH_CHECK(ctx);
+    return B200SLAM_OK;
 }
 
 int poses_launch(b200slam_ctx *ctx, const b200slam_map *m, int64_t P, int64_t index_base,

@@ -156,10 +156,17 @@ int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const floa
                                 int64_t row_end, int allreduce, b200slam_match *result);
 
 /* Queues the same lattice match on the context's stream WITHOUT reading anything back
- * (for device-timed loops and CUDA-graph capture); fetch with b200slam_match_fetch. */
+ * (for device-timed loops and CUDA-graph capture); fetch with b200slam_match_fetch.
+ * allreduce: 0 = this rank's shard only; 1 = exchange and merge with the other ranks;
+ * 2 = POST this rank's result to its peers (NVLink peer memory, fire and forget) and merge the
+ * PREVIOUS post of a sequence of such calls in the same kernel tail -- the ranks drift by up to a
+ * step instead of running in lockstep; b200slam_exchange_collect_async after the last call of
+ * the sequence merges what is still pending, and b200slam_match_fetch then returns the global
+ * result of that last match.  Posts and collects pair up in order on every rank. */
 int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
                                  const float step[3], const int n[3], int64_t row_begin,
                                  int64_t row_end, int allreduce);
+int b200slam_exchange_collect_async(b200slam_ctx *ctx);
 int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result);
 
 /* Arbitrary pose / particle list: poses[P][3] = {x, y, theta}; ct/st optional [P]
@@ -193,6 +200,11 @@ void b200slam_graph_destroy(b200slam_ctx *ctx, b200slam_graph *graph);
  * CUDA events on the context's stream (the only stream the kernels run on), so callers can
  * time kernels without a CUDA binding of their own.  slot in [0, 4096). */
 int b200slam_event_record(b200slam_ctx *ctx, int slot);
+/* Makes everything queued on `ctx` from now on wait for event `slot` of `other` (a second
+ * context on the same GPU = a second stream): cross-stream dependencies for callers that
+ * pipeline independent work, e.g. the transform of the next map under the match on the current
+ * one.  Usable inside b200slam_graph_begin/end of `ctx` (the other stream joins the capture). */
+int b200slam_event_wait(b200slam_ctx *ctx, b200slam_ctx *other, int slot);
 int b200slam_event_elapsed_ms(b200slam_ctx *ctx, int slot_start, int slot_stop, float *ms);
 
 /* ---- particle weights + systematic resampling (extension; not in the reference) ----
