@@ -43,6 +43,7 @@ int b200slam_create(b200slam_ctx **out, int device)
     b200slam_ctx *ctx = new (std::nothrow) b200slam_ctx();
     if (!ctx) return B200SLAM_ERR_NOMEM;
     ctx->device = device;
+    ctx->use_pdl = getenv("B200SLAM_NO_PDL") == nullptr;
 #define CREATE_TRY(expr)                                                                      \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

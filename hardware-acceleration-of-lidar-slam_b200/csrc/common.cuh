@@ -70,6 +70,8 @@ struct b200slam_ctx {
     cudaStream_t stream = nullptr;
     char err[512] = {0};
     uint64_t launches = 0;
+    bool use_pdl = true;         // programmatic dependent launch between consecutive scan-matching kernels
+    bool prev_launch_was_lattice = false;   // the last kernel queued on the stream was a scan-matching kernel
 
     // scan (sensor frame), device resident
     float *d_scan_x = nullptr, *d_scan_y = nullptr;   // one allocation: x[scan_cap] | y[scan_cap]
@@ -162,6 +164,7 @@ int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
 #define LAUNCH_CHECK(ctx)                                                                    \
     do {                                                                                     \
         (ctx)->launches++;                                                                   \
+        (ctx)->prev_launch_was_lattice = false;                                              \
         CUDA_TRY((ctx), cudaGetLastError());                                                 \
     } while (0)
 
@@ -199,6 +202,20 @@ int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float mi
 
 int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send,
                        unsigned long long *d_recv, int count_per_rank);
+
+// Programmatic dependent launch (PDL) between consecutive scan-matching kernels: a kernel lets
+// the NEXT one in the stream start (launch latency, table construction, its whole gather loop
+// -- none of which depends on this kernel) while its own last CTA is still reducing and
+// tracing, and the next one waits for this one right before it touches the shared match state.
+// Both are no-ops for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grids()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // packed arg-min key helpers (scores are sums of non-negative floats, so the IEEE bit
 // pattern orders like the value and uint64 min == (lowest score, then lowest index))

@@ -297,6 +297,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     __shared__ unsigned int xchg_words[4];
     __shared__ unsigned int epoch_s;
 
+    pdl_launch_dependents();                      // the next scan-matching kernel may start
     const float *tab = A.tables ? A.tables : T.v;
     const float *ctT = tab, *stT = tab + A.nth_tab, *sxtT = tab + 2 * A.nth_tab, *sytT = sxtT + A.ntx;
 
@@ -430,6 +431,9 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
             }
         }
     }
+    // Scores and tables above depend on the scan, the launch parameters and the field only.  The
+    // match state below is shared with the kernel in front (its last CTA resets it).
+    pdl_wait_prior_grids();
     best = warp_min_u64(best);
     if (lane == 0) red[warp] = best;
     __syncthreads();
@@ -614,8 +618,21 @@ int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T
     }
     dim3 grid((A.nty + TYT - 1) / TYT, (A.ntx + TXT - 1) / TXT, nth_cover);
     A.total_ctas = grid.x * grid.y * grid.z;
-    kern<<<grid, 32 * WX * WY, smem, ctx->stream>>>(A, T);
+    // PDL only behind another scan-matching kernel: everything else this kernel follows (EDT,
+    // rasterisation, copies) produces data its early part reads, and keeps full stream order.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(32 * WX * WY);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (ctx->use_pdl && ctx->prev_launch_was_lattice && !A.scores) ? 1 : 0;
+    CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, A, T));
     LAUNCH_CHECK(ctx);
+    ctx->prev_launch_was_lattice = true;
     return B200SLAM_OK;
 }
 
