@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- pose x beam evals/s and EDT Mcells/s of the b200slam hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config1|config3|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config1|config2|config3|config4|tiny]
     python bench.py --impl reference ...        # the reference's own CPU code, same metric
 
 A "step" is one pass of the hot path over one batch of synthetic input: the clamped EDT of
@@ -560,6 +560,7 @@ def run_particles_arm(args, synth):
     ctx.event_record(4001)
     barrier()
     dev_ms = ctx.event_elapsed_ms(4000, 4001)
+    launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     best = ctx.match_fetch()
     # e2e: particles from host memory every step, weights + ancestors back
@@ -607,13 +608,147 @@ def run_particles_arm(args, synth):
         dist.destroy_process_group()
 
 
+def run_pyramid_arm(args, synth):
+    """--workload config4 (BASELINE.json configs[4]): multi-resolution correlative search over a
+    3-level EDT pyramid (2048^2 @ 4p, 4096^2 @ 2p, 8192^2 @ p; coarsest first), 10 M coarse poses
+    over 8 GPUs = 20 x 250 x 250 = 1.25 M per GPU (weak scaling: the theta range grows with N),
+    then two 16 x 32 x 32 refinements, each level seeded by the previous winner
+    (Subsystem_1/main.c:901-918 generalised).  A step = the three transforms + the three
+    matches (b200slam_pyramid_match: candidate rows of every level sharded over the ranks, the
+    per-rank bests exchanged inside the kernels' tails)."""
+    mod = importlib.import_module(PKG)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+    w = synth.make_workload("config3")
+    occ_f = w["occ"]
+    nbeams = len(w["scan_x"])
+    ctx = mod.Context(local_rank)
+    if world > 1:
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+    maps, pins = [], []
+    for f in (4, 2, 1):                                        # coarsest first
+        rows, cols = occ_f.shape[0] // f, occ_f.shape[1] // f
+        pin = ctx.pinned_empty((rows, cols), np.int32)
+        pin[...] = occ_f.reshape(rows, f, cols, f).max(axis=(1, 3))
+        pixel, tl = synth.centred_geometry(rows, cols, 0.1 * f)
+        m = ctx.new_map(rows, cols)
+        m.set_geometry(pixel, tl).upload_occupancy(pin)
+        maps.append(m); pins.append(pin)
+    scan_x = ctx.pinned_empty((nbeams,), np.float32); scan_x[...] = w["scan_x"]
+    scan_y = ctx.pinned_empty((nbeams,), np.float32); scan_y[...] = w["scan_y"]
+    ctx.scan_upload(scan_x, scan_y)
+    steps = np.array([[0.2, 0.2, 0.034908], [0.1, 0.1, 0.017454], [0.05, 0.05, 0.008727]], np.float32)
+    ns = np.array([[20 * world, 250, 250], [16, 32, 32], [16, 32, 32]], np.int32)
+    poses_total = int(sum(int(a) * int(b) * int(c) for a, b, c in ns))
+    evals_total = poses_total * nbeams
+    cells = sum(int(p.size) for p in pins)
+
+    def step():
+        for m in maps:
+            m.edt(10.0)
+        return ctx.pyramid_match(maps, w["pose0"], steps, ns)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(W):
+        res = step()
+    # dominant kernel: this rank's share of the coarsest level, an event pair around each launch
+    KA = 10
+    rb, re = rank * 20 * 250, (rank + 1) * 20 * 250
+    barrier()
+    for i in range(KA):
+        ctx.event_record(2 * i)
+        ctx.score_lattice_async(maps[0], w["pose0"], steps[0], tuple(int(x) for x in ns[0]), rb, re, False)
+        ctx.event_record(2 * i + 1)
+    ctx.sync()
+    lat_ms = sum(ctx.event_elapsed_ms(2 * i, 2 * i + 1) for i in range(KA)) / KA
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.event_record(4000)
+    for _ in range(K):
+        res = step()
+    ctx.event_record(4001)
+    barrier()
+    dev_ms = ctx.event_elapsed_ms(4000, 4001)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    # e2e: the three occupancy grids and the scan from pinned host memory every step
+    KE = max(3, min(K, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(KE):
+        for m, pin in zip(maps, pins):
+            m.upload_occupancy(pin)
+        ctx.scan_upload(scan_x, scan_y)
+        res_e = step()
+    ctx.sync()
+    e2e_s = (time.perf_counter() - t0) / KE
+    barrier()
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_s, lat_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, lat_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        ms_per_step = dev_ms / K
+        peak, peak_src = measured_peak_gbs()
+        coarse_evals = 20 * 250 * 250 * nbeams
+        lat_bytes = 4.0 * coarse_evals + 4.0 * 20 * 250 * 250 + 8.0 * nbeams
+        line = {
+            "metric": METRIC, "value": evals_total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"config4: 3-level EDT pyramid (2048^2 @ 0.4 m, 4096^2 @ 0.2 m, 8192^2 @ 0.1 m, max_dist 10) + "
+                                   f"coarse-to-fine correlative search, {poses_total} candidate poses x {nbeams} beams "
+                                   f"({20 * world}x250x250 coarse, then 16x32x32 twice)",
+                       "lattices": [[int(x) for x in r] for r in ns], "beams": nbeams,
+                       "lattice_steps": [[float(x) for x in r] for r in steps],
+                       "parallelism": f"candidate rows of every level sharded over {world} GPU(s), maps replicated",
+                       "l2": "the three maps (704 MB of occupancy + field) exceed the 126 MB L2",
+                       "timing": "eager launches, one host round trip per level (the next level is seeded by the winner)"},
+            "edt_mcells_per_step": cells / 1e6,
+            "roofline": {"bound": "hbm", "kernel": "lattice_kernel", "achieved": lat_bytes / (lat_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": lat_bytes / (lat_ms * 1e-3) / 1e9 / peak, "ms": lat_ms,
+                         "algorithmic_bytes": lat_bytes, "traffic": ncu_traffic("lattice_kernel:config4"),
+                         "evals_per_s": coarse_evals / (lat_ms * 1e-3), "peak_source": peak_src,
+                         "note": "coarsest level, this rank's 20 x 250 x 250 share; 4 B per pose x beam evaluation, gathers "
+                                 "served by L1/L2"},
+            "e2e": {"value": evals_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells * 4 + 8 * nbeams,
+                    "d2h_bytes_per_step": 3 * 16, "ms_per_step": e2e_s * 1e3, "steps": KE},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "result": {"best_index": [int(r.best_index) for r in res], "best_score": [float(r.best_score) for r in res],
+                       "e2e_best_index": [int(r.best_index) for r in res_e]},
+        }
+        print(json.dumps(line), flush=True)
+    for m in maps:
+        m.close()
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config1", choices=["config1", "config2", "config3", "tiny"])
+    ap.add_argument("--workload", default="config1", choices=["config1", "config2", "config3", "config4", "tiny"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="keep every step's EDT and match strictly back to back (no second stream)")
@@ -626,9 +761,13 @@ def main():
     if args.impl == "reference":
         if args.workload == "config2":
             args.workload = "config1"       # the reference has no particle filter: its matcher on the same map
+        if args.workload == "config4":
+            args.workload = "config3"       # ... and no pyramid: its matcher on the finest map
         run_reference_arm(args, synth)
     elif args.workload == "config2":
         run_particles_arm(args, synth)
+    elif args.workload == "config4":
+        run_pyramid_arm(args, synth)
     else:
         run_b200_arm(args, synth)
 

@@ -245,9 +245,9 @@ struct LatticeTables {
 // Gather pipeline shape: U beams per group, NBUF register buffers (NBUF - 1 groups in flight);
 // GUARD = table rows appended for padding (a multiple of NBUF*U) and for the prefetches that
 // run past the end.
-template <int TYPT>
+template <int TYPT, int UM = 1>
 struct LatticePipe {
-    static constexpr int U = TYPT >= 16 ? 1 : 16 / TYPT;
+    static constexpr int U = UM * (TYPT >= 16 ? 1 : 16 / TYPT);      // UM: deeper groups for low-occupancy shapes
     static constexpr int NBUF = TYPT >= 16 ? 2 : 3;
     static constexpr int PAD = NBUF * U;
     static constexpr int GUARD = PAD - 1 + (NBUF - 1) * U;
@@ -276,14 +276,14 @@ struct LatticeArgs {
 
 // TYPT candidates (consecutive ty) per thread, WX warps along tx, WY warps along ty.
 // Dynamic shared memory: colT[cb][TXT] | rowT[cb][TYT] | Sx[cb] | Sy[cb]
-template <int TYPT, int WX, int WY>
+template <int TYPT, int WX, int WY, int UM = 1>
 __global__ void __launch_bounds__(32 * WX * WY)
 lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ LatticeTables T)
 {
     constexpr int TXT = 32 * WX;
     constexpr int TYT = TYPT * WY;
     constexpr int NT = 32 * WX * WY;
-    using P = LatticePipe<TYPT>;
+    using P = LatticePipe<TYPT, UM>;
     constexpr int U = P::U, NBUF = P::NBUF, GUARD = P::GUARD;
     static_assert(NT % TXT == 0 && NT % TYT == 0, "tile shape");
     extern __shared__ __align__(16) int lat_smem[];
@@ -593,13 +593,13 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
     }
 }
 
-template <int TYPT, int WX, int WY>
+template <int TYPT, int WX, int WY, int UM = 1>
 int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T, int nth_cover)
 {
     constexpr int TXT = 32 * WX, TYT = TYPT * WY;
-    auto kern = lattice_kernel<TYPT, WX, WY>;
+    auto kern = lattice_kernel<TYPT, WX, WY, UM>;
     // Beams per chunk: the whole scan when its tables fit the budget, else even chunks.
-    constexpr int GUARD = LatticePipe<TYPT>::GUARD;
+    constexpr int GUARD = LatticePipe<TYPT, UM>::GUARD;
     const int per_beam = (TXT + TYT + 2) * 4;
     const int budget = TYPT >= 16 ? 56 * 1024 : 100 * 1024;
     int cb = A.nbeams > 0 ? A.nbeams : 1;
@@ -676,21 +676,47 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     const int nth_cover = L.nth_tab;
     const long long cands = (long long)(L.row_end - L.row_begin) * L.nty;
 
-    // Candidates per thread: as many as still leave ~16 warps per SM; big register tiles
-    // amortise the per-chunk tables on large sweeps, small lattices need every thread.
-    long long want_warps = 16LL * ctx->sm_count;
-    if (const char *e = getenv("B200SLAM_LATTICE_WARPS_PER_SM")) want_warps = (long long)atoi(e) * ctx->sm_count;
-    if (cands >= want_warps * 32 * 16 && L.nty >= 64 && L.ntx >= 64)
-        return launch_lattice_cfg<16, 2, 4>(ctx, A, T, nth_cover);       // 64 x 64 tile, 256 thr
-    if (cands >= want_warps * 32 * 8 && L.nty >= 64)
-        return launch_lattice_cfg<8, 1, 8>(ctx, A, T, nth_cover);        // 32 x 64 tile, 256 thr
-    if (cands >= want_warps * 32 * 4 && L.nty >= 32)
-        return launch_lattice_cfg<4, 1, 8>(ctx, A, T, nth_cover);        // 32 x 32 tile
-    if (cands >= want_warps * 32 * 2 && L.nty >= 16)
-        return launch_lattice_cfg<2, 1, 8>(ctx, A, T, nth_cover);        // 32 x 16 tile
-    if (L.nty > 4)
-        return launch_lattice_cfg<1, 1, 8>(ctx, A, T, nth_cover);        // 32 x 8 tile
-    return launch_lattice_cfg<1, 1, 4>(ctx, A, T, nth_cover);            // 32 x 4 tile, 128 thr
+    // Tile shape.  A thread owns TYPT candidates (consecutive ty); per warp and beam the inner loop
+    // costs 1 (column LDS) + TYPT/4 (row LDS.128) + 1.5 * TYPT (gathers, ~1.5 lines each) L1
+    // wavefronts, so big register tiles are cheaper per evaluation (the `per_eval` factors below,
+    // relative to TYPT = 16) -- but a sweep is only as fast as its busiest SM.  Model: every SM
+    // runs ceil(CTAs / SMs) tiles one after the other; pick the shape with the lowest
+    // tiles-per-SM x candidates-per-tile x per-evaluation cost.  (Measured on config 1,
+    // 64 x 32 x 32 x 360 beams: 32 x 16 tiles with 16-beam groups 24.9 us isolated / 9.8 us back
+    // to back, 32 x 8 tiles 27.0 / 14.9, 32 x 32 tiles 33.2 / 13.4.)
+    struct Shape { int typt, wx, wy, um; double per_eval; };
+    static const Shape shapes[] = {
+        {16, 2, 4, 1, 1.00}, {8, 1, 8, 1, 1.05}, {4, 1, 8, 1, 1.13}, {2, 1, 8, 2, 1.40}, {1, 1, 8, 1, 1.95}, {1, 1, 4, 1, 1.95},
+    };
+    int pick_t = 0, pick_x = 0, pick_y = 0, pick_m = 1;
+    if (const char *e = getenv("B200SLAM_LATTICE_CFG"))                   // tuning / test aid: "TYPT,WX,WY[,UM]"
+        if (sscanf(e, "%d,%d,%d,%d", &pick_t, &pick_x, &pick_y, &pick_m) < 3) pick_t = 0;
+    if (!pick_t) {
+        const double covered = (double)(L.row_end - L.row_begin) / ((double)nth_cover * L.ntx);   // row shards: part of the grid
+        double best_cost = 1e300;
+        for (const Shape &sh : shapes) {
+            const int txt = 32 * sh.wx, tyt = sh.typt * sh.wy;
+            double ctas = (double)nth_cover * ((L.ntx + txt - 1) / txt) * ((L.nty + tyt - 1) / tyt) * covered;
+            if (ctas < 1.0) ctas = 1.0;
+            const double per_sm = (double)((long long)((ctas + ctx->sm_count - 1) / ctx->sm_count));
+            const double cost = (per_sm < 1.0 ? 1.0 : per_sm) * txt * tyt * sh.per_eval;
+            if (cost < best_cost * 0.999) {                                // ties: the bigger register tile
+                best_cost = cost;
+                pick_t = sh.typt; pick_x = sh.wx; pick_y = sh.wy; pick_m = sh.um;
+            }
+        }
+    }
+#define B200SLAM_CFG(T_, X_, Y_, M_) \
+    if (pick_t == T_ && pick_x == X_ && pick_y == Y_ && pick_m == M_) return launch_lattice_cfg<T_, X_, Y_, M_>(ctx, A, T, nth_cover);
+    B200SLAM_CFG(16, 2, 4, 1)        // 64 x 64 tile, 256 threads
+    B200SLAM_CFG(8, 1, 8, 1)         // 32 x 64
+    B200SLAM_CFG(4, 1, 8, 1)         // 32 x 32
+    B200SLAM_CFG(2, 1, 8, 2)         // 32 x 16, groups of 16 beams
+    B200SLAM_CFG(2, 1, 8, 1)
+    B200SLAM_CFG(1, 1, 8, 1)         // 32 x 8
+    B200SLAM_CFG(1, 1, 4, 1)         // 32 x 4, 128 threads
+#undef B200SLAM_CFG
+    return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "B200SLAM_LATTICE_CFG names no compiled tile shape");
 }
 
 int exchange_collect_launch(b200slam_ctx *ctx)

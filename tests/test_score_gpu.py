@@ -65,6 +65,24 @@ def test_lattice_matches_oracle_shapes(ctx, oracle, synth, n):
         m.close()
 
 
+@pytest.mark.parametrize("cfg", ["16,2,4", "8,1,8", "4,1,8", "2,1,8,2", "2,1,8", "1,1,8", "1,1,4"])
+def test_lattice_every_compiled_tile_shape(ctx, oracle, synth, monkeypatch, cfg):
+    # the launcher picks a tile shape from a cost model; here every compiled shape is forced
+    # in turn (B200SLAM_LATTICE_CFG is read at each launch) on lattices that leave partial tiles
+    w = synth.make_workload("tiny")
+    m, om = _setup(ctx, oracle, w)
+    try:
+        monkeypatch.setenv("B200SLAM_LATTICE_CFG", cfg)
+        for n in [(3, 3, 3), (2, 33, 17), (3, 70, 67)]:
+            _check_lattice(ctx, oracle, m, om, w, n)
+        monkeypatch.setenv("B200SLAM_LATTICE_CFG", "3,1,8")
+        with pytest.raises(Exception):
+            ctx.score_lattice(m, w["pose0"], w["step"], (3, 3, 3))
+    finally:
+        monkeypatch.delenv("B200SLAM_LATTICE_CFG", raising=False)
+        m.close()
+
+
 @pytest.mark.parametrize("nbeams", [0, 1, 31, 64, 65, 129, 1079, 2500])
 def test_lattice_ragged_beam_counts(ctx, oracle, synth, nbeams):
     w = synth.make_workload("tiny")
@@ -276,3 +294,73 @@ def test_config3_full_size_4m_x_1080_properties(ctx, oracle, synth, b200slam):
         assert index == res.best_index and np.float32(score) == np.float32(res.best_score)
     finally:
         m.close()
+
+
+@pytest.mark.gpu
+def test_config4_full_size_pyramid_10m_properties(ctx, oracle, synth, b200slam):
+    """BASELINE configs[4] at full size: 3-level EDT pyramid (2048^2 @ 4p, 4096^2 @ 2p, 8192^2 @ p) and a
+    coarse-to-fine search of 160 x 250 x 250 = 10 M coarse poses x 1080 beams, then 16 x 32 x 32 twice,
+    each level seeded by the previous winner (main.c:901-918 generalised; the reference has no 3-level
+    pyramid, so this is parity with the oracle restatement).  10.8 G evaluations are out of the oracle's
+    reach, so: (1) every level's winner re-scored by the oracle as a single pose matches bit for bit and
+    the NEXT level's lattice really is centred on it, (2) the coarse score table is consistent with the
+    winner (min, lowest index among equals), (3) one oracle-scored theta slice of the coarse level and the
+    two complete fine levels match bit for bit, (4) eight row shards of the coarse level merge to the same
+    winner."""
+    w = synth.make_workload("config3")
+    occ_f = w["occ"]
+    steps = np.array([[0.2, 0.2, 0.034908], [0.1, 0.1, 0.017454], [0.05, 0.05, 0.008727]], np.float32)
+    ns = np.array([[160, 250, 250], [16, 32, 32], [16, 32, 32]], np.int32)
+    maps, omaps = [], []
+    try:
+        for f in (4, 2, 1):
+            rows, cols = occ_f.shape[0] // f, occ_f.shape[1] // f
+            occ = occ_f.reshape(rows, f, cols, f).max(axis=(1, 3)).astype(np.int32)
+            pixel, tl = synth.centred_geometry(rows, cols, 0.1 * f)
+            mp = ctx.new_map(rows, cols)
+            mp.set_geometry(pixel, tl).upload_occupancy(occ).edt()
+            maps.append(mp)
+            omaps.append(oracle.make_map(mp.download_field(), pixel, tl))
+        ctx.scan_upload(w["scan_x"], w["scan_y"])
+        got = ctx.pyramid_match(maps, w["pose0"], steps, ns)
+        seed = np.array(w["pose0"], np.float32)
+        for lvl, g in enumerate(got):
+            n = tuple(int(x) for x in ns[lvl])
+            # (1) the winner, re-scored by the oracle as a single pose
+            _, oscore, ohits = oracle.score_poses(omaps[lvl], w["scan_x"], w["scan_y"], g.pose().reshape(1, 3))
+            assert bits(oscore)[0] == bits(np.float32(g.best_score)) and int(ohits[0]) == g.best_hits
+            # ... and it is the lattice point of THIS level's seed that its index names
+            ith, rem = divmod(g.best_index, n[1] * n[2])
+            itx, ity = divmod(rem, n[2])
+            want_pose = [b200slam.lattice_value(float(seed[d]), float(steps[lvl][d]), k, n[a])
+                         for d, k, a in ((0, itx, 1), (1, ity, 2), (2, ith, 0))]
+            assert np.array_equal(bits(g.pose()), bits(np.array(want_pose, np.float32)))
+            if lvl == 0:
+                res, scores, _ = ctx.score_lattice(maps[0], seed, steps[0], n, want_scores=True)
+                assert res.best_index == g.best_index
+                # (2) table vs winner
+                assert bits(scores[g.best_index]) == bits(np.float32(g.best_score))
+                assert g.best_index == int(np.flatnonzero(scores == scores.min())[0])
+                # (3) one theta slice through the oracle
+                per_theta = n[1] * n[2]
+                th = b200slam.lattice_value(float(seed[2]), float(steps[0][2]), 97, n[0])
+                _, oslice, _ = oracle.score_lattice(omaps[0], w["scan_x"], w["scan_y"],
+                                                    np.array([seed[0], seed[1], th], np.float32), steps[0], (1, n[1], n[2]))
+                assert np.array_equal(bits(oslice), bits(scores[97 * per_theta:98 * per_theta]))
+                # (4) shards
+                keys = []
+                for r in range(8):
+                    rb, re = b200slam.shard_range(n[0] * n[1], 8, r)
+                    part = ctx.score_lattice_rows(maps[0], seed, steps[0], n, rb, re)
+                    keys.append(b200slam.pack_key(part.best_score, part.best_index))
+                score, index = b200slam.unpack_key(b200slam.merge_keys(np.array(keys, np.uint64)))
+                assert index == g.best_index and np.float32(score) == np.float32(g.best_score)
+            else:
+                # (3) the refinement levels are small enough for the oracle in full
+                ores, _, _ = oracle.score_lattice(omaps[lvl], w["scan_x"], w["scan_y"], seed, steps[lvl], n)
+                assert ores.best_index == g.best_index and ores.best_hits == g.best_hits
+                assert np.float32(ores.best_score).tobytes() == np.float32(g.best_score).tobytes()
+            seed = g.pose()
+    finally:
+        for mp in maps:
+            mp.close()

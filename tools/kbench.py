@@ -82,6 +82,33 @@ def bench_lattice(mod, synth, ctx, names):
         m.close()
 
 
+def bench_lattice_sweep(mod, synth, ctx, name="config1"):
+    """Tile-shape sweep of the lattice matcher through B200SLAM_LATTICE_CFG (read at every launch)."""
+    w = synth.make_workload(name)
+    rows, cols = w["occ"].shape
+    m = ctx.new_map(rows, cols)
+    m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+    ctx.scan_upload(w["scan_x"], w["scan_y"])
+    n = w["n"]
+    evals = n[0] * n[1] * n[2] * len(w["scan_x"])
+    ref = None
+    for cfg in os.environ.get("SWEEP", "1,1,8 2,1,8 2,1,4 4,1,4 4,1,2 4,1,8 8,1,2 8,1,4 1,1,4").split():
+        os.environ["B200SLAM_LATTICE_CFG"] = cfg
+        ms = time_loop(ctx, lambda i: ctx.score_lattice_async(m, w["pose0"], w["step"], n), 200)
+        # isolated: an event pair around every launch (no overlap with the neighbours)
+        K = 50
+        for i in range(K):
+            ctx.event_record(100 + 2 * i); ctx.score_lattice_async(m, w["pose0"], w["step"], n); ctx.event_record(101 + 2 * i)
+        ctx.sync()
+        iso = sorted(ctx.event_elapsed_ms(100 + 2 * i, 101 + 2 * i) for i in range(K))[K // 2]
+        r = ctx.match_fetch()
+        ref = ref or (r.best_index, r.best_score)
+        print(f"lattice {name} cfg={cfg:7s}: back-to-back {ms * 1e3:8.2f} us  isolated median {iso * 1e3:8.2f} us  "
+              f"{evals / ms / 1e9:7.3f} Tevals/s  same_result={(r.best_index, r.best_score) == ref}", flush=True)
+    os.environ.pop("B200SLAM_LATTICE_CFG", None)
+    m.close()
+
+
 def bench_poses(mod, synth, ctx):
     w = synth.make_workload("config1")
     rows, cols = w["occ"].shape
@@ -133,6 +160,8 @@ def main():
             bench_edt(mod, synth, ctx, [(8192, 8192)])
         if "lattice" in what:
             bench_lattice(mod, synth, ctx, ["tiny", "config1", "config3"])
+        if "latsweep" in what:
+            bench_lattice_sweep(mod, synth, ctx)
         if "poses" in what:
             bench_poses(mod, synth, ctx)
 
