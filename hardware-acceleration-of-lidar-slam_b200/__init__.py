@@ -24,6 +24,7 @@ HEADER_PATH = os.path.join(REPO_ROOT, "include", "b200slam.h")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 UNIQUE_ID_BYTES = 128
+MATCH_LATENCY, MATCH_THROUGHPUT = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
@@ -100,6 +101,7 @@ def load_library() -> C.CDLL:
         "b200slam_match_fetch": (i, [vp, C.POINTER(Match)]),
         "b200slam_score_poses": (i, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.POINTER(Match)]),
         "b200slam_fastmatch": (i, [vp, vp, c_float_p, c_float_p, c_float_p, vp, c_int_p]),
+        "b200slam_set_match_mode": (i, [vp, i]),
         "b200slam_graph_begin": (i, [vp]),
         "b200slam_graph_end": (i, [vp, C.POINTER(vp)]),
         "b200slam_graph_launch": (i, [vp, vp]),
@@ -284,6 +286,10 @@ class Context:
 
     def stream(self) -> int:
         return int(self.L.b200slam_stream(self.h) or 0)
+
+    def set_match_mode(self, mode: int):
+        """MATCH_LATENCY (default) or MATCH_THROUGHPUT: tile-shape policy of the lattice kernel."""
+        self._check(self.L.b200slam_set_match_mode(self.h, int(mode)))
 
     def launch_count(self) -> int:
         return int(self.L.b200slam_launch_count(self.h))

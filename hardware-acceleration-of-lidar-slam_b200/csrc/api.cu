@@ -109,6 +109,15 @@ int b200slam_sync(b200slam_ctx *ctx)
 
 void *b200slam_stream(b200slam_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+int b200slam_set_match_mode(b200slam_ctx *ctx, int mode)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    if (mode != B200SLAM_MATCH_LATENCY && mode != B200SLAM_MATCH_THROUGHPUT)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "unknown match mode %d", mode);
+    ctx->match_mode = mode;
+    return B200SLAM_OK;
+}
+
 uint64_t b200slam_launch_count(const b200slam_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int b200slam_device_info(const b200slam_ctx *ctx, char *name, int *sm_count, int *cc_major,

@@ -72,6 +72,7 @@ struct b200slam_ctx {
     uint64_t launches = 0;
     bool use_pdl = true;         // programmatic dependent launch between consecutive scan-matching kernels
     bool prev_launch_was_lattice = false;   // the last kernel queued on the stream was a scan-matching kernel
+    int match_mode = B200SLAM_MATCH_LATENCY; // tile-shape policy of the lattice kernel (b200slam_set_match_mode)
 
     // scan (sensor frame), device resident
     float *d_scan_x = nullptr, *d_scan_y = nullptr;   // one allocation: x[scan_cap] | y[scan_cap]

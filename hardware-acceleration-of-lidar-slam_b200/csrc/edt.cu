@@ -316,8 +316,10 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     using C = EdtCfg<R, NW>;
     auto kern = edt_tma_kernel<R, NW, NST>;
     const size_t smem = edt_smem_bytes<R, NW, NST>(t2);
-    static int occupancy = 0;        // resident CTAs per SM (per instantiation)
-    static size_t smem_set = 0;
+    static int occupancy_dev[64] = {};        // resident CTAs per SM (per instantiation and device)
+    static size_t smem_set_dev[64] = {};
+    int &occupancy = occupancy_dev[ctx->device & 63];
+    size_t &smem_set = smem_set_dev[ctx->device & 63];
     if (smem > smem_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;

@@ -611,10 +611,12 @@ int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T
     cb = (cb + 3) & ~3;                                   // keeps the int4 row loads aligned
     A.cb = cb;
     const size_t smem = (size_t)(cb + GUARD) * per_beam;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    // Opt in to large dynamic shared memory once per instantiation and device -- unconditionally: the
+    // 48 KB default applies to static + dynamic together, so a chunk just under 48 KB needs it too.
+    static bool smem_set[64] = {};
+    if (!smem_set[ctx->device & 63]) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
-        smem_set = 104 * 1024;
+        smem_set[ctx->device & 63] = true;
     }
     dim3 grid((A.nty + TYT - 1) / TYT, (A.ntx + TXT - 1) / TXT, nth_cover);
     A.total_ctas = grid.x * grid.y * grid.z;
@@ -679,11 +681,14 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     // Tile shape.  A thread owns TYPT candidates (consecutive ty); per warp and beam the inner loop
     // costs 1 (column LDS) + TYPT/4 (row LDS.128) + 1.5 * TYPT (gathers, ~1.5 lines each) L1
     // wavefronts, so big register tiles are cheaper per evaluation (the `per_eval` factors below,
-    // relative to TYPT = 16) -- but a sweep is only as fast as its busiest SM.  Model: every SM
-    // runs ceil(CTAs / SMs) tiles one after the other; pick the shape with the lowest
-    // tiles-per-SM x candidates-per-tile x per-evaluation cost.  (Measured on config 1,
-    // 64 x 32 x 32 x 360 beams: 32 x 16 tiles with 16-beam groups 24.9 us isolated / 9.8 us back
-    // to back, 32 x 8 tiles 27.0 / 14.9, 32 x 32 tiles 33.2 / 13.4.)
+    // relative to TYPT = 16) -- but a single sweep is only as fast as its busiest SM.  Latency
+    // mode (default): every SM runs ceil(CTAs / SMs) tiles one after the other; pick the shape
+    // with the lowest tiles-per-SM x candidates-per-tile x per-evaluation cost.  Throughput mode
+    // (b200slam_set_match_mode: many independent matches in flight): total work only, CTAs x
+    // candidates-per-tile x per-evaluation cost -- the other kernels in flight fill the SMs one
+    // launch leaves idle.  Measured on config 1 (64 x 32 x 32 x 360 beams; one launch alone /
+    // EDT+match step with the next EDT running under the match): 32 x 16 tiles with 16-beam
+    // groups 24.9 / 31.6 us, 32 x 8 tiles 27.1 / 27.4 us, 32 x 32 tiles 33.3 / 23.2 us.
     struct Shape { int typt, wx, wy, um; double per_eval; };
     static const Shape shapes[] = {
         {16, 2, 4, 1, 1.00}, {8, 1, 8, 1, 1.05}, {4, 1, 8, 1, 1.13}, {2, 1, 8, 2, 1.40}, {1, 1, 8, 1, 1.95}, {1, 1, 4, 1, 1.95},
@@ -699,7 +704,8 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
             double ctas = (double)nth_cover * ((L.ntx + txt - 1) / txt) * ((L.nty + tyt - 1) / tyt) * covered;
             if (ctas < 1.0) ctas = 1.0;
             const double per_sm = (double)((long long)((ctas + ctx->sm_count - 1) / ctx->sm_count));
-            const double cost = (per_sm < 1.0 ? 1.0 : per_sm) * txt * tyt * sh.per_eval;
+            const double units = ctx->match_mode == B200SLAM_MATCH_THROUGHPUT ? ctas : (per_sm < 1.0 ? 1.0 : per_sm);
+            const double cost = units * txt * tyt * sh.per_eval;
             if (cost < best_cost * 0.999) {                                // ties: the bigger register tile
                 best_cost = cost;
                 pick_t = sh.typt; pick_x = sh.wx; pick_y = sh.wy; pick_m = sh.um;

@@ -185,6 +185,17 @@ int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3]
                        const float search_resolution[3], float pose_out[3], float *best_hits,
                        int *best_hits_size);
 
+/* ---- scheduling hint for the scan matcher ---------------------------------------------
+ * The lattice kernel comes in several tile shapes (candidates per thread x warps per CTA).
+ * B200SLAM_MATCH_LATENCY (default): one match at a time, as FastMatch is called per scan
+ * (main.c:902-918) -- pick the shape whose busiest SM finishes first.  B200SLAM_MATCH_THROUGHPUT:
+ * many independent matches are kept in flight (batched replay, bench.py's pipelined turn) --
+ * pick the shape with the fewest L1 wavefronts per evaluation even if one launch alone then
+ * occupies only part of the GPU.  Results are identical bit for bit in either mode. */
+#define B200SLAM_MATCH_LATENCY    0
+#define B200SLAM_MATCH_THROUGHPUT 1
+int b200slam_set_match_mode(b200slam_ctx *ctx, int mode);
+
 /* ---- CUDA graphs -----------------------------------------------------------------
  * The replay loop's per-scan work (EDT + two matches, main.c:865-918) is a handful of
  * microsecond-scale kernels; capture the *_async / map_edt calls once and replay them.

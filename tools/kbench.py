@@ -92,7 +92,7 @@ def bench_lattice_sweep(mod, synth, ctx, name="config1"):
     n = w["n"]
     evals = n[0] * n[1] * n[2] * len(w["scan_x"])
     ref = None
-    for cfg in os.environ.get("SWEEP", "1,1,8 2,1,8 2,1,4 4,1,4 4,1,2 4,1,8 8,1,2 8,1,4 1,1,4").split():
+    for cfg in os.environ.get("SWEEP", "1,1,8 2,1,8,2 2,1,8 4,1,8 8,1,8 16,2,4 1,1,4").split():
         os.environ["B200SLAM_LATTICE_CFG"] = cfg
         ms = time_loop(ctx, lambda i: ctx.score_lattice_async(m, w["pose0"], w["step"], n), 200)
         # isolated: an event pair around every launch (no overlap with the neighbours)
@@ -107,6 +107,60 @@ def bench_lattice_sweep(mod, synth, ctx, name="config1"):
               f"{evals / ms / 1e9:7.3f} Tevals/s  same_result={(r.best_index, r.best_score) == ref}", flush=True)
     os.environ.pop("B200SLAM_LATTICE_CFG", None)
     m.close()
+
+
+def bench_pipeline_ab(mod, synth, ctx, name="config1"):
+    """A/B of tile shapes inside bench.py's pipelined step (EDT of step i+1 on a second stream under the
+    match of step i, one CUDA graph per turn of the map ring), all in one process, interleaved twice."""
+    w = synth.make_workload(name)
+    rows, cols = w["occ"].shape
+    n = w["n"]
+    ring = 9 if rows <= 2048 else 2
+    maps = []
+    for i in range(ring):
+        m = ctx.new_map(rows, cols)
+        m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(
+            w["occ"] if i == 0 else synth.grid_rooms(rows, cols, synth.SEED_GRID + i))
+        maps.append(m)
+    ctx.scan_upload(w["scan_x"], w["scan_y"])
+    ctx_e = mod.Context(0)
+    evals = n[0] * n[1] * n[2] * len(w["scan_x"])
+    cfgs = os.environ.get("SWEEP", "1,1,8 2,1,8,2 4,1,8 2,1,8").split()
+    graphs = {}
+    for cfg in cfgs:
+        os.environ["B200SLAM_LATTICE_CFG"] = cfg.split("/")[0]
+        os.environ.pop("B200SLAM_EDT_CB", None)
+        if "/" in cfg:
+            os.environ["B200SLAM_EDT_CB"] = cfg.split("/")[1]
+        for i in range(ring):
+            maps[i].edt(10.0); ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n)
+            ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
+        ctx.sync(); ctx_e.sync()
+        ctx.graph_begin()
+        for i in range(ring):
+            maps[i].edt(10.0); ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n)
+        gs = ctx.graph_end()
+        ctx.graph_begin()
+        ctx.event_record(3000); ctx_e.event_wait(ctx, 3000)
+        for i in range(ring):
+            ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
+            ctx_e.event_record(3100 + i); ctx.event_wait(ctx_e, 3100 + i)
+            ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n)
+        ctx_e.event_record(3200); ctx.event_wait(ctx_e, 3200)
+        gp = ctx.graph_end()
+        graphs[cfg] = (gs, gp)
+    os.environ.pop("B200SLAM_LATTICE_CFG", None)
+    os.environ.pop("B200SLAM_EDT_CB", None)
+    for rep in range(2):
+        for cfg in cfgs:
+            gs, gp = graphs[cfg]
+            ser = time_loop(ctx, lambda i: ctx.graph_launch(gs), 30) / ring
+            pip = time_loop(ctx, lambda i: ctx.graph_launch(gp), 30) / ring
+            print(f"pipeline {name} rep {rep} cfg={cfg:11s}: serial {ser * 1e3:7.2f} us/step  pipelined {pip * 1e3:7.2f} us/step "
+                  f"({evals / pip / 1e9:6.3f} Tevals/s)", flush=True)
+    ctx_e.close()
+    for m in maps:
+        m.close()
 
 
 def bench_poses(mod, synth, ctx):
@@ -160,6 +214,8 @@ def main():
             bench_edt(mod, synth, ctx, [(8192, 8192)])
         if "lattice" in what:
             bench_lattice(mod, synth, ctx, ["tiny", "config1", "config3"])
+        if "pipe" in what:
+            bench_pipeline_ab(mod, synth, ctx)
         if "latsweep" in what:
             bench_lattice_sweep(mod, synth, ctx)
         if "poses" in what:
