@@ -25,6 +25,7 @@ HEADER_PATH = os.path.join(REPO_ROOT, "include", "b200slam.h")
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4, -5
 UNIQUE_ID_BYTES = 128
 MATCH_LATENCY, MATCH_THROUGHPUT = 0, 1
+EDT_GATHER_NCCL, EDT_GATHER_P2P = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
@@ -102,6 +103,9 @@ def load_library() -> C.CDLL:
         "b200slam_score_poses": (i, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.POINTER(Match)]),
         "b200slam_fastmatch": (i, [vp, vp, c_float_p, c_float_p, c_float_p, vp, c_int_p]),
         "b200slam_set_match_mode": (i, [vp, i]),
+        "b200slam_map_edt_rows": (i, [vp, vp, f, i, i]),
+        "b200slam_map_share": (i, [vp, vp]),
+        "b200slam_map_edt_sharded": (i, [vp, vp, f, i]),
         "b200slam_graph_begin": (i, [vp]),
         "b200slam_graph_end": (i, [vp, C.POINTER(vp)]),
         "b200slam_graph_launch": (i, [vp, vp]),
@@ -230,6 +234,21 @@ class Map:
 
     def edt(self, max_dist: float = 10.0):
         self.ctx._check(self.ctx.L.b200slam_map_edt(self.ctx.h, self.h, max_dist))
+        return self
+
+    def edt_rows(self, row_begin: int, row_end: int, max_dist: float = 10.0):
+        """Output rows [row_begin, row_end) only (this GPU)."""
+        self.ctx._check(self.ctx.L.b200slam_map_edt_rows(self.ctx.h, self.h, max_dist, row_begin, row_end))
+        return self
+
+    def share(self):
+        """Collective: maps every rank's copy of this map's field through CUDA IPC."""
+        self.ctx._check(self.ctx.L.b200slam_map_share(self.ctx.h, self.h))
+        return self
+
+    def edt_sharded(self, mode: int = EDT_GATHER_NCCL, max_dist: float = 10.0):
+        """Collective: every rank transforms its row block; blocks exchanged by NCCL or inside the kernel."""
+        self.ctx._check(self.ctx.L.b200slam_map_edt_sharded(self.ctx.h, self.h, max_dist, mode))
         return self
 
     def download_field(self, out: np.ndarray | None = None) -> np.ndarray:

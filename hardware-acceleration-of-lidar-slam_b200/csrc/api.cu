@@ -185,6 +185,7 @@ void b200slam_map_destroy(b200slam_ctx *ctx, b200slam_map *map)
 {
     if (!map) return;
     if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (map->shared_nranks) comm_unshare_map(ctx, map);
     cudaFree(map->d_occ);
     cudaFree(map->d_field_alloc);
     delete map;

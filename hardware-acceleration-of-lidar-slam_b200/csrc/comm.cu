@@ -20,6 +20,9 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     char why[256] = "";
 };
@@ -52,6 +55,9 @@ NcclApi *nccl_api()
     SYM(CommInitRank, "ncclCommInitRank");
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(AllGather, "ncclAllGather");
+    SYM(Broadcast, "ncclBroadcast");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return &api;
@@ -70,6 +76,75 @@ int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send, unsi
     if (r != ncclSuccess)
         return b200slam_set_error(ctx, B200SLAM_ERR_NCCL, "ncclAllGather -> %s", api->GetErrorString(r));
     return B200SLAM_OK;
+}
+
+int comm_gather_row_blocks(b200slam_ctx *ctx, float *d_field, int pitch, int rows)
+{
+    NcclApi *api = nccl_api();
+    if (!api->handle || !ctx->nccl_comm)
+        return b200slam_set_error(ctx, B200SLAM_ERR_NCCL, "no communicator (%s)", api->why);
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int n = ctx->nranks;
+    ncclResult_t r = ncclSuccess;
+    if (rows % n == 0) {
+        const size_t blk = (size_t)(rows / n) * pitch;
+        r = api->AllGather(d_field + blk * ctx->rank, d_field, blk, ncclFloat, comm, ctx->stream);
+    } else {
+        r = api->GroupStart();
+        for (int k = 0; k < n && r == ncclSuccess; ++k) {
+            int64_t b, e;
+            b200slam_shard_range(rows, n, k, &b, &e);
+            if (e > b) {
+                float *blk = d_field + (size_t)b * pitch;
+                r = api->Broadcast(blk, blk, (size_t)(e - b) * pitch, ncclFloat, k, comm, ctx->stream);
+            }
+        }
+        ncclResult_t r2 = api->GroupEnd();
+        if (r == ncclSuccess) r = r2;
+    }
+    if (r != ncclSuccess)
+        return b200slam_set_error(ctx, B200SLAM_ERR_NCCL, "field row-block exchange -> %s", api->GetErrorString(r));
+    return B200SLAM_OK;
+}
+
+namespace {
+
+// Device-side barrier over the ranks: everybody stores the barrier's number into its slot of
+// every peer's buffer and waits until all the slots of its own buffer have reached it.  The
+// system-scope fences order the peer-memory stores of the kernels queued before the barrier
+// (the row-sharded EDT's remote rows) against the flag, and the loads of the kernels behind it.
+__global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, unsigned long long epoch)
+{
+    const int r = threadIdx.x;
+    __threadfence_system();
+    if (r < X.nranks) {
+        *reinterpret_cast<volatile unsigned long long *>(&X.peers[r]->bar[X.rank]) = epoch;
+        const volatile unsigned long long *mine = &X.peers[X.rank]->bar[r];
+        while (*mine < epoch) {}
+    }
+    __threadfence_system();
+}
+
+}  // namespace
+
+int comm_peer_barrier(b200slam_ctx *ctx)
+{
+    if (!ctx->p2p_ready) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "peer memory exchange is not set up");
+    XchgArgs X;
+    X.peers = ctx->d_peers; X.nranks = ctx->nranks; X.rank = ctx->rank;
+    peer_barrier_kernel<<<1, 64, 0, ctx->stream>>>(X, ++ctx->bar_epoch);
+    LAUNCH_CHECK(ctx);
+    return B200SLAM_OK;
+}
+
+void comm_unshare_map(b200slam_ctx *ctx, b200slam_map *map)
+{
+    for (int r = 0; r < map->shared_nranks; ++r) {
+        if (map->peer_alloc[r] && map->peer_alloc[r] != map->d_field_alloc) cudaIpcCloseMemHandle(map->peer_alloc[r]);
+        map->peer_alloc[r] = nullptr;
+    }
+    map->shared_nranks = 0;
+    (void)ctx;
 }
 
 namespace {
@@ -182,6 +257,88 @@ int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id_i
     // are all-gathered with NCCL instead (same answers, ~20 us more latency per match).
     if (nranks > 1 && !getenv("B200SLAM_NO_P2P")) setup_peer_exchange(ctx);
     return B200SLAM_OK;
+}
+
+/* Collective: every rank calls it with its own copy of the (identically sized) map. */
+int b200slam_map_share(b200slam_ctx *ctx, b200slam_map *map)
+{
+    if (!ctx || !map) return B200SLAM_ERR_ARG;
+    if (!ctx->nccl_comm || ctx->nranks < 2) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_comm_init first");
+    if (ctx->nranks > 8) return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "peer-shared maps support up to 8 ranks");
+    if (map->shared_nranks) return B200SLAM_OK;
+    const int n = ctx->nranks;
+    constexpr int REC = 10;                       // 64-byte handle + ok flag + size check
+    unsigned long long rec[REC] = {0}, all[8 * REC] = {0};
+    cudaIpcMemHandle_t h;
+    bool ok = ctx->p2p_ready && cudaIpcGetMemHandle(&h, map->d_field_alloc) == cudaSuccess;
+    if (ok) memcpy(rec, &h, sizeof h);
+    rec[8] = ok ? 1 : 0;
+    rec[9] = ((unsigned long long)map->cap_rows << 32) | (unsigned int)map->field_pitch;
+    unsigned long long *d_send = nullptr, *d_recv = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_send, sizeof rec));
+    CUDA_TRY(ctx, cudaMalloc(&d_recv, sizeof(rec) * n));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_send, rec, sizeof rec, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = comm_allgather_u64(ctx, d_send, d_recv, REC);
+    if (rc == B200SLAM_OK) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(all, d_recv, sizeof(rec) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(d_send); cudaFree(d_recv);
+    if (rc) return rc;
+    for (int r = 0; r < n; ++r) ok = ok && all[r * REC + 8] == 1 && all[r * REC + 9] == rec[9];
+    if (!ok) {
+        cudaGetLastError();
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "maps cannot be peer-shared (no CUDA IPC / P2P, or sizes differ)");
+    }
+    map->shared_nranks = n;
+    for (int r = 0; r < n; ++r) {
+        if (r == ctx->rank) { map->peer_alloc[r] = map->d_field_alloc; continue; }
+        cudaIpcMemHandle_t ph;
+        memcpy(&ph, &all[r * REC], sizeof ph);
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            comm_unshare_map(ctx, map);
+            return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "cudaIpcOpenMemHandle failed for rank %d's field", r);
+        }
+        map->peer_alloc[r] = static_cast<float *>(p);
+    }
+    return B200SLAM_OK;
+}
+
+int b200slam_map_edt_rows(b200slam_ctx *ctx, b200slam_map *map, float max_dist, int row_begin, int row_end)
+{
+    if (!ctx || !map) return B200SLAM_ERR_ARG;
+    return edt_launch_rows(ctx, map->d_occ, map->occ_pitch, map->d_field, map->field_pitch, map->rows, map->cols,
+                           max_dist, row_begin, row_end, nullptr, 0);
+}
+
+int b200slam_map_edt_sharded(b200slam_ctx *ctx, b200slam_map *map, float max_dist, int mode)
+{
+    if (!ctx || !map) return B200SLAM_ERR_ARG;
+    if (!ctx->nccl_comm || ctx->nranks < 2) return b200slam_map_edt(ctx, map, max_dist);
+    int64_t rb, re;
+    b200slam_shard_range(map->rows, ctx->nranks, ctx->rank, &rb, &re);
+    if (mode == B200SLAM_EDT_GATHER_NCCL) {
+        int rc = edt_launch_rows(ctx, map->d_occ, map->occ_pitch, map->d_field, map->field_pitch, map->rows,
+                                 map->cols, max_dist, (int)rb, (int)re, nullptr, 0);
+        if (rc) return rc;
+        return comm_gather_row_blocks(ctx, map->d_field, map->field_pitch, map->rows);
+    }
+    if (mode != B200SLAM_EDT_GATHER_P2P) return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "unknown gather mode %d", mode);
+    if (map->shared_nranks != ctx->nranks)
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_map_share must be called first");
+    float *peers[7];
+    int np = 0;
+    for (int r = 0; r < ctx->nranks; ++r)
+        if (r != ctx->rank) peers[np++] = map->peer_alloc[r] + B200SLAM_FIELD_PAD;
+    // nobody may still be reading the old field of a peer when its new rows arrive
+    int rc = comm_peer_barrier(ctx);
+    if (rc) return rc;
+    rc = edt_launch_rows(ctx, map->d_occ, map->occ_pitch, map->d_field, map->field_pitch, map->rows, map->cols,
+                         max_dist, (int)rb, (int)re, peers, np);
+    if (rc) return rc;
+    return comm_peer_barrier(ctx);           // ... and every rank's rows have landed everywhere
 }
 
 int b200slam_comm_destroy(b200slam_ctx *ctx)

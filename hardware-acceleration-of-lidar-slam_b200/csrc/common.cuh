@@ -24,6 +24,10 @@ struct b200slam_map {
     float *d_field = nullptr;         // [0][0]
     float pixel_size = 1.0f, top_left_x = 0.0f, top_left_y = 0.0f;
     bool has_geometry = false;
+    // b200slam_map_share: every rank's field allocation mapped here through CUDA IPC
+    // (peer_alloc[own rank] == d_field_alloc); nullptr until shared
+    float *peer_alloc[64] = {};
+    int shared_nranks = 0;
 };
 
 // Device-side state of a match.  work_key / tickets are the in-flight arg-min cell and the
@@ -58,6 +62,7 @@ struct XchgSlot {
 };
 struct XchgBuf {
     XchgSlot slot[XCHG_EPOCHS][XCHG_MAX_RANKS];
+    unsigned long long bar[XCHG_MAX_RANKS];   // peer barrier: bar[r] = last barrier epoch rank r has reached
 };
 struct XchgArgs {                     // kernel-side view; peers == nullptr: no exchange
     XchgBuf *const *peers;            // [nranks] device pointers (own buffer at [rank])
@@ -150,6 +155,7 @@ struct b200slam_ctx {
     XchgBuf **d_peers = nullptr;          // device array [nranks]
     XchgBuf *peer_ptrs[XCHG_MAX_RANKS] = {};   // host copy (for closing the IPC mappings)
     bool p2p_ready = false;
+    unsigned long long bar_epoch = 0;     // peer barriers issued so far (same on every rank)
 };
 
 int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
@@ -172,6 +178,12 @@ int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
 // ---- internal entry points between translation units ---------------------------------
 int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
                int field_pitch, int rows, int cols, float max_dist);
+
+// Output rows [row_begin, row_end) only, each row also stored into `npeers` (<= 7) other fields
+// of identical layout (peer GPUs' copies of the map, mapped through CUDA IPC).
+int edt_launch_rows(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
+                    int field_pitch, int rows, int cols, float max_dist, int row_begin, int row_end,
+                    float *const *peer_fields, int npeers);
 
 struct LatticeLaunch {
     const b200slam_map *map;
@@ -203,6 +215,13 @@ int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float mi
 
 int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send,
                        unsigned long long *d_recv, int count_per_rank);
+// In-place exchange of row blocks of a field of `rows` rows x `pitch` floats: rank r owns the rows
+// b200slam_shard_range(rows, nranks, r) (one ncclAllGather when the blocks are equal, grouped
+// ncclBroadcasts otherwise).
+int comm_gather_row_blocks(b200slam_ctx *ctx, float *d_field, int pitch, int rows);
+// All ranks wait for each other on the device (flags in peer memory); needs p2p_ready.
+int comm_peer_barrier(b200slam_ctx *ctx);
+void comm_unshare_map(b200slam_ctx *ctx, b200slam_map *map);
 
 // Programmatic dependent launch (PDL) between consecutive scan-matching kernels: a kernel lets
 // the NEXT one in the stream start (launch latency, table construction, its whole gather loop

@@ -97,10 +97,19 @@ __device__ __forceinline__ uint32_t h2scaled(uint32_t X)
 
 // Pass 2 for the R rows of one batch: window rows r .. r+2R feed output row r.
 // CHECK = false is the interior path (no row / column predicates).
-template <int R, bool CHECK>
+// NDEST > 1 (row-sharded transform on several GPUs): every result is also stored at the same
+// offset of each peer's field (peer_delta[k] = byte distance from this GPU's field to peer k's,
+// mapped through CUDA IPC), so the all-gather of the row blocks happens inside the kernel,
+// row by row, over NVLink.
+struct EdtPeers {
+    long long delta[7];
+    int n;                       // number of EXTRA destinations (0 = this GPU only)
+};
+template <int R, bool CHECK, bool MULTI>
 __device__ __forceinline__ void edt_emit_rows(const uint32_t (&win)[3 * R], const unsigned char *lut,
                                               uint32_t lane4, uint32_t clampv, unsigned char *pb,
-                                              uint32_t pitch_bytes, int rows_left, bool s0, bool s1)
+                                              uint32_t pitch_bytes, int rows_left, bool s0, bool s1,
+                                              const EdtPeers &peers)
 {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -125,6 +134,15 @@ __device__ __forceinline__ void edt_emit_rows(const uint32_t (&win)[3 * R], cons
             o[0] = f0;
             o[32] = f1;
         }
+        if (MULTI) {
+            for (int k = 0; k < peers.n; ++k) {
+                float *q = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(o) + peers.delta[k]);
+                if (!CHECK || r < rows_left) {
+                    if (!CHECK || s0) q[0] = f0;
+                    if (!CHECK || s1) q[32] = f1;
+                }
+            }
+        }
     }
 }
 
@@ -143,11 +161,15 @@ struct EdtCfg {
 };
 
 // Dynamic shared memory: [stage ring][sqrt table][mbarriers][arrival counters]
-template <int R, int NW, int NST>
+// Output rows [row_begin, row_end) only (the whole grid, or one rank's block of a row-sharded
+// transform); the input halo above and below comes from the full occupancy either way.
+template <int R, int NW, int NST, bool MULTI>
 __global__ void __launch_bounds__(EdtCfg<R, NW>::THREADS)
 edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out, uint32_t pitch_bytes,
-               int rows, int cols, int chunk_batches, int t2, float max_dist)
+               int row_begin, int row_end, int cols, int chunk_batches, int t2, float max_dist,
+               const __grid_constant__ EdtPeers peers)
 {
+    const int rows = row_end;
     using C = EdtCfg<R, NW>;
     constexpr int B = R;                          // rows per stage / batch
     constexpr int WN = 3 * R;                     // register window rows
@@ -160,7 +182,7 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * (64 * NW);
-    const int y0 = blockIdx.y * chunk_batches * B;
+    const int y0 = row_begin + blockIdx.y * chunk_batches * B;
     const int out_rows = min(chunk_batches * B, rows - y0);
     const int nb_out = (out_rows + B - 1) / B;
     const int nbl = nb_out + 2;                   // stages to stream: halo + chunk + halo
@@ -241,9 +263,9 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
             const int yb = y0 + (t - 2) * B;
             unsigned char *pb = obase + (size_t)(uint32_t)yb * pitch_bytes;
             if (interior && yb + B <= rows)
-                edt_emit_rows<R, false>(win, lut, lane4, clampv, pb, pitch_bytes, 0, true, true);
+                edt_emit_rows<R, false, MULTI>(win, lut, lane4, clampv, pb, pitch_bytes, 0, true, true, peers);
             else
-                edt_emit_rows<R, true>(win, lut, lane4, clampv, pb, pitch_bytes, rows - yb, s0, s1);
+                edt_emit_rows<R, true, MULTI>(win, lut, lane4, clampv, pb, pitch_bytes, rows - yb, s0, s1, peers);
         }
         // ---- slide the window down by B rows ------------------------------------------
 #pragma unroll
@@ -309,12 +331,12 @@ size_t edt_smem_bytes(int t2)
     return (size_t)NST * C::STAGE_BYTES + (size_t)(t2 + 1) * EDT_SCALE + NST * (sizeof(uint64_t) + sizeof(int));
 }
 
-template <int R, int NW, int NST>
+template <int R, int NW, int NST, bool MULTI>
 int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field, int field_pitch,
-               int rows, int cols, int t2, float max_dist)
+               int rows, int cols, int t2, float max_dist, int row_begin, int row_end, const EdtPeers &peers)
 {
     using C = EdtCfg<R, NW>;
-    auto kern = edt_tma_kernel<R, NW, NST>;
+    auto kern = edt_tma_kernel<R, NW, NST, MULTI>;
     const size_t smem = edt_smem_bytes<R, NW, NST>(t2);
     static int occupancy_dev[64] = {};        // resident CTAs per SM (per instantiation and device)
     static size_t smem_set_dev[64] = {};
@@ -352,7 +374,7 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     // that only run pass 1, plus the pipeline fill); pick the cb that minimises waves x cost
     // for the number of CTAs the GPU holds at once.
     const int gx = (cols + 64 * NW - 1) / (64 * NW);
-    const int nbatch = (rows + R - 1) / R;
+    const int nbatch = (row_end - row_begin + R - 1) / R;
     const long resident = (long)ctx->sm_count * occupancy;
     int best_cb = 1;
     double best_cost = 1e300;
@@ -365,21 +387,29 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     if (nbatch >= 14 && (long)gx * ((nbatch + 13) / 14) * 2 >= 5 * resident) best_cb = 14;
     if (const char *e = getenv("B200SLAM_EDT_CB")) best_cb = max(1, min(atoi(e), nbatch));   // tuning knob
     const int gy = (nbatch + best_cb - 1) / best_cb;
-    kern<<<dim3(gx, gy), C::THREADS, smem, ctx->stream>>>(tmap, d_field, (uint32_t)field_pitch * 4u, rows, cols, best_cb, t2,
-                                                         max_dist);
+    kern<<<dim3(gx, gy), C::THREADS, smem, ctx->stream>>>(tmap, d_field, (uint32_t)field_pitch * 4u, row_begin, row_end, cols,
+                                                         best_cb, t2, max_dist, peers);
     LAUNCH_CHECK(ctx);
     return B200SLAM_OK;
 }
 
 template <int R>
 int launch_fused(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field, int field_pitch,
-                 int rows, int cols, int t2, float max_dist)
+                 int rows, int cols, int t2, float max_dist, int row_begin, int row_end, const EdtPeers &peers)
 {
+    if (peers.n > 0)
+        return launch_tma<R, 3, 3, true>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist,
+                                         row_begin, row_end, peers);
     if (const char *e = getenv("B200SLAM_EDT_NST")) {
-        if (atoi(e) == 2) return launch_tma<R, 3, 2>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
-        if (atoi(e) == 4) return launch_tma<R, 3, 4>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
+        if (atoi(e) == 2)
+            return launch_tma<R, 3, 2, false>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist,
+                                              row_begin, row_end, peers);
+        if (atoi(e) == 4)
+            return launch_tma<R, 3, 4, false>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist,
+                                              row_begin, row_end, peers);
     }
-    return launch_tma<R, 3, 3>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
+    return launch_tma<R, 3, 3, false>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist,
+                                      row_begin, row_end, peers);
 }
 
 }  // namespace
@@ -387,7 +417,24 @@ int launch_fused(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *
 int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
                int field_pitch, int rows, int cols, float max_dist)
 {
+    return edt_launch_rows(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, max_dist, 0, rows, nullptr, 0);
+}
+
+int edt_launch_rows(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
+                    int field_pitch, int rows, int cols, float max_dist, int row_begin, int row_end,
+                    float *const *peer_fields, int npeers)
+{
     if (rows <= 0 || cols <= 0) return B200SLAM_OK;
+    if (row_begin < 0 || row_end > rows || npeers < 0 || npeers > 7)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "EDT row range [%d, %d) of %d rows / %d peers", row_begin,
+                                  row_end, rows, npeers);
+    if (row_end <= row_begin) return B200SLAM_OK;
+    EdtPeers peers;
+    peers.n = npeers;
+    for (int k = 0; k < 7; ++k)
+        peers.delta[k] = k < npeers ? (long long)(reinterpret_cast<const char *>(peer_fields[k]) -
+                                                  reinterpret_cast<const char *>(d_field))
+                                    : 0;
     if (!(max_dist > 0.0f) || max_dist > 255.0f)
         return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "max_dist %g out of (0, 255]", max_dist);
     // Window radius and clamp index exactly as the float compare at main.c:235 decides.
@@ -401,7 +448,7 @@ int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     const bool tma_ok = (occ_pitch % 4 == 0) && ((uintptr_t)d_occ % 16 == 0);
     if (tma_ok) {
         switch (R) {
-#define CASE(RR) case RR: return launch_fused<RR>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist);
+#define CASE(RR) case RR: return launch_fused<RR>(ctx, d_occ, occ_pitch, d_field, field_pitch, rows, cols, t2, max_dist, row_begin, row_end, peers);
             CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
             CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
 #undef CASE
@@ -409,7 +456,9 @@ int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
         }
     }
     static_assert(EDT_MAX_FUSED_R == 14, "switch above covers 1..14");
-    // R == 0 (max_dist <= 1) or R > 14: generic two-pass kernels.
+    // R == 0 (max_dist <= 1) or R > 14: generic two-pass kernels (whole grid, this GPU only).
+    if (row_begin != 0 || row_end != rows || npeers > 0)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "row-sharded EDT needs 1 < max_dist <= 15 (radius %d)", R);
     const size_t need = (size_t)rows * cols;
     if (need > ctx->edt_scratch_cap) {
         if (ctx->d_edt_scratch) cudaFree(ctx->d_edt_scratch);

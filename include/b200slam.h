@@ -260,6 +260,29 @@ int b200slam_pyramid_match(b200slam_ctx *ctx, b200slam_map *const *maps, int lev
 int b200slam_comm_unique_id(void *id_out /*[128]*/);            /* rank 0 */
 int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id /*[128]*/);
 int b200slam_comm_destroy(b200slam_ctx *ctx);
+/* Row-sharded transform (BASELINE configs[3]: "8192x8192 grid EDT (row-sharded)").  The
+ * transform is clamped at max_dist, so a block of output rows needs only a ceil(max_dist)-1 row
+ * halo of the INPUT, which every rank already holds (the occupancy is replicated): nothing is
+ * exchanged to compute.  What has to travel is the OUTPUT, because every rank scores against the
+ * whole field:
+ *   b200slam_map_edt_rows     this GPU only, output rows [row_begin, row_end) (also the cheap way
+ *                             to refresh the field after a local change of the occupancy);
+ *   b200slam_map_edt_sharded  every rank transforms its block b200slam_shard_range(rows, nranks,
+ *                             rank) and the blocks are exchanged so that all ranks end with the
+ *                             whole field.  B200SLAM_EDT_GATHER_NCCL: in-place ncclAllGather (equal
+ *                             blocks) or grouped ncclBroadcasts.  B200SLAM_EDT_GATHER_P2P: the EDT
+ *                             kernel itself stores every row it produces into every peer's field
+ *                             over NVLink (fields mapped through CUDA IPC by b200slam_map_share,
+ *                             <= 8 ranks), bracketed by two device-side barriers -- compute and
+ *                             all-gather are one kernel.
+ * Collective calls: every rank must make them in the same order with identically sized maps.
+ * Without a communicator b200slam_map_edt_sharded is b200slam_map_edt. */
+#define B200SLAM_EDT_GATHER_NCCL 0
+#define B200SLAM_EDT_GATHER_P2P  1
+int b200slam_map_edt_rows(b200slam_ctx *ctx, b200slam_map *map, float max_dist, int row_begin, int row_end);
+int b200slam_map_share(b200slam_ctx *ctx, b200slam_map *map);
+int b200slam_map_edt_sharded(b200slam_ctx *ctx, b200slam_map *map, float max_dist, int mode);
+
 /* Even split of `total` units over nranks (pure host arithmetic). */
 void b200slam_shard_range(int64_t total, int nranks, int rank, int64_t *begin, int64_t *end);
 /* Systematic-resampling slots owned by a rank (pure host): the k in [0, n_global) whose

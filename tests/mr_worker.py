@@ -121,6 +121,32 @@ def run_gpu(mod, synth):
     m.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
     check(np.array_equal(m.download_field().view(np.uint32), pb["field"].view(np.uint32)), "EDT differs")
     ctx.scan_upload(w["scan_x"], w["scan_y"])
+    # ---- row-sharded EDT: every rank transforms its block, blocks exchanged --------
+    # NCCL in-place gather (equal and unequal blocks), then the fused kernel that stores each row
+    # into every peer's field over NVLink; a sentinel field shows that every row really arrived
+    for rws in (rows, rows - 3):
+        ms = ctx.new_map(rws, cols)
+        ms.upload_occupancy(np.ascontiguousarray(w["occ"][:rws]))
+        want = pb["orc"].edt(np.ascontiguousarray(w["occ"][:rws]))
+        ms.upload_field(np.full((rws, cols), -1.0, np.float32))
+        ms.edt_sharded(mod.EDT_GATHER_NCCL)
+        check(np.array_equal(ms.download_field().view(np.uint32), want.view(np.uint32)),
+              f"row-sharded EDT + NCCL gather differs ({rws} rows)")
+        try:
+            ms.share()
+            shared = True
+        except mod.B200SlamError as e:
+            shared = False
+            if rank == 0:
+                print(f"[mr_worker] peer-shared maps unavailable here ({e}); fused EDT gather not exercised", flush=True)
+        if shared:
+            for _ in range(2):                                   # twice: the barriers' epochs advance
+                ms.upload_field(np.full((rws, cols), -1.0, np.float32))
+                ms.edt_sharded(mod.EDT_GATHER_P2P)
+                check(np.array_equal(ms.download_field().view(np.uint32), want.view(np.uint32)),
+                      f"row-sharded EDT with in-kernel peer stores differs ({rws} rows)")
+        dist.barrier()                                           # nobody unmaps while a peer may still write
+        ms.close()
     # ---- lattice, rows sharded, winner all-gathered over NCCL ----------------------------------
     nrows = n[0] * n[1]
     rb, re = mod.shard_range(nrows, world, rank)

@@ -134,3 +134,28 @@ def test_bad_arguments_are_reported_not_fatal(ctx, b200slam, synth):
         assert np.array_equal(ctx.edt(occ), np.full((8, 8), 10.0, np.float32))
     finally:
         m.close()
+
+
+def test_edt_row_ranges_compose_and_touch_nothing_else(ctx, oracle, synth):
+    """b200slam_map_edt_rows (one rank's block of the row-sharded transform): ranges that
+    are not multiples of the 9-row batch, a one-row and an empty range; rows outside a range keep the
+    sentinel; the union equals the oracle bit for bit (the halo comes from the full occupancy)."""
+    rows, cols = 1000, 700
+    occ = synth.grid_bernoulli(rows, cols, 0.01, synth.SEED_GRID + 77)
+    want = oracle.edt(occ)
+    m = ctx.new_map(rows, cols)
+    try:
+        m.upload_occupancy(occ)
+        m.upload_field(np.full((rows, cols), -1.0, np.float32))
+        m.edt_rows(0, 0)
+        m.edt_rows(331, 332)
+        got = m.download_field()
+        assert np.array_equal(bits(got[331]), bits(want[331]))
+        assert (np.delete(got, 331, axis=0) == -1.0).all()
+        for rb, re in [(0, 331), (332, 640), (640, 993), (993, 1000)]:
+            m.edt_rows(rb, re)
+        assert np.array_equal(bits(m.download_field()), bits(want))
+        with pytest.raises(Exception):
+            m.edt_rows(10, rows + 1)
+    finally:
+        m.close()
