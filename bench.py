@@ -6,22 +6,30 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input: the clamped EDT of
 the occupancy grid followed by the correlative scan match of every lattice candidate against
-the fresh distance field, ending in the arg-min (BASELINE.json configs[1]: 2048x2048 grid,
-64 x 32 x 32 = 65 536 candidate poses x 360 beams).
+the fresh distance field, ending in the arg-min.  Default workload: BASELINE.json configs[1]
+(2048x2048 grid, 64 x 32 x 32 = 65 536 candidate poses x 360 beams, the single-GPU
+configuration); the same line carries under "largest_sweep" the same measurements on
+configs[3] (8192x8192 grid, 256 x 128 x 128 = 4 194 304 poses x 1080 beams per GPU), the sweep
+north_star states its roofline and scaling targets on.  --workload config2 / config4 are the
+particle-filter step (configs[2]) and the 3-level pyramid search (configs[4]).
 
 Own arm, per rank (one process per GPU; torch.distributed only for barrier / max-over-ranks):
   * `value`  : whole-job pose x beam evals / s with inputs resident in HBM: K steps replayed
                back to back as CUDA graphs (the step is a handful of microsecond kernels),
                bracketed by barrier + sync, timed with CUDA events on the library's stream,
                max over ranks.  Steps cycle through a ring of distinct maps larger than L2.
-  * per-kernel durations (eager pass, CUDA events around every kernel) -> `roofline`
+               Many independent steps are in flight, so the matcher runs with the library's
+               throughput tile-shape policy (b200slam_set_match_mode); `serial_ms_per_step` is
+               the same K steps strictly one kernel after the other with the default policy.
+  * per-kernel durations (eager pass, CUDA events around every kernel) -> `roofline`,
+               `rooflines` (incl. the matcher under the default, one-match-at-a-time policy)
   * `e2e`    : the same step through the host-buffer C ABI calls: H2D of the int32 grid and
                the scan from pinned memory and D2H of the match result inside the timed region
   * `cpu_baseline` (rank 0, N == 1): the reference's own EDT2 + FastMatch2 (oracle/_ref) or the
                oracle port, 1 core, on a bounded sample of the same workload
 N > 1: weak scaling -- every rank keeps the per-GPU workload (map replicated, its own block
 of theta rows of an N-times larger lattice) and the per-rank bests are all-gathered with
-NCCL inside the step.
+NCCL inside the step (through NVLink peer memory in the kernel's tail where CUDA IPC works).
 """
 from __future__ import annotations
 
@@ -255,7 +263,10 @@ def workload_config(w, args, world) -> dict:
 
 # ----------------------------------------------------------------------------------------
 def run_b200_arm(args, synth):
-    mod = importlib.import_module(PKG)
+    """The default arm.  Prints the bench line for args.workload; when that is config1 (BASELINE
+    configs[1], the single-GPU configuration) the line also carries, under "largest_sweep", the same
+    measurements on config3 (configs[3]: 8192^2 grid, 4 M poses x 1080 beams per GPU -- the sweep
+    north_star's roofline and scaling targets are stated on), taken in the same run."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -265,7 +276,30 @@ def run_b200_arm(args, synth):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    K, W = args.steps, max(args.warmup, 3)
+    line = measure_workload(args, synth, args.workload, dist, args.steps, want_cpu=not args.no_cpu)
+    if args.workload == "config1" and not args.no_extra:
+        big = measure_workload(args, synth, "config3", dist, max(4, min(args.steps, 20)), want_cpu=False)
+        if rank == 0:
+            keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "serial_ms_per_step", "config",
+                    "edt_mcells_per_s", "match_evals_per_s_per_gpu", "roofline", "rooflines", "e2e", "gpu_launches",
+                    "result")
+            line["largest_sweep"] = {k: big[k] for k in keep if k in big}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_workload(args, synth, workload, dist, K, want_cpu):
+    """One workload, measured as the module docstring describes -> the JSON line (rank 0; None elsewhere)."""
+    mod = importlib.import_module(PKG)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args = argparse.Namespace(**dict(vars(args), workload=workload))
+    W = max(args.warmup, 3)
+    line = None
 
     w = synth.make_workload(args.workload)
     rows, cols = w["occ"].shape
@@ -511,9 +545,8 @@ def run_b200_arm(args, synth):
             "result": {"best_index": int(last.best_index), "best_score": float(last.best_score),
                        "best_hits": int(last.best_hits), "e2e_best_index": int(res.best_index)},
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and want_cpu:
             line["cpu_baseline"] = cpu_sample(w, synth, budget_s=args.cpu_seconds)
-        print(json.dumps(line), flush=True)
 
     for g in graphs + [g for g in {id(turn): turn, id(turn_serial): turn_serial}.values() if g is not None]:
         ctx.graph_destroy(g)
@@ -521,10 +554,10 @@ def run_b200_arm(args, synth):
         ctx_e.close()
     for m in maps:
         m.close()
-    ctx.close()
     if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        dist.barrier()                    # nobody tears its peer-mapped buffers down while a peer still spins on them
+    ctx.close()
+    return line
 
 
 def run_particles_arm(args, synth):
@@ -780,6 +813,7 @@ def main():
     ap.add_argument("--latency-mode", action="store_true",
                     help="keep the library's default tile-shape policy (one match at a time) in the timed region too")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="config1 only: skip the extra config3 measurement")
     ap.add_argument("--no-allreduce", action="store_true",
                     help="diagnostic: N > 1 without the per-step exchange of bests (ranks run independently)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
