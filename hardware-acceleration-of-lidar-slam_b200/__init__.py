@@ -103,6 +103,17 @@ def load_library() -> C.CDLL:
         "b200slam_score_poses": (i, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.POINTER(Match)]),
         "b200slam_fastmatch": (i, [vp, vp, c_float_p, c_float_p, c_float_p, vp, c_int_p]),
         "b200slam_set_match_mode": (i, [vp, i]),
+        "b200slam_lidar_set": (i, [vp, c_float_p, c_float_p, i, f]),
+        "b200slam_scan_read": (i, [vp, c_float_p, i, c_int_p]),
+        "b200slam_scan_transform": (i, [vp, c_float_p]),
+        "b200slam_scan_download": (i, [vp, c_float_p, c_float_p, c_float_p, c_float_p, c_int_p]),
+        "b200slam_mappoints_upload": (i, [vp, c_float_p, c_float_p, i, i]),
+        "b200slam_mappoints_from_scan": (i, [vp]),
+        "b200slam_mappoints_grow": (i, [vp, f, c_int_p]),
+        "b200slam_mappoints_download": (i, [vp, c_float_p, c_float_p, c_int_p]),
+        "b200slam_local_map_extract": (i, [vp, f, c_int_p]),
+        "b200slam_local_map_download": (i, [vp, c_float_p, c_float_p, c_int_p]),
+        "b200slam_map_rasterise_local": (i, [vp, vp, f, c_int_p, c_int_p, c_float_p]),
         "b200slam_map_edt_rows": (i, [vp, vp, f, i, i]),
         "b200slam_map_share": (i, [vp, vp]),
         "b200slam_map_edt_sharded": (i, [vp, vp, f, i]),
@@ -182,6 +193,26 @@ def lattice_value(p: float, s: float, k: int, n: int) -> float:
     return float(load_library().b200slam_lattice_value(C.c_float(p), C.c_float(s), k, n))
 
 
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(c_float_p)
+
+
+_LIBM = None
+
+
+def libm_cosf_sinf(a: np.ndarray):
+    """glibc cosf / sinf element by element (what the reference calls: main.c:90-91, 101-102)."""
+    global _LIBM
+    if _LIBM is None:
+        _LIBM = C.CDLL("libm.so.6")
+        for nm in ("cosf", "sinf"):
+            getattr(_LIBM, nm).restype = C.c_float
+            getattr(_LIBM, nm).argtypes = [C.c_float]
+    ca = np.array([_LIBM.cosf(float(v)) for v in a], np.float32)
+    sa = np.array([_LIBM.sinf(float(v)) for v in a], np.float32)
+    return ca, sa
+
+
 def _f3(v):
     return (C.c_float * 3)(*[float(x) for x in v])
 
@@ -224,6 +255,14 @@ class Map:
         tl = (C.c_float * 2)()
         self.ctx._check(self.ctx.L.b200slam_map_rasterise(self.ctx.h, self.h, x.ctypes.data, y.ctypes.data, len(x),
                                                           pixel_size, C.byref(r), C.byref(c), tl))
+        self.rows, self.cols = r.value, c.value
+        return r.value, c.value, (np.float32(tl[0]), np.float32(tl[1]))
+
+    def rasterise_local(self, pixel_size: float):
+        """The same from the device-resident local map (Context.local_map_extract)."""
+        r, c = C.c_int32(0), C.c_int32(0)
+        tl = (C.c_float * 2)()
+        self.ctx._check(self.ctx.L.b200slam_map_rasterise_local(self.ctx.h, self.h, pixel_size, C.byref(r), C.byref(c), tl))
         self.rows, self.cols = r.value, c.value
         return r.value, c.value, (np.float32(tl[0]), np.float32(tl[1]))
 
@@ -309,6 +348,67 @@ class Context:
     def set_match_mode(self, mode: int):
         """MATCH_LATENCY (default) or MATCH_THROUGHPUT: tile-shape policy of the lattice kernel."""
         self._check(self.L.b200slam_set_match_mode(self.h, int(mode)))
+
+    # -- scan front end / map points (device resident) ------------------------------------
+    def lidar_set(self, angles, range_min: float):
+        """angles: the beam angles as the reference accumulates them (main.c:53-57); cos / sin by numpy's
+        float32 libm calls would differ from glibc's cosf / sinf, so they are taken from libm via ctypes."""
+        a = np.ascontiguousarray(angles, np.float32)
+        ca, sa = libm_cosf_sinf(a)
+        self._lidar_n = len(a)
+        self._check(self.L.b200slam_lidar_set(self.h, _fptr(ca), _fptr(sa), len(a), range_min))
+
+    def scan_read(self, ranges, max_range: int = 24) -> int:
+        r = np.ascontiguousarray(ranges, np.float32)
+        assert len(r) == self._lidar_n
+        n = C.c_int(0)
+        self._check(self.L.b200slam_scan_read(self.h, _fptr(r), int(max_range), C.byref(n)))
+        self._nbeams = n.value
+        return n.value
+
+    def scan_transform(self, pose):
+        self._check(self.L.b200slam_scan_transform(self.h, _f3(pose)))
+
+    def scan_download(self, transformed: bool = True):
+        cap = 4096 if not hasattr(self, "_lidar_n") else max(4096, self._lidar_n)
+        x, y = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        tx, ty = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        n = C.c_int(0)
+        self._check(self.L.b200slam_scan_download(self.h, _fptr(x), _fptr(y), _fptr(tx) if transformed else None,
+                                                  _fptr(ty) if transformed else None, C.byref(n)))
+        k = n.value
+        return (x[:k].copy(), y[:k].copy(), tx[:k].copy(), ty[:k].copy()) if transformed else (x[:k].copy(), y[:k].copy())
+
+    def mappoints_upload(self, x, y, offset: int = 0):
+        x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+        self._check(self.L.b200slam_mappoints_upload(self.h, _fptr(x), _fptr(y), len(x), offset))
+
+    def mappoints_from_scan(self):
+        self._check(self.L.b200slam_mappoints_from_scan(self.h))
+
+    def mappoints_grow(self, threshold: float = 1.5) -> int:
+        n = C.c_int(0)
+        self._check(self.L.b200slam_mappoints_grow(self.h, threshold, C.byref(n)))
+        return n.value
+
+    def mappoints_download(self):
+        n = C.c_int(0)
+        self._check(self.L.b200slam_mappoints_download(self.h, None, None, C.byref(n)))
+        x, y = np.empty(max(n.value, 1), np.float32), np.empty(max(n.value, 1), np.float32)
+        self._check(self.L.b200slam_mappoints_download(self.h, _fptr(x), _fptr(y), C.byref(n)))
+        return x[:n.value].copy(), y[:n.value].copy()
+
+    def local_map_extract(self, border: float = 1.0) -> int:
+        n = C.c_int(0)
+        self._check(self.L.b200slam_local_map_extract(self.h, border, C.byref(n)))
+        return n.value
+
+    def local_map_download(self):
+        n = C.c_int(0)
+        self._check(self.L.b200slam_local_map_download(self.h, None, None, C.byref(n)))
+        x, y = np.empty(max(n.value, 1), np.float32), np.empty(max(n.value, 1), np.float32)
+        self._check(self.L.b200slam_local_map_download(self.h, _fptr(x), _fptr(y), C.byref(n)))
+        return x[:n.value].copy(), y[:n.value].copy()
 
     def launch_count(self) -> int:
         return int(self.L.b200slam_launch_count(self.h))

@@ -92,6 +92,7 @@ void b200slam_destroy(b200slam_ctx *ctx)
     cudaFree(ctx->d_ancestors); cudaFree(ctx->d_wsum); cudaFreeHost(ctx->h_wsum);
     cudaFree(ctx->d_edt_scratch);
     cudaFree(ctx->d_points); cudaFreeHost(ctx->h_points);
+    frontend_free(ctx);
     for (int i = 0; i < LAT_SLOTS; ++i)
         if (ctx->lat_event[i]) cudaEventDestroy(ctx->lat_event[i]);
     for (int i = 0; i < 4096; ++i)
@@ -218,18 +219,31 @@ int b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const in
     return B200SLAM_OK;
 }
 
-int b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x, const float *y, int npoints,
-                           float pixel_size, int *rows_out, int *cols_out, float top_left_out[2])
+}  // extern "C" (internal helpers below have C++ linkage)
+
+int ensure_points_capacity(b200slam_ctx *ctx, size_t npoints)
 {
-    if (!ctx || !map || !x || !y || npoints <= 0 || !(pixel_size > 0.0f)) return B200SLAM_ERR_ARG;
-    // main.c:272-289: bounding box, strict compares, seeded with point 0
-    float minXY[2] = {x[0], y[0]}, maxXY[2] = {x[0], y[0]};
-    for (int a = 0; a < npoints; ++a) {
-        if (x[a] < minXY[0]) minXY[0] = x[a];
-        if (x[a] > maxXY[0]) maxXY[0] = x[a];
-        if (y[a] < minXY[1]) minXY[1] = y[a];
-        if (y[a] > maxXY[1]) maxXY[1] = y[a];
+    if (npoints <= ctx->points_cap) return B200SLAM_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t cap = (npoints + 4095) & ~(size_t)4095;
+    float *d = nullptr, *h = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(float) * 2 * cap));
+    CUDA_TRY(ctx, cudaHostAlloc(&h, sizeof(float) * 2 * cap, cudaHostAllocDefault));
+    if (ctx->d_points && ctx->local_n > 0) {       // keep a resident local map across the growth
+        CUDA_TRY(ctx, cudaMemcpy(d, ctx->d_points, sizeof(float) * ctx->local_n, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(ctx, cudaMemcpy(d + cap, ctx->d_points + ctx->points_cap, sizeof(float) * ctx->local_n,
+                                 cudaMemcpyDeviceToDevice));
     }
+    cudaFree(ctx->d_points); cudaFreeHost(ctx->h_points);
+    ctx->d_points = d; ctx->h_points = h;
+    ctx->points_cap = cap;
+    return B200SLAM_OK;
+}
+
+int rasterise_from_bbox(b200slam_ctx *ctx, b200slam_map *map, int npoints, const float bbox[4], float pixel_size,
+                        int *rows_out, int *cols_out, float top_left_out[2])
+{
+    float minXY[2] = {bbox[0], bbox[1]}, maxXY[2] = {bbox[2], bbox[3]};
     // main.c:296-305: 3-pixel margin; size = (int)roundf(extent / pixel) + 1, every step rounded to float
     int S[2];
     for (int a = 0; a < 2; ++a) {
@@ -247,23 +261,6 @@ int b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x,
     if (rows > map->cap_rows || cols > map->cap_cols || rows <= 0 || cols <= 0)
         return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "rasterised grid %d x %d exceeds the map capacity %d x %d",
                                   rows, cols, map->cap_rows, map->cap_cols);
-    if ((size_t)npoints > ctx->points_cap) {
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_points); cudaFreeHost(ctx->h_points);
-        ctx->d_points = ctx->h_points = nullptr;
-        ctx->points_cap = 0;
-        const size_t cap = ((size_t)npoints + 4095) & ~(size_t)4095;
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_points, sizeof(float) * 2 * cap));
-        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_points, sizeof(float) * 2 * cap, cudaHostAllocDefault));
-        ctx->points_cap = cap;
-    }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));          // pinned staging buffer free again
-    memcpy(ctx->h_points, x, sizeof(float) * npoints);
-    memcpy(ctx->h_points + ctx->points_cap, y, sizeof(float) * npoints);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points, ctx->h_points, sizeof(float) * npoints, cudaMemcpyHostToDevice,
-                                  ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points + ctx->points_cap, ctx->h_points + ctx->points_cap,
-                                  sizeof(float) * npoints, cudaMemcpyHostToDevice, ctx->stream));
     map->rows = rows;
     map->cols = cols;
     map->pixel_size = pixel_size;                                          // main.c:357-362
@@ -271,6 +268,34 @@ int b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x,
     map->top_left_y = minXY[1];
     map->has_geometry = true;
     return rasterise_launch(ctx, map, npoints, minXY[0], minXY[1], pixel_size);
+}
+
+extern "C" {
+
+int b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x, const float *y, int npoints,
+                           float pixel_size, int *rows_out, int *cols_out, float top_left_out[2])
+{
+    if (!ctx || !map || !x || !y || npoints <= 0 || !(pixel_size > 0.0f)) return B200SLAM_ERR_ARG;
+    // main.c:272-289: bounding box, strict compares, seeded with point 0
+    float bbox[4] = {x[0], y[0], x[0], y[0]};
+    for (int a = 0; a < npoints; ++a) {
+        if (x[a] < bbox[0]) bbox[0] = x[a];
+        if (x[a] > bbox[2]) bbox[2] = x[a];
+        if (y[a] < bbox[1]) bbox[1] = y[a];
+        if (y[a] > bbox[3]) bbox[3] = y[a];
+    }
+    int rc = ensure_points_capacity(ctx, (size_t)npoints);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));          // pinned staging buffer free again
+    memcpy(ctx->h_points, x, sizeof(float) * npoints);
+    memcpy(ctx->h_points + ctx->points_cap, y, sizeof(float) * npoints);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points, ctx->h_points, sizeof(float) * npoints, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points + ctx->points_cap, ctx->h_points + ctx->points_cap,
+                                  sizeof(float) * npoints, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->local_n = npoints;                                     // these points ARE the resident local map now
+    for (int i = 0; i < 4; ++i) ctx->local_bbox[i] = bbox[i];
+    return rasterise_from_bbox(ctx, map, npoints, bbox, pixel_size, rows_out, cols_out, top_left_out);
 }
 
 int b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist)
@@ -345,23 +370,39 @@ int b200slam_edt(b200slam_ctx *ctx, const int32_t *occ, int occ_stride, float *o
 
 /* ---- scan + lattice ------------------------------------------------------------ */
 
+}  // extern "C"
+
+int ensure_scan_capacity(b200slam_ctx *ctx, int nbeams)
+{
+    if (nbeams <= ctx->scan_cap && ctx->d_scan_x) return B200SLAM_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_scan_x); cudaFree(ctx->d_hit_values); cudaFreeHost(ctx->h_scan); cudaFreeHost(ctx->h_hit_values);
+    ctx->d_scan_x = ctx->d_scan_y = ctx->d_hit_values = ctx->h_scan = ctx->h_hit_values = nullptr;
+    ctx->scan_cap = 0;
+    // at least the reference's bestHits[2500] (main.c:376), so that buffer is never re-allocated (and its
+    // stale tail lost) for scans the reference itself could hold
+    const int cap = ((nbeams > 2500 ? nbeams : 2500) + 255) & ~255;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_scan_x, sizeof(float) * 2 * cap));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_hit_values, sizeof(float) * 2 * cap));
+    // FastMatchParameters.bestHits is a zero-initialised global that every match overwrites from
+    // the front (main.c:374-378, 515); entries past the last candidate's count keep older values
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_hit_values, 0, sizeof(float) * 2 * cap, ctx->stream));
+    CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_scan, sizeof(float) * 2 * cap, cudaHostAllocDefault));
+    CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_hit_values, sizeof(float) * cap, cudaHostAllocDefault));
+    if (!ctx->scan_event) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->scan_event, cudaEventDisableTiming));
+    ctx->d_scan_y = ctx->d_scan_x + cap;
+    ctx->scan_cap = cap;
+    return B200SLAM_OK;
+}
+
+extern "C" {
+
 int b200slam_scan_upload(b200slam_ctx *ctx, const float *x, const float *y, int nbeams)
 {
     if (!ctx || nbeams < 0 || (nbeams > 0 && (!x || !y))) return B200SLAM_ERR_ARG;
-    if (nbeams > ctx->scan_cap || !ctx->d_scan_x) {
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_scan_x); cudaFree(ctx->d_hit_values); cudaFreeHost(ctx->h_scan); cudaFreeHost(ctx->h_hit_values);
-        ctx->d_scan_x = ctx->d_scan_y = ctx->d_hit_values = ctx->h_scan = ctx->h_hit_values = nullptr;
-        ctx->scan_cap = 0;
-        const int cap = ((nbeams > 0 ? nbeams : 1) + 255) & ~255;
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_scan_x, sizeof(float) * 2 * cap));
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_hit_values, sizeof(float) * 2 * cap));
-        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_scan, sizeof(float) * 2 * cap, cudaHostAllocDefault));
-        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_hit_values, sizeof(float) * cap, cudaHostAllocDefault));
-        if (!ctx->scan_event) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->scan_event, cudaEventDisableTiming));
-        ctx->d_scan_y = ctx->d_scan_x + cap;
-        ctx->scan_cap = cap;
-    }
+    int rc = ensure_scan_capacity(ctx, nbeams);
+    if (rc) return rc;
+    ctx->scan_t_valid = false;
     if (nbeams > 0) {
         // one pinned, truly asynchronous copy of x | y (callers hand in pageable arrays)
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->scan_event));

@@ -138,6 +138,21 @@ struct b200slam_ctx {
     float *d_points = nullptr, *h_points = nullptr;   // device / pinned
     size_t points_cap = 0;
 
+    // scan front end (frontend.cu): lidar tables, raw ranges, world-frame scan, map points.
+    // The local map extracted from the map points lives in d_points (what rasterisation reads).
+    float *d_lidar = nullptr;            // cos | sin of the beam angles, each [lidar_n]
+    int lidar_n = 0;
+    float lidar_range_min = 0.0f;
+    float *d_ranges = nullptr, *h_ranges = nullptr;   // device / pinned, [lidar_n]
+    float *d_scan_t = nullptr;           // tx | ty, each [scan_t_cap]
+    int scan_t_cap = 0;
+    bool scan_t_valid = false;
+    float *d_mp = nullptr;               // map points x | y, each [mp_cap]
+    int mp_cap = 0, mp_size = 0;
+    int local_n = -1;                    // points of the resident local map (-1: none)
+    float local_bbox[4] = {0, 0, 0, 0};  // min x, min y, max x, max y of the local map
+    struct FrontOut { int count; int pad; float bbox[4]; } *d_front = nullptr, *h_front = nullptr;
+
     // generic EDT scratch (u16 column distances)
     uint16_t *d_edt_scratch = nullptr;
     size_t edt_scratch_cap = 0;
@@ -212,6 +227,12 @@ int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_
 
 int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float min_x, float min_y,
                      float pixel_size);
+// One level of OccupationalGrid from points already in ctx->d_points whose bounding box is known.
+int rasterise_from_bbox(b200slam_ctx *ctx, b200slam_map *map, int npoints, const float bbox[4], float pixel_size,
+                        int *rows_out, int *cols_out, float top_left_out[2]);
+int ensure_points_capacity(b200slam_ctx *ctx, size_t npoints);
+int ensure_scan_capacity(b200slam_ctx *ctx, int nbeams);
+void frontend_free(b200slam_ctx *ctx);
 
 int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send,
                        unsigned long long *d_recv, int count_per_rank);

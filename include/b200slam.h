@@ -185,6 +185,45 @@ int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3]
                        const float search_resolution[3], float pose_out[3], float *best_hits,
                        int *best_hits_size);
 
+/* ---- scan front end and map points on the device (the steps either side of the hot path) ----
+ * With these the per-scan loop of the reference's main() (Subsystem_1/main.c:859-970) keeps the
+ * scan, the map points, the local map, both grids and both distance fields on the device: 4
+ * bytes per beam go up per scan and a pose comes back.  All arithmetic is the reference's
+ * (products and sums rounded separately, strict compares, compaction in input order); cos / sin
+ * of the beam angles and of the pose come from the HOST libm, like the lattice tables.
+ *
+ *   b200slam_lidar_set          SetLidarParameters, main.c:45-58: cos_a[i] = cosf(angles[i]),
+ *                               sin_a[i] = sinf(angles[i]) computed by the caller; range_min
+ *   b200slam_scan_read          readAScan, main.c:71-95: drop r < range_min | r > max_range,
+ *                               x = r * cos, y = r * sin, compacted in beam order into the context's
+ *                               scan (what b200slam_scan_upload would have received); *size = scan.size
+ *   b200slam_scan_transform     Transform, main.c:97-118: world-frame tx / ty for POSE
+ *   b200slam_scan_download      any of x, y, tx, ty (each optional) and the size
+ *   b200slam_mappoints_upload   MapPoints map (main.c:121-131): points [offset, offset + n), offset <=
+ *                               current size; the size becomes offset + n
+ *   b200slam_mappoints_from_scan  Initialise, main.c:136-145: map <- world-frame scan
+ *   b200slam_mappoints_grow     main.c:942-948: for j < bestHits_size (of the winner of the LAST
+ *                               match): bestHits[j] (hits of the last candidate scored) > threshold ->
+ *                               append scan.tx[j], scan.ty[j]; *added = newPointSize
+ *   b200slam_mappoints_download
+ *   b200slam_local_map_extract  ExtractLocalMap, main.c:155-198: bounding box of the world-frame scan
+ *                               +- border, map points strictly inside, order kept; *size = local_map.size
+ *   b200slam_local_map_download
+ *   b200slam_map_rasterise_local  one level of OccupationalGrid (main.c:271-354) from the resident local
+ *                               map: b200slam_map_rasterise without the points crossing PCIe */
+int b200slam_lidar_set(b200slam_ctx *ctx, const float *cos_a, const float *sin_a, int nbeams, float range_min);
+int b200slam_scan_read(b200slam_ctx *ctx, const float *ranges, int max_range, int *size);
+int b200slam_scan_transform(b200slam_ctx *ctx, const float pose[3]);
+int b200slam_scan_download(b200slam_ctx *ctx, float *x, float *y, float *tx, float *ty, int *size);
+int b200slam_mappoints_upload(b200slam_ctx *ctx, const float *x, const float *y, int n, int offset);
+int b200slam_mappoints_from_scan(b200slam_ctx *ctx);
+int b200slam_mappoints_grow(b200slam_ctx *ctx, float threshold, int *added);
+int b200slam_mappoints_download(b200slam_ctx *ctx, float *x, float *y, int *size);
+int b200slam_local_map_extract(b200slam_ctx *ctx, float border, int *size);
+int b200slam_local_map_download(b200slam_ctx *ctx, float *x, float *y, int *size);
+int b200slam_map_rasterise_local(b200slam_ctx *ctx, b200slam_map *map, float pixel_size, int *rows, int *cols,
+                                 float top_left[2]);
+
 /* ---- scheduling hint for the scan matcher ---------------------------------------------
  * The lattice kernel comes in several tile shapes (candidates per thread x warps per CTA).
  * B200SLAM_MATCH_LATENCY (default): one match at a time, as FastMatch is called per scan

@@ -73,6 +73,17 @@ class Oracle:
         L.orc_fastmatch.restype = None
         L.orc_fastmatch.argtypes = [C.POINTER(OrcMap), c_float_p, c_float_p, C.c_int, c_float_p,
                                     c_float_p, c_float_p, c_float_p, c_int_p]
+        L.orc_lidar_angles.restype = None
+        L.orc_lidar_angles.argtypes = [C.c_float, C.c_float, C.c_int, c_float_p]
+        L.orc_read_scan.restype = C.c_int
+        L.orc_read_scan.argtypes = [c_float_p, c_float_p, C.c_int, C.c_float, C.c_int, c_float_p, c_float_p]
+        L.orc_transform.restype = None
+        L.orc_transform.argtypes = [c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, c_float_p]
+        L.orc_extract_local_map.restype = C.c_int
+        L.orc_extract_local_map.argtypes = [c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, C.c_float,
+                                            c_float_p, c_float_p]
+        L.orc_grow_map.restype = C.c_int
+        L.orc_grow_map.argtypes = [c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int]
         L.orc_exp_det.restype = C.c_float
         L.orc_exp_det.argtypes = [C.c_float]
         L.orc_weights_resample.restype = None
@@ -117,6 +128,41 @@ class Oracle:
         m._keep = field
         return m
 
+    # -- scan front end / map points ---------------------------------------------------
+    def lidar_angles(self, angle_min=-2.351831, inc=0.004363, n=1079):
+        a = np.empty(n, np.float32)
+        self.lib.orc_lidar_angles(angle_min, inc, n, _fp(a))
+        return a
+
+    def read_scan(self, ranges, angles, range_min=0.023, max_range=24):
+        r = np.ascontiguousarray(ranges, np.float32); a = np.ascontiguousarray(angles, np.float32)
+        x, y = np.empty(len(r), np.float32), np.empty(len(r), np.float32)
+        n = self.lib.orc_read_scan(_fp(r), _fp(a), len(r), range_min, int(max_range), _fp(x), _fp(y))
+        return x[:n].copy(), y[:n].copy()
+
+    def transform(self, x, y, pose):
+        x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+        p = np.asarray(pose, np.float32)
+        tx, ty = np.empty_like(x), np.empty_like(y)
+        self.lib.orc_transform(_fp(x), _fp(y), len(x), _fp(p), _fp(tx), _fp(ty))
+        return tx, ty
+
+    def extract_local_map(self, tx, ty, map_x, map_y, border=1.0):
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        mx = np.ascontiguousarray(map_x, np.float32); my = np.ascontiguousarray(map_y, np.float32)
+        lx, ly = np.empty(max(len(mx), 1), np.float32), np.empty(max(len(mx), 1), np.float32)
+        n = self.lib.orc_extract_local_map(_fp(tx), _fp(ty), len(tx), _fp(mx), _fp(my), len(mx), border, _fp(lx), _fp(ly))
+        return lx[:n].copy(), ly[:n].copy()
+
+    def grow_map(self, best_hits, best_hits_size, tx, ty, map_x, map_y):
+        bh = np.ascontiguousarray(best_hits, np.float32)
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        n0 = len(map_x)
+        mx = np.empty(n0 + best_hits_size, np.float32); my = np.empty(n0 + best_hits_size, np.float32)
+        mx[:n0] = map_x; my[:n0] = map_y
+        k = self.lib.orc_grow_map(_fp(bh), int(best_hits_size), _fp(tx), _fp(ty), _fp(mx), _fp(my), n0)
+        return mx[:n0 + k].copy(), my[:n0 + k].copy()
+
     def score_lattice(self, omap, scan_x, scan_y, pose0, step, n, want_scores=True, want_last_hits=False):
         sx = np.ascontiguousarray(scan_x, np.float32)
         sy = np.ascontiguousarray(scan_y, np.float32)
@@ -146,13 +192,15 @@ class Oracle:
                                  _fp(scores), _ip(hits), C.byref(res))
         return res, scores, hits
 
-    def fastmatch(self, omap, scan_x, scan_y, pose, res3):
+    def fastmatch(self, omap, scan_x, scan_y, pose, res3, hits_buf=None):
+        """hits_buf: a persistent float32 array standing in for the global FastMatchParameters.bestHits
+        (main.c:376): only its first last_hits entries are overwritten, the rest keeps older values."""
         sx = np.ascontiguousarray(scan_x, np.float32)
         sy = np.ascontiguousarray(scan_y, np.float32)
         p = np.asarray(pose, np.float32)
         r = np.asarray(res3, np.float32)
         out = np.zeros(3, np.float32)
-        hits = np.zeros(max(len(sx), 1), np.float32)
+        hits = np.zeros(max(len(sx), 1), np.float32) if hits_buf is None else hits_buf
         n = C.c_int32(0)
         self.lib.orc_fastmatch(C.byref(omap), _fp(sx), _fp(sy), len(sx), _fp(p), _fp(r), _fp(out), _fp(hits),
                                C.byref(n))
@@ -211,6 +259,17 @@ class RefFastMatchParameters(C.Structure):  # main.c:374-378
 
 class RefLocalMap(C.Structure):  # main.c:147-151
     _fields_ = [("x", C.c_float * 25000), ("y", C.c_float * 25000), ("size", C.c_int)]
+
+
+class RefLidar(C.Structure):  # main.c:35-42
+    _fields_ = [("angle_min", C.c_float), ("angle_max", C.c_float), ("angle_increment", C.c_float),
+                ("range_min", C.c_float), ("range_max", C.c_float), ("angles", C.c_float * COLUMN)]
+
+
+class RefMapPoints(C.Structure):  # main.c:121-131
+    _fields_ = [("x", C.c_float * 20000), ("y", C.c_float * 20000), ("size", C.c_int),
+                ("newPoints_x", C.c_float * 4000), ("newPoints_y", C.c_float * 4000), ("newPointsSize", C.c_int),
+                ("pose", C.c_float * 3)]
 
 
 def reference_available() -> bool:
@@ -296,6 +355,52 @@ class Reference:
             tl = g.top_left_corner2 if fine else g.top_left_corner
             out.append((grid, field, (np.float32(tl[0]), np.float32(tl[1]))))
         return out
+
+    # -- the reference's own front-end functions on its own globals -----------------------
+    def lidar_angles(self):
+        """SetLidarParameters() (main.c:45-58) -> its angle table and range_min."""
+        self.lib.SetLidarParameters.restype = None
+        self.lib.SetLidarParameters()
+        lid = RefLidar.in_dll(self.lib, "lidar")
+        return np.ctypeslib.as_array(lid.angles).copy(), float(lid.range_min)
+
+    def read_a_scan(self, ranges, usable_range=24):
+        """test_input_memory <- ranges; readAScan(usable_range) (main.c:71-95) -> scan.x, scan.y."""
+        r = np.ascontiguousarray(ranges, np.float32)
+        assert len(r) == COLUMN
+        tim = (C.c_float * COLUMN).in_dll(self.lib, "test_input_memory")
+        C.memmove(tim, r.ctypes.data, r.nbytes)
+        self.lib.readAScan.restype = None
+        self.lib.readAScan.argtypes = [C.c_int]
+        self.lib.readAScan(int(usable_range))
+        n = int(self.scan.size)
+        return np.ctypeslib.as_array(self.scan.x)[:n].copy(), np.ctypeslib.as_array(self.scan.y)[:n].copy()
+
+    def transform(self, pose):
+        """Transform(pose) (main.c:97-118) on the current scan -> scan.tx, scan.ty."""
+        p = np.asarray(pose, np.float32)
+        self.lib.Transform.restype = None
+        self.lib.Transform.argtypes = [c_float_p]
+        self.lib.Transform(_fp(p))
+        n = int(self.scan.size)
+        return np.ctypeslib.as_array(self.scan.tx)[:n].copy(), np.ctypeslib.as_array(self.scan.ty)[:n].copy()
+
+    def extract_local_map(self, map_x, map_y, border=1.0):
+        """map <- (map_x, map_y); ExtractLocalMap(border) (main.c:155-198) -> local_map."""
+        mp = RefMapPoints.in_dll(self.lib, "map")
+        n = len(map_x)
+        assert n <= 20000
+        xs = np.zeros(20000, np.float32); xs[:n] = map_x
+        ys = np.zeros(20000, np.float32); ys[:n] = map_y
+        C.memmove(mp.x, xs.ctypes.data, xs.nbytes)
+        C.memmove(mp.y, ys.ctypes.data, ys.nbytes)
+        mp.size = n
+        self.lib.ExtractLocalMap.restype = None
+        self.lib.ExtractLocalMap.argtypes = [C.c_float]
+        self.lib.ExtractLocalMap(C.c_float(border))
+        lm = RefLocalMap.in_dll(self.lib, "local_map")
+        k = int(lm.size)
+        return np.ctypeslib.as_array(lm.x)[:k].copy(), np.ctypeslib.as_array(lm.y)[:k].copy()
 
     def set_scan(self, x, y):
         n = len(x)

@@ -447,3 +447,97 @@ int orc_occupational_grid(const float *x, const float *y, int n, float pixel_siz
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Scan front end and map points                                              */
+/* ------------------------------------------------------------------------- */
+
+void orc_lidar_angles(float angle_min, float angle_increment, int n, float *angles)
+{
+    /* main.c:53-57 */
+    float angle = angle_min;
+    for (int i = 0; i < n; i++) {
+        angles[i] = angle;
+        angle += angle_increment;
+    }
+}
+
+int orc_read_scan(const float *ranges, const float *angles, int n, float range_min, int max_range,
+                  float *x, float *y)
+{
+    /* main.c:73-94; maxRange is an int there, converted for the compare */
+    int maxRange = max_range;
+    int valid_points = 0;
+    for (int i = 0; i < n; i++) {
+        if ((ranges[i] < range_min) | (ranges[i] > maxRange)) {
+            continue;
+        } else {
+            float test_input = ranges[i];
+            float lidar_angle = angles[i];
+            x[valid_points] = test_input * cosf(lidar_angle);
+            y[valid_points] = test_input * sinf(lidar_angle);
+            valid_points++;
+        }
+    }
+    return valid_points;
+}
+
+void orc_transform(const float *x, const float *y, int n, const float pose[3], float *tx, float *ty)
+{
+    /* main.c:98-117 */
+    float px = pose[0];
+    float py = pose[1];
+    float theta = pose[2];
+    float ct = cosf(theta);
+    float st = sinf(theta);
+    for (int i = 0; i < n; i++) {
+        float scan_x = x[i];
+        float scan_y = y[i];
+        tx[i] = (ct * scan_x + st * scan_y) + px;
+        ty[i] = (-st * scan_x + ct * scan_y) + py;
+    }
+}
+
+int orc_extract_local_map(const float *tx, const float *ty, int n, const float *map_x, const float *map_y,
+                          int map_size, float border, float *local_x, float *local_y)
+{
+    /* main.c:156-176: bounding box, strict compares seeded with point 0 */
+    float minX = tx[0], minY = ty[0], maxX = tx[0], maxY = ty[0];
+    for (int i = 1; i < n; i++) {
+        if (tx[i] < minX) minX = tx[i];
+        if (tx[i] > maxX) maxX = tx[i];
+        if (ty[i] < minY) minY = ty[i];
+        if (ty[i] > maxY) maxY = ty[i];
+    }
+    /* main.c:179-182 */
+    minX = minX - border;
+    minY = minY - border;
+    maxX = maxX + border;
+    maxY = maxY + border;
+    /* main.c:185-197 */
+    int valid_points = 0;
+    for (int i = 0; i < map_size; i++) {
+        float mx = map_x[i], my = map_y[i];
+        if ((mx > minX) && (mx < maxX) && (my > minY) && (my < maxY)) {
+            local_x[valid_points] = mx;
+            local_y[valid_points] = my;
+            valid_points++;
+        }
+    }
+    return valid_points;
+}
+
+int orc_grow_map(const float *best_hits, int best_hits_size, const float *tx, const float *ty,
+                 float *map_x, float *map_y, int map_size)
+{
+    /* main.c:941-948 */
+    int newPointSize = 0;
+    for (int j = 0; j < best_hits_size; j++) {
+        if (best_hits[j] > 1.5) {
+            map_x[map_size + newPointSize] = tx[j];
+            map_y[map_size + newPointSize] = ty[j];
+            newPointSize++;
+        }
+    }
+    return newPointSize;
+}

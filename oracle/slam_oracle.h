@@ -18,6 +18,9 @@
  *     those same objects (tests/golden/make_golden.py).
  *   - orc_occupational_grid is PINNED the same way (reference OccupationalGrid run on its own
  *     globals, both pixel sizes).
+ *   - orc_read_scan, orc_transform, orc_extract_local_map are PINNED against the reference's
+ *     readAScan / Transform / ExtractLocalMap run on its own globals (tests/test_frontend.py);
+ *     orc_grow_map restates code that is inline in main() and is pinned end to end by the replay.
  *   - orc_score_poses restates the same per-beam arithmetic for an arbitrary pose
  *     list; it is pinned through the lattice (a lattice expanded to a pose list
  *     must give identical scores).
@@ -46,6 +49,25 @@ extern "C" {
 int orc_occupational_grid(const float *x, const float *y, int n, float pixel_size, int32_t *grid,
                           int stride, int cap_rows, int cap_cols, int *rows, int *cols,
                           float *min_x, float *min_y);
+
+/* ---- scan front end and map points ------ */
+
+/* SetLidarParameters, Subsystem_1/main.c:45-58: angles by repeated float addition. */
+void orc_lidar_angles(float angle_min, float angle_increment, int n, float *angles);
+/* readAScan, main.c:71-95: drops r < range_min | r > max_range (int), x = r * cosf(a),
+ * y = r * sinf(a), compacted in beam order.  Returns scan.size. */
+int orc_read_scan(const float *ranges, const float *angles, int n, float range_min, int max_range,
+                  float *x, float *y);
+/* Transform, main.c:97-118. */
+void orc_transform(const float *x, const float *y, int n, const float pose[3], float *tx, float *ty);
+/* ExtractLocalMap, main.c:155-198.  Returns local_map.size. */
+int orc_extract_local_map(const float *tx, const float *ty, int n, const float *map_x, const float *map_y,
+                          int map_size, float border, float *local_x, float *local_y);
+/* Map growth inside main(), main.c:942-948: for j < best_hits_size: best_hits[j] > 1.5 appends
+ * (tx[j], ty[j]) at map_size + k.  Returns newPointSize.  PINNED only end to end (the code is inline
+ * in main(): tests/test_replay.py compares a whole replay's pose trace and map dump). */
+int orc_grow_map(const float *best_hits, int best_hits_size, const float *tx, const float *ty,
+                 float *map_x, float *map_y, int map_size);
 
 /* ---- distance transform ------------------------------------------------- */
 
