@@ -499,9 +499,11 @@ class Context:
                                                 C.byref(res)))
         return res, scores, hits
 
-    def fastmatch(self, m: Map, pose, res3):
+    def fastmatch(self, m: Map, pose, res3, hits_buf=None):
+        """hits_buf: a persistent float32 array standing in for the global FastMatchParameters.bestHits
+        (at least as long as the scan): the call rewrites its leading entries exactly as the reference does."""
         out = (C.c_float * 3)()
-        hits = np.zeros(max(self._nbeams, 1), np.float32)
+        hits = np.zeros(max(self._nbeams, 1), np.float32) if hits_buf is None else hits_buf
         n = C.c_int32(0)
         self._check(self.L.b200slam_fastmatch(self.h, m.h, _f3(pose), _f3(res3), out, hits.ctypes.data,
                                               C.byref(n)))

@@ -673,8 +673,12 @@ int b200slam_score_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pos
     rc = b200slam_match_fetch(ctx, result ? result : &tmp);       // copies the result block and synchronises
     if (rc) return rc;
     const b200slam_match *m = result ? result : &tmp;
-    if (last_hit_values && m->last_hits > 0)
-        memcpy(last_hit_values, ctx->h_hit_values, sizeof(float) * (size_t)m->last_hits);
+    // FastMatch-sized lattices rewrite more than the last candidate's entries (main.c:515, see MatchDev)
+    int written = m->last_hits;
+    if (!ctx->last.gathered && ctx->h_match->written_hits > written && ctx->h_match->written_hits <= ctx->nbeams)
+        written = ctx->h_match->written_hits;
+    if (last_hit_values && written > 0)
+        memcpy(last_hit_values, ctx->h_hit_values, sizeof(float) * (size_t)written);
     return B200SLAM_OK;
 }
 

@@ -46,7 +46,15 @@ struct MatchDev {
     unsigned long long gkey;    // GLOBAL result of the last collected exchange (all ranks merged)
     int gbest_hits;
     int glast_hits;
+    // FastMatch-sized lattices (<= MATCH_SMALL candidates): per-candidate hit counts, and how many
+    // leading entries of the hit-value buffer this match (re)wrote.  The reference lets EVERY candidate
+    // overwrite bestHits[] from index 0 (main.c:515), so behind the last candidate's hits the buffer
+    // holds those of the most recent candidate that had more; the kernel's tail reproduces that.
+    int written_hits;
+    int pad2;
+    int cand_hits[64];
 };
+constexpr int MATCH_SMALL = 64;
 
 // Peer-memory exchange of per-rank match results (multi-GPU): every context owns one
 // XchgBuf; the last CTA of a scoring kernel stores its {key, best_hits, last_hits} into

@@ -194,11 +194,12 @@ __global__ void __launch_bounds__(64) exchange_only_kernel(MatchDev *match, cons
 struct TraceCand {
     float ct, st, sxt, syt;
 };
+// lo0 / lo1: only compacted positions >= lo are stored (the staircase behind the last candidate).
 template <int NT>
 __device__ void trace_pair(const float *__restrict__ field, int pitch, int rows, int cols,
                            const float *__restrict__ scan_x, const float *__restrict__ scan_y, int nbeams,
                            float ipixel, const TraceCand (&cand)[2], float *vals0, float *vals1, int *red,
-                           int (&count)[2])
+                           int (&count)[2], int lo0 = 0, int lo1 = 0)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     count[0] = count[1] = 0;
@@ -230,8 +231,9 @@ __device__ void trace_pair(const float *__restrict__ field, int pitch, int rows,
             before1 += w < warp ? c1 : 0; total1 += c1;
         }
         const unsigned below = (1u << lane) - 1u;
-        if (in[0]) vals0[count[0] + before0 + __popc(m0 & below)] = v[0];
-        if (in[1]) vals1[count[1] + before1 + __popc(m1 & below)] = v[1];
+        const int p0 = count[0] + before0 + __popc(m0 & below), p1 = count[1] + before1 + __popc(m1 & below);
+        if (in[0] && p0 >= lo0) vals0[p0] = v[0];
+        if (in[1] && p1 >= lo1) vals1[p1] = v[1];
         count[0] += total0;
         count[1] += total1;
     }
@@ -276,10 +278,12 @@ struct LatticeArgs {
 
 // TYPT candidates (consecutive ty) per thread, WX warps along tx, WY warps along ty.
 // Dynamic shared memory: colT[cb][TXT] | rowT[cb][TYT] | Sx[cb] | Sy[cb]
-template <int TYPT, int WX, int WY, int UM = 1>
+// COUNT (FastMatch-sized lattices only): every thread also counts its candidate's in-bounds beams.
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false>
 __global__ void __launch_bounds__(32 * WX * WY)
 lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ LatticeTables T)
 {
+    static_assert(!COUNT || TYPT == 1, "per-candidate hit counts: one candidate per thread");
     constexpr int TXT = 32 * WX;
     constexpr int TYT = TYPT * WY;
     constexpr int NT = 32 * WX * WY;
@@ -319,6 +323,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
         float acc[TYPT];
 #pragma unroll
         for (int j = 0; j < TYPT; ++j) acc[j] = 0.0f;            // main.c:507
+        int nhits = 0;                                           // COUNT only
 
         for (int c0 = 0; c0 < A.nbeams; c0 += A.cb) {
             const int cb = min(A.cb, A.nbeams - c0);
@@ -388,7 +393,11 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                         for (int j = 0; j < TYPT; ++j) ro[j] = rp[i * TYT + j];
                     }
 #pragma unroll
-                    for (int j = 0; j < TYPT; ++j) dst[u][j] = ldg_ordered(A.field + __viaddmax_s32(c, ro[j], -1));
+                    for (int j = 0; j < TYPT; ++j) {
+                        const int off = __viaddmax_s32(c, ro[j], -1);
+                        dst[u][j] = ldg_ordered(A.field + off);
+                        if constexpr (COUNT) nhits += off >= 0 ? 1 : 0;
+                    }
                 }
                 // order fence for the compiler: the additions below stay behind these loads
 #pragma unroll
@@ -425,6 +434,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                 if (ity < A.nty) {
                     const long long lin = row * A.nty + ity;
                     if (A.scores) A.scores[lin] = acc[j];
+                    if constexpr (COUNT) A.match->cand_hits[lin] = nhits;
                     const unsigned long long k = pack_key(acc[j], (unsigned int)lin);
                     best = k < best ? k : best;
                 }
@@ -460,6 +470,31 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
         trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand,
                        A.hit_values, A.hit_values + A.hit_stride, tail_red, hits);
     }
+    int written = hits[1];
+    if constexpr (COUNT) {
+        // main.c:515: every candidate overwrites bestHits[] from index 0 in loop order, so behind the
+        // last candidate's hits[1] values the array holds those of the most recent candidate that had
+        // more hits, and so on: walk the candidates backwards and let each one that is longer than what
+        // has been written so far supply the entries it alone still owns.
+        if (key != ~0ull) {
+            const int ncand = A.nth * A.ntx * A.nty;
+            for (int c = ncand - 2; c >= 0; --c) {
+                const int nc = *reinterpret_cast<volatile int *>(&A.match->cand_hits[c]);
+                if (nc <= written) continue;                                       // uniform across the CTA
+                const int ity = c % A.nty, itx = (c / A.nty) % A.ntx, jth = c / A.nty / A.ntx;
+                TraceCand cand[2];
+                cand[0].ct = ctT[jth - A.th_first]; cand[0].st = stT[jth - A.th_first];
+                cand[0].sxt = sxtT[itx]; cand[0].syt = sytT[ity];
+                cand[1] = cand[0];
+                int n2[2];
+                float *tail = A.hit_values + A.hit_stride;
+                __syncthreads();
+                trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand, tail,
+                               tail, tail_red, n2, written, written);
+                written = nc;
+            }
+        }
+    }
     const int best_hits = hits[0], last_hits = hits[1];
     const unsigned long long out_key = key;
     if (A.xchg.peers) {
@@ -478,6 +513,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
         A.match->key = out_key;
         A.match->best_hits = best_hits;
         A.match->last_hits = last_hits;
+        A.match->written_hits = written;
         A.match->work_key = ~0ull;
         A.match->tickets = 0u;
         if (A.xchg.peers) A.match->epoch = epoch_s;
@@ -593,11 +629,11 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
     }
 }
 
-template <int TYPT, int WX, int WY, int UM = 1>
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false>
 int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T, int nth_cover)
 {
     constexpr int TXT = 32 * WX, TYT = TYPT * WY;
-    auto kern = lattice_kernel<TYPT, WX, WY, UM>;
+    auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT>;
     // Beams per chunk: the whole scan when its tables fit the budget, else even chunks.
     constexpr int GUARD = LatticePipe<TYPT, UM>::GUARD;
     const int per_beam = (TXT + TYT + 2) * 4;
@@ -689,6 +725,11 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     // launch leaves idle.  Measured on config 1 (64 x 32 x 32 x 360 beams; one launch alone /
     // EDT+match step with the next EDT running under the match): 32 x 16 tiles with 16-beam
     // groups 24.9 / 31.6 us, 32 x 8 tiles 27.1 / 27.4 us, 32 x 32 tiles 33.3 / 23.2 us.
+    // FastMatch-sized lattices (the reference's 3 x 3 x 3): one candidate per thread with per-candidate
+    // hit counts, so that the tail can leave bestHits[] exactly as the reference's loop does.
+    if (!getenv("B200SLAM_LATTICE_CFG") && (long long)L.nth * L.ntx * L.nty <= MATCH_SMALL && L.row_begin == 0 &&
+        L.row_end == (int64_t)L.nth * L.ntx && !A.xchg.peers && L.nth_tab == L.nth)
+        return launch_lattice_cfg<1, 1, 4, 1, true>(ctx, A, T, nth_cover);
     struct Shape { int typt, wx, wy, um; double per_eval; };
     static const Shape shapes[] = {
         {16, 2, 4, 1, 1.00}, {8, 1, 8, 1, 1.05}, {4, 1, 8, 1, 1.13}, {2, 1, 8, 2, 1.40}, {1, 1, 8, 1, 1.95}, {1, 1, 4, 1, 1.95},

@@ -364,3 +364,31 @@ def test_config4_full_size_pyramid_10m_properties(ctx, oracle, synth, b200slam):
     finally:
         for mp in maps:
             mp.close()
+
+
+@pytest.mark.gpu
+def test_fastmatch_leaves_besthits_exactly_as_the_reference_loop(ctx, oracle, synth):
+    """main.c:515: EVERY candidate overwrites FastMatchParameters.bestHits[] from index 0, in loop order, and
+    the array is a global that is never cleared.  After a call it therefore holds the last candidate's
+    hits, behind them those of the most recent candidate that had more, and behind those whatever earlier
+    calls left.  main.c:942-948 reads bestHits[j] for j < bestHits_size (the WINNER's count), which can
+    reach into that tail.  Poses at the edge of the grid make the 27 candidates' counts differ."""
+    w = synth.make_workload("tiny")
+    m, om = _setup(ctx, oracle, w)
+    try:
+        rows, cols = w["occ"].shape
+        gbuf, obuf = np.zeros(2500, np.float32), np.zeros(2500, np.float32)
+        res = np.array([0.3, 0.3, 0.05], np.float32)
+        saw_tail = False
+        for k in range(8):
+            # walk the pose towards (and past) the right / bottom edge
+            pose = np.array([w["pose0"][0] + 1.9 * k, w["pose0"][1] + 1.3 * k, w["pose0"][2] + 0.21 * k], np.float32)
+            gp, _, gn = ctx.fastmatch(m, pose, res, hits_buf=gbuf)
+            op, _, on = oracle.fastmatch(om, w["scan_x"], w["scan_y"], pose, res, hits_buf=obuf)
+            assert np.array_equal(bits(gp), bits(op)) and gn == on
+            assert np.array_equal(bits(gbuf), bits(obuf)), f"call {k}: bestHits differs at {np.flatnonzero(gbuf != obuf)[:5]}"
+            lat, _, _ = oracle.score_lattice(om, w["scan_x"], w["scan_y"], pose, [res[0], res[0], res[2]], (3, 3, 3))
+            saw_tail |= lat.best_hits > lat.last_hits
+        assert saw_tail, "the test never exercised the winner-longer-than-last case"
+    finally:
+        m.close()
