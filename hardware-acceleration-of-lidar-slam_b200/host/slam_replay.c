@@ -1,0 +1,167 @@
+/*
+ * slam_replay.c -- the reference's per-scan loop with every data step on the device.
+ *
+ * Host code in C on top of include/b200slam.h, restating the CONTROL FLOW of the reference's
+ * main() (Subsystem_1/main.c:825-990 == Subsystem_1/main_accelerated.c:840-1005): CSV replay,
+ * first scan initialises the map, then per scan readAScan -> (after a mini update: Transform,
+ * ExtractLocalMap, OccupationalGrid + both distance transforms) -> constant-velocity guess ->
+ * FastMatch on the coarse or FastMatch2 on the fine grid -> FastMatch2 refinement -> mini-update
+ * test -> map growth.  The scan, the map points, the local map, both grids and both distance
+ * fields never leave the GPU: per scan 4 bytes per beam go up, and the scan size, the matched
+ * poses and the local-map / growth counts come back.  Output is the reference's, byte for byte:
+ * "scan N" / "pose = ..." lines (main.c:860, 965) and the map dump "%f,%f\n" (main.c:983-985).
+ *
+ *     b200slam_replay <lidar.csv> <map_out.csv> [nscans = 3480]
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
+
+#include "b200slam.h"
+
+#define COLUMN 1079                                /* main.c:7 */
+
+static b200slam_ctx *ctx;
+
+static void must(int rc, const char *what)
+{
+    if (rc) {
+        fprintf(stderr, "b200slam_replay: %s failed (%d): %s\n", what, rc, b200slam_last_error(ctx));
+        exit(1);
+    }
+}
+
+static int read_row(FILE *fp, float *ranges)
+{
+    for (int k = 0; k < COLUMN; k++) {             /* main.c:22-30 */
+        float value;
+        if (fscanf(fp, "%f,", &value) != 1) return k == 0 ? 0 : -1;
+        ranges[k] = value;
+    }
+    return 1;
+}
+
+static void build_grids(b200slam_map *coarse, b200slam_map *fine, float pixel, float pixel2)
+{
+    /* OccupationalGrid, main.c:271-363: both levels rasterised from the resident local map and
+     * transformed in place */
+    must(b200slam_map_rasterise_local(ctx, coarse, pixel, NULL, NULL, NULL), "rasterise (coarse)");
+    must(b200slam_map_edt(ctx, coarse, 10.0f), "EDT (coarse)");
+    must(b200slam_map_rasterise_local(ctx, fine, pixel2, NULL, NULL, NULL), "rasterise (fine)");
+    must(b200slam_map_edt(ctx, fine, 10.0f), "EDT (fine)");
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) {
+        fprintf(stderr, "usage: %s <lidar.csv> <map_out.csv> [nscans]\n", argv[0]);
+        return 2;
+    }
+    const int row = argc > 3 ? atoi(argv[3]) : 3480;          /* main_accelerated.c:6 */
+    clock_t start = clock();
+
+    float pose[3] = {0, 0, 0};
+    /* main.c:832-840 */
+    const float fastResolution[3] = {0.05f, 0.05f, 0.008727f};
+    const float fastResolution2[3] = {0.025f, 0.025f, 0.004363f};
+    const float borderSize = 1;
+    const float pixelSize = 0.2f, pixelSize2 = 0.1f;
+    const float miniUpdateDT = 0.3f, miniUpdateDR = 0.0872665f;
+
+    FILE *fp = fopen(argv[1], "r");
+    if (!fp) { fprintf(stderr, "Failed to open the file.\n"); return 1; }
+    const char *dev = getenv("B200SLAM_DEVICE");
+    must(b200slam_create(&ctx, dev ? atoi(dev) : 0), "b200slam_create");
+
+    /* SetLidarParameters, main.c:45-58; cos / sin of the beam angles as readAScan takes them (:90-91) */
+    static float cos_a[COLUMN], sin_a[COLUMN], ranges[COLUMN];
+    {
+        float angle = -2.351831f;
+        for (int i = 0; i < COLUMN; i++) {
+            cos_a[i] = cosf(angle);
+            sin_a[i] = sinf(angle);
+            angle += 0.004363f;
+        }
+    }
+    must(b200slam_lidar_set(ctx, cos_a, sin_a, COLUMN, 0.023f), "b200slam_lidar_set");
+    b200slam_map *coarse = NULL, *fine = NULL;
+    must(b200slam_map_create(ctx, 200, 200, &coarse), "map_create");     /* main.c:201 */
+    must(b200slam_map_create(ctx, 400, 400, &fine), "map_create");       /* main.c:207 */
+
+    float (*path)[3] = malloc(sizeof(float[3]) * (size_t)(row > 0 ? row : 1));
+    float map_pose[3];
+    int size = 0;
+
+    /* scan 0 (main.c:843-853) */
+    if (read_row(fp, ranges) != 1) { fprintf(stderr, "empty dataset\n"); return 1; }
+    must(b200slam_scan_read(ctx, ranges, 24, &size), "scan_read");
+    must(b200slam_scan_transform(ctx, pose), "scan_transform");
+    must(b200slam_mappoints_from_scan(ctx), "mappoints_from_scan");      /* Initialise */
+    for (int i = 0; i < 3; i++) { map_pose[i] = pose[i]; path[0][i] = pose[i]; }
+
+    int miniUpdated = 1, path_iter = 1;
+    for (int scan_iter = 1; scan_iter < row; scan_iter++) {
+        printf("scan %d\n", scan_iter + 1);
+        if (read_row(fp, ranges) != 1) {
+            fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
+            return 1;
+        }
+        must(b200slam_scan_read(ctx, ranges, 24, &size), "scan_read");
+        int scan_transform_flag = 0;
+        if (miniUpdated) {                                                /* main.c:865-872 */
+            must(b200slam_scan_transform(ctx, pose), "scan_transform");
+            scan_transform_flag = 1;
+            must(b200slam_local_map_extract(ctx, borderSize, NULL), "local_map_extract");
+            build_grids(coarse, fine, pixelSize, pixelSize2);
+        }
+        /* constant-velocity motion model, main.c:875-898 */
+        float pose_guess[3];
+        if (scan_iter > 1) {
+            for (int i = 0; i < 3; i++) {
+                const float dp = pose[i] - path[path_iter - 2][i];        /* DiffPose(previous_pose, pose) */
+                pose_guess[i] = pose[i] + dp;
+            }
+        } else {
+            for (int i = 0; i < 3; i++) pose_guess[i] = pose[i];
+        }
+        /* main.c:901-922 */
+        float matched[3];
+        must(b200slam_fastmatch(ctx, miniUpdated ? coarse : fine, pose_guess, fastResolution, matched, NULL, NULL),
+             "fastmatch");
+        must(b200slam_fastmatch(ctx, fine, matched, fastResolution2, pose, NULL, NULL), "fastmatch2");
+        /* mini update, main.c:928-961 */
+        float dp[3];
+        for (int i = 0; i < 3; i++) dp[i] = fabsf(pose[i] - map_pose[i]);
+        if (dp[0] > miniUpdateDT || dp[1] > miniUpdateDT || dp[2] > miniUpdateDR) {
+            miniUpdated = 1;
+            if (!scan_transform_flag) must(b200slam_scan_transform(ctx, pose), "scan_transform");
+            must(b200slam_mappoints_grow(ctx, 1.5f, NULL), "mappoints_grow");
+            for (int i = 0; i < 3; i++) map_pose[i] = pose[i];
+        } else {
+            miniUpdated = 0;
+        }
+        printf("pose = %f  %f  %f\n", pose[0], pose[1], pose[2]);
+        for (int i = 0; i < 3; i++) path[path_iter][i] = pose[i];
+        path_iter++;
+    }
+    must(b200slam_sync(ctx), "sync");
+    printf("time taken = %f\n", (double)(clock() - start) / CLOCKS_PER_SEC);
+    fclose(fp);
+
+    int n = 0;
+    must(b200slam_mappoints_download(ctx, NULL, NULL, &n), "mappoints_download");
+    float *mx = malloc(sizeof(float) * (size_t)(n > 0 ? n : 1)), *my = malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    must(b200slam_mappoints_download(ctx, mx, my, &n), "mappoints_download");
+    FILE *fp1 = fopen(argv[2], "w");
+    if (!fp1) { fprintf(stderr, "cannot write %s\n", argv[2]); return 1; }
+    for (int j = 0; j < n; j++) fprintf(fp1, "%f,%f\n", mx[j], my[j]);   /* main.c:983-985 */
+    fclose(fp1);
+    fprintf(stderr, "b200slam_replay: %d scans, %d map points, %llu kernel launches\n", row, n,
+            (unsigned long long)b200slam_launch_count(ctx));
+    free(mx); free(my); free(path);
+    b200slam_map_destroy(ctx, coarse);
+    b200slam_map_destroy(ctx, fine);
+    b200slam_destroy(ctx);
+    return 0;
+}

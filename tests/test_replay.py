@@ -73,3 +73,23 @@ def test_dropin_replay_is_byte_identical(reference_run, dataset, b200slam):
     diff = [i for i, (a, b) in enumerate(zip(ref_lines, gpu_lines)) if a != b]
     assert not diff, f"first differing line {diff[0]}: ref={ref_lines[diff[0]]!r} gpu={gpu_lines[diff[0]]!r}"
     assert gpu_map == ref_map
+
+
+@pytest.mark.gpu
+def test_device_resident_replay_is_byte_identical(reference_run, dataset, b200slam):
+    """b200slam_replay (host/slam_replay.c): the control flow of the reference's main() in C over the ABI,
+    with readAScan / Transform / ExtractLocalMap / OccupationalGrid / both EDTs / FastMatch / FastMatch2 / map
+    growth all on the device.  Same pose trace, same map dump, byte for byte --
+    which also pins the inline map-growth code of main() (main.c:942-948) end to end."""
+    d, csv = dataset
+    exe = os.path.join(os.path.dirname(b200slam.LIB_PATH), "b200slam_replay")
+    assert os.path.exists(exe), "b200slam_replay missing: run __graft_entry__.build()"
+    mapout = str(d / "map_dev.csv")
+    p = subprocess.run([exe, csv, mapout, str(NSCANS)], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    gpu_lines = [ln for ln in p.stdout.splitlines() if not ln.startswith("time taken")]
+    ref_lines, ref_map = reference_run
+    assert len(gpu_lines) == len(ref_lines)
+    diff = [i for i, (a, b) in enumerate(zip(ref_lines, gpu_lines)) if a != b]
+    assert not diff, f"first differing line {diff[0]}: ref={ref_lines[diff[0]]!r} gpu={gpu_lines[diff[0]]!r}"
+    assert open(mapout, "rb").read() == ref_map
