@@ -13,6 +13,11 @@
  *         (Subsystem_1/main.c:271 -- the step in front of the transform: map points are
  *          rasterised and transformed on the device, 8 bytes per point cross PCIe instead of
  *          4 bytes per cell)
+ *     void readAScan(const int usableRange)            (main.c:71)
+ *     void Transform(const float POSE[3])               (main.c:97)
+ *     void ExtractLocalMap(const float BORDERSIZE)      (main.c:155)
+ *         (the steps in front of OccupationalGrid, on the device; their results are also written
+ *          back into the reference's globals scan / local_map, which main() itself reads)
  * so that the unmodified reference program, built as a shared object, calls the GPU path
  * when this library precedes it in the link order (ELF symbol interposition, see
  * INTEGRATION.md).  FastMatch* read the reference's globals `scan` and `occ_grid` and write
@@ -22,6 +27,7 @@
  * Errors: the reference functions return void and cannot fail, and there is no CPU
  * fallback by design, so any failure prints the library's message and aborts.
  */
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -57,6 +63,21 @@ typedef struct {                              /* main.c:147-151 */
     int size;
 } myLocalMap;
 
+typedef struct {                              /* main.c:35-42 */
+    float angle_min, angle_max, angle_increment, range_min, range_max;
+    float angles[REF_COLUMN];
+} LidarParameters;
+
+typedef struct {                              /* main.c:121-131 */
+    float x[20000];
+    float y[20000];
+    int size;
+    float newPoints_x[4000];
+    float newPoints_y[4000];
+    int newPointsSize;
+    float pose[3];
+} MapPoints;
+
 typedef struct {                              /* main.c:374-378 */
     float pose[3];
     float bestHits[2500];
@@ -68,6 +89,9 @@ extern ScanData scan __attribute__((weak));
 extern MyGrid occ_grid __attribute__((weak));
 extern MyFastMatchParameters FastMatchParameters __attribute__((weak));
 extern myLocalMap local_map __attribute__((weak));
+extern LidarParameters lidar __attribute__((weak));
+extern MapPoints map __attribute__((weak));
+extern float test_input_memory[REF_COLUMN] __attribute__((weak));
 
 static b200slam_ctx *g_ctx;
 static float g_scan_x[REF_COLUMN], g_scan_y[REF_COLUMN];   /* the scan the device currently holds */
@@ -79,6 +103,12 @@ static struct {
     int rows, cols;
     const float *host_field;                  /* which host array the device copy mirrors */
 } g_maps[2];
+
+static float g_lidar_angles[REF_COLUMN];                    /* the angle table the device's cos / sin came from */
+static int g_lidar_set;
+static int g_local_on_device;                               /* local_map == the device-resident local map */
+static float g_map_x[20000], g_map_y[20000];               /* the map points the device currently holds */
+static int g_map_size;
 
 static void die(const char *what, int rc)
 {
@@ -146,6 +176,8 @@ void euclidean_distance_transform2(int input_map[400][400], float output_distanc
     edt_common(1, &input_map[0][0], &output_distance_map[0][0], 400, height, width);
 }
 
+static void sync_device_scan(void);
+
 static void fastmatch_common(int slot, const float POSE[3], const float searchResolution[3])
 {
     if (!&scan || !&occ_grid || !&FastMatchParameters) {
@@ -169,14 +201,7 @@ static void fastmatch_common(int slot, const float POSE[3], const float searchRe
                                    slot ? occ_grid.top_left_corner2[1] : occ_grid.top_left_corner[1]);
     if (rc) die("b200slam_map_set_geometry", rc);
     /* main.c:417-421.  FastMatch and FastMatch2 of one iteration see the same scan: upload once. */
-    if (g_scan_size != scan.size || memcmp(g_scan_x, scan.x, sizeof(float) * (size_t)scan.size) ||
-        memcmp(g_scan_y, scan.y, sizeof(float) * (size_t)scan.size)) {
-        rc = b200slam_scan_upload(ctx(), scan.x, scan.y, scan.size);
-        if (rc) die("b200slam_scan_upload", rc);
-        memcpy(g_scan_x, scan.x, sizeof(float) * (size_t)scan.size);
-        memcpy(g_scan_y, scan.y, sizeof(float) * (size_t)scan.size);
-        g_scan_size = scan.size;
-    }
+    sync_device_scan();
     rc = b200slam_fastmatch(ctx(), m, POSE, searchResolution, FastMatchParameters.pose,
                             FastMatchParameters.bestHits, &FastMatchParameters.bestHits_size);
     if (rc) die("b200slam_fastmatch", rc);
@@ -201,9 +226,15 @@ static void occgrid_level(int slot, float pixel)
     int rows = 0, cols = 0;
     float tl[2];
     if (!g_maps[slot].map) slot_map(slot, S, S);
-    int rc = b200slam_map_rasterise(ctx(), g_maps[slot].map, local_map.x, local_map.y, local_map.size, pixel,
+    int rc;
+    if (g_local_on_device) {          /* ExtractLocalMap left the very same points on the device */
+        rc = b200slam_map_rasterise_local(ctx(), g_maps[slot].map, pixel, &rows, &cols, tl);
+        if (rc) die("b200slam_map_rasterise_local", rc);
+    } else {
+        rc = b200slam_map_rasterise(ctx(), g_maps[slot].map, local_map.x, local_map.y, local_map.size, pixel,
                                     &rows, &cols, tl);
-    if (rc) die("b200slam_map_rasterise", rc);
+        if (rc) die("b200slam_map_rasterise", rc);
+    }
     g_maps[slot].rows = rows;
     g_maps[slot].cols = cols;
     rc = b200slam_map_edt(ctx(), g_maps[slot].map, 10.0f);                  /* main.c:355-356 */
@@ -237,10 +268,92 @@ void OccupationalGrid(const float PIXELSIZE, const float PIXELSIZE2)
     occgrid_level(1, PIXELSIZE2);
 }
 
+/* ---- the steps in front of OccupationalGrid --------------------------- */
+
+/* main.c:71-95.  Reads test_input_memory / lidar, leaves scan.x / scan.y / scan.size. */
+void readAScan(const int usableRange)
+{
+    float *volatile raw = test_input_memory;                        /* weak: NULL when the reference is not loaded */
+    if (!&scan || !&lidar || !raw) {
+        fprintf(stderr, "libb200slam_dropin: readAScan needs the reference globals scan / lidar / test_input_memory\n");
+        abort();
+    }
+    int rc;
+    if (!g_lidar_set || memcmp(g_lidar_angles, lidar.angles, sizeof g_lidar_angles)) {
+        static float ca[REF_COLUMN], sa[REF_COLUMN];
+        for (int i = 0; i < REF_COLUMN; i++) {                       /* main.c:90-91 */
+            ca[i] = cosf(lidar.angles[i]);
+            sa[i] = sinf(lidar.angles[i]);
+        }
+        rc = b200slam_lidar_set(ctx(), ca, sa, REF_COLUMN, lidar.range_min);
+        if (rc) die("b200slam_lidar_set", rc);
+        memcpy(g_lidar_angles, lidar.angles, sizeof g_lidar_angles);
+        g_lidar_set = 1;
+    }
+    rc = b200slam_scan_read(ctx(), raw, usableRange, &scan.size);
+    if (rc) die("b200slam_scan_read", rc);
+    rc = b200slam_scan_download(ctx(), scan.x, scan.y, NULL, NULL, NULL);
+    if (rc) die("b200slam_scan_download", rc);
+    memcpy(g_scan_x, scan.x, sizeof(float) * (size_t)scan.size);    /* the device holds exactly this scan */
+    memcpy(g_scan_y, scan.y, sizeof(float) * (size_t)scan.size);
+    g_scan_size = scan.size;
+}
+
+static void sync_device_scan(void)
+{
+    if (g_scan_size != scan.size || memcmp(g_scan_x, scan.x, sizeof(float) * (size_t)scan.size) ||
+        memcmp(g_scan_y, scan.y, sizeof(float) * (size_t)scan.size)) {
+        int rc = b200slam_scan_upload(ctx(), scan.x, scan.y, scan.size);
+        if (rc) die("b200slam_scan_upload", rc);
+        memcpy(g_scan_x, scan.x, sizeof(float) * (size_t)scan.size);
+        memcpy(g_scan_y, scan.y, sizeof(float) * (size_t)scan.size);
+        g_scan_size = scan.size;
+    }
+}
+
+/* main.c:97-118.  Leaves scan.tx / scan.ty. */
+void Transform(const float POSE[3])
+{
+    if (!&scan) {
+        fprintf(stderr, "libb200slam_dropin: Transform needs the reference global scan\n");
+        abort();
+    }
+    sync_device_scan();
+    int rc = b200slam_scan_transform(ctx(), POSE);
+    if (rc) die("b200slam_scan_transform", rc);
+    rc = b200slam_scan_download(ctx(), NULL, NULL, scan.tx, scan.ty, NULL);
+    if (rc) die("b200slam_scan_download", rc);
+}
+
+/* main.c:155-198.  Reads scan.tx / scan.ty (as the last Transform left them on the device) and map,
+ * leaves local_map.  main() appends to map.x / map.y itself (main.c:942-948): only what changed
+ * since the last call is uploaded. */
+void ExtractLocalMap(const float BORDERSIZE)
+{
+    if (!&scan || !&map || !&local_map) {
+        fprintf(stderr, "libb200slam_dropin: ExtractLocalMap needs the reference globals scan / map / local_map\n");
+        abort();
+    }
+    int same = 0;                                  /* leading points the device already holds */
+    const int lim = g_map_size < map.size ? g_map_size : map.size;
+    while (same < lim && g_map_x[same] == map.x[same] && g_map_y[same] == map.y[same]) same++;
+    int rc = b200slam_mappoints_upload(ctx(), map.x + same, map.y + same, map.size - same, same);
+    if (rc) die("b200slam_mappoints_upload", rc);
+    memcpy(g_map_x + same, map.x + same, sizeof(float) * (size_t)(map.size - same));
+    memcpy(g_map_y + same, map.y + same, sizeof(float) * (size_t)(map.size - same));
+    g_map_size = map.size;
+    rc = b200slam_local_map_extract(ctx(), BORDERSIZE, &local_map.size);
+    if (rc) die("b200slam_local_map_extract", rc);
+    rc = b200slam_local_map_download(ctx(), local_map.x, local_map.y, NULL);
+    if (rc) die("b200slam_local_map_download", rc);
+    g_local_on_device = 1;
+}
+
 /* The host field array may be rewritten by someone other than our transform (tests do);
  * callers can force a re-upload on the next FastMatch. */
 void b200slam_dropin_invalidate(void)
 {
     g_maps[0].host_field = NULL;
     g_maps[1].host_field = NULL;
+    g_local_on_device = 0;
 }

@@ -32,6 +32,13 @@ static void must(int rc, const char *what)
     }
 }
 
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 static int read_row(FILE *fp, float *ranges)
 {
     for (int k = 0; k < COLUMN; k++) {             /* main.c:22-30 */
@@ -100,10 +107,15 @@ int main(int argc, char **argv)
     must(b200slam_mappoints_from_scan(ctx), "mappoints_from_scan");      /* Initialise */
     for (int i = 0; i < 3; i++) { map_pose[i] = pose[i]; path[0][i] = pose[i]; }
 
-    int miniUpdated = 1, path_iter = 1;
+    int miniUpdated = 1, path_iter = 1, rebuilds = 0;
+    double t_parse = 0.0;
+    const double t_loop = now_s();
     for (int scan_iter = 1; scan_iter < row; scan_iter++) {
         printf("scan %d\n", scan_iter + 1);
-        if (read_row(fp, ranges) != 1) {
+        const double tp = now_s();
+        const int got = read_row(fp, ranges);
+        t_parse += now_s() - tp;
+        if (got != 1) {
             fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
             return 1;
         }
@@ -114,6 +126,7 @@ int main(int argc, char **argv)
             scan_transform_flag = 1;
             must(b200slam_local_map_extract(ctx, borderSize, NULL), "local_map_extract");
             build_grids(coarse, fine, pixelSize, pixelSize2);
+            rebuilds++;
         }
         /* constant-velocity motion model, main.c:875-898 */
         float pose_guess[3];
@@ -146,6 +159,7 @@ int main(int argc, char **argv)
         path_iter++;
     }
     must(b200slam_sync(ctx), "sync");
+    const double loop_s = now_s() - t_loop;
     printf("time taken = %f\n", (double)(clock() - start) / CLOCKS_PER_SEC);
     fclose(fp);
 
@@ -157,8 +171,10 @@ int main(int argc, char **argv)
     if (!fp1) { fprintf(stderr, "cannot write %s\n", argv[2]); return 1; }
     for (int j = 0; j < n; j++) fprintf(fp1, "%f,%f\n", mx[j], my[j]);   /* main.c:983-985 */
     fclose(fp1);
-    fprintf(stderr, "b200slam_replay: %d scans, %d map points, %llu kernel launches\n", row, n,
-            (unsigned long long)b200slam_launch_count(ctx));
+    fprintf(stderr, "b200slam_replay: %d scans, %d map points, %d map rebuilds, %llu kernel launches; loop %.3f s wall "
+                    "of which CSV parsing %.3f s -> %.1f us per scan on the device path\n", row, n, rebuilds,
+            (unsigned long long)b200slam_launch_count(ctx), loop_s, t_parse,
+            row > 1 ? 1e6 * (loop_s - t_parse) / (row - 1) : 0.0);
     free(mx); free(my); free(path);
     b200slam_map_destroy(ctx, coarse);
     b200slam_map_destroy(ctx, fine);
