@@ -396,7 +396,9 @@ def measure_workload(args, synth, workload, dist, K, want_cpu):
             # inside a turn every match POSTS its per-rank best to the peers and merges the PREVIOUS
             # step's posts in the same kernel tail (allreduce = 2), so ranks are not held in
             # lockstep; one collect at the end of the turn merges the last step
-            post = 2 if allreduce else 0
+            # ... or, when a whole turn fits the exchange ring (<= 15 steps), POSTS only (allreduce = 3) and
+            # the collect at the end of the turn merges every step's posts: no kernel waits for a peer
+            post = (3 if ring <= 15 else 2) if allreduce else 0
             if not args.no_pipeline:
                 ctx.set_match_mode(mod.MATCH_LATENCY)          # strictly sequential kernels: the default policy
             ctx.graph_begin()
@@ -446,6 +448,8 @@ def measure_workload(args, synth, workload, dist, K, want_cpu):
     if use_graph and turn is not turn_serial:
         run_steps(max(W, ring), turn_serial)
         barrier()
+        if world > 1 and allreduce:
+            run_steps(ring, turn_serial)
         ctx.event_record(4002)
         run_steps(K, turn_serial)
         ctx.event_record(4003)
@@ -453,6 +457,11 @@ def measure_workload(args, synth, workload, dist, K, want_cpu):
         serial_ms = ctx.event_elapsed_ms(4002, 4003) / K
     run_steps(max(W, ring), turn)
     barrier()
+    if world > 1 and use_graph and allreduce:
+        # The ranks leave the host-side barrier hundreds of microseconds apart -- a quarter of a
+        # 100-step timed region at 25 us per step.  One more untimed turn, which ends in the
+        # device-side collect, lines the GPUs up; the start event follows it on the stream.
+        run_steps(ring, turn)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.event_record(4000)
     run_steps(K, turn)

@@ -532,6 +532,13 @@ int queue_lattice(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3], co
     const bool multi = allreduce != 0 && ctx->nccl_comm && ctx->nranks > 1;
     L.exchange = multi && ctx->p2p_ready;      // posted from the kernel's tail over NVLink peer memory
     L.collect_prev = L.exchange && allreduce == 2;
+    L.post_deferred = L.exchange && allreduce == 3;
+    if (L.post_deferred) {                                    // recorded only: the collect kernel posts the burst
+        if (ctx->posted_uncollected >= XCHG_MAX_POSTED)
+            return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "more than %d posted matches without "
+                                      "b200slam_exchange_collect_async", XCHG_MAX_POSTED);
+        ctx->posted_uncollected++;
+    }
     if (want_scores) {
         const size_t need = (size_t)nrows * n[2];
         if (need > ctx->scores_cap) {
@@ -642,6 +649,7 @@ int b200slam_exchange_collect_async(b200slam_ctx *ctx)
 {
     if (!ctx) return B200SLAM_ERR_ARG;
     if (!(ctx->nccl_comm && ctx->nranks > 1 && ctx->p2p_ready)) return B200SLAM_OK;   // nothing was deferred
+    ctx->posted_uncollected = 0;
     return exchange_collect_launch(ctx);
 }
 

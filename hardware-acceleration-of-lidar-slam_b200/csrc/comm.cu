@@ -171,7 +171,8 @@ void setup_peer_exchange(b200slam_ctx *ctx)
               cudaMemset(ctx->d_xchg, 0, sizeof(XchgBuf)) == cudaSuccess &&
               cudaMalloc(&ctx->d_peers, sizeof(XchgBuf *) * n) == cudaSuccess &&
               cudaMemset(&ctx->d_match->epoch, 0, sizeof(unsigned int)) == cudaSuccess &&
-              cudaMemset(&ctx->d_match->collected, 0, sizeof(unsigned int)) == cudaSuccess;
+              cudaMemset(&ctx->d_match->collected, 0, sizeof(unsigned int)) == cudaSuccess &&
+              cudaMemset(&ctx->d_match->posted, 0, sizeof(unsigned int)) == cudaSuccess;
     // handle record: 64-byte IPC handle + 8-byte ok flag, padded to 80 bytes (10 x u64)
     constexpr int REC = 10;
     unsigned long long rec[REC] = {0};

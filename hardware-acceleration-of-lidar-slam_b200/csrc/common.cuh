@@ -51,9 +51,14 @@ struct MatchDev {
     // overwrite bestHits[] from index 0 (main.c:515), so behind the last candidate's hits the buffer
     // holds those of the most recent candidate that had more; the kernel's tail reproduces that.
     int written_hits;
-    int pad2;
+    unsigned int posted;        // peer exchanges whose result has actually been stored into the peers' buffers
     int cand_hits[64];
+    // deferred posts (allreduce = 3): a burst of matches records each result here; the collect
+    // kernel at the end of the burst sends them all to the peers at once, so no scoring kernel has
+    // NVLink stores in flight when it completes (measured: ~8 us per kernel on a 2-GPU box)
+    struct Outbox { unsigned long long key; int best_hits, last_hits; } outbox[32];
 };
+static_assert(sizeof(MatchDev::outbox) / sizeof(MatchDev::Outbox) == 32, "outbox ring == XCHG_EPOCHS");
 constexpr int MATCH_SMALL = 64;
 
 // Peer-memory exchange of per-rank match results (multi-GPU): every context owns one
@@ -62,9 +67,14 @@ constexpr int MATCH_SMALL = 64;
 // words of that epoch have landed in its own buffer, and merges.  The four 32-bit payload
 // words travel as 8-byte stores {data, epoch} (each store is atomic and carries its own
 // validity flag, like NCCL's LL protocol), so no fence and no separate flag are needed.
-// 4 epochs of slots: a rank can run at most two posts ahead of the slowest reader.
+// 32 epochs of slots.  With a merge in every kernel tail a rank runs at most two posts ahead of
+// the slowest reader; with post-only bursts (allreduce = 3) a rank posts a burst only after its
+// blocking collect of the previous burst, which needed every peer's posts of that burst, which
+// the peers issued after collecting the burst before -- so slots at distance >= two bursts
+// (2 x XCHG_MAX_POSTED <= 32) have been consumed everywhere.
 constexpr int XCHG_MAX_RANKS = 64;
-constexpr int XCHG_EPOCHS = 4;
+constexpr int XCHG_EPOCHS = 32;
+constexpr int XCHG_MAX_POSTED = 15;   // posts a rank may issue between two blocking collects (two bursts fit the ring)
 struct XchgSlot {
     unsigned long long w[4];          // {key lo, key hi, best_hits, last_hits}, each | (epoch << 32)
 };
@@ -179,6 +189,7 @@ struct b200slam_ctx {
     XchgBuf *peer_ptrs[XCHG_MAX_RANKS] = {};   // host copy (for closing the IPC mappings)
     bool p2p_ready = false;
     unsigned long long bar_epoch = 0;     // peer barriers issued so far (same on every rank)
+    int posted_uncollected = 0;           // post-only matches queued since the last blocking collect
 };
 
 int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
@@ -221,6 +232,7 @@ struct LatticeLaunch {
     float *d_scores;   // optional
     bool exchange;     // post the result to the other ranks through peer memory from the kernel's tail
     bool collect_prev; // ... and merge the previous, deferred exchange in the same tail
+    bool post_deferred; // record the result in the outbox only; the next collect kernel posts it
 };
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);

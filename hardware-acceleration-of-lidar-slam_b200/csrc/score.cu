@@ -160,12 +160,23 @@ __device__ __forceinline__ void exchange_collect(const XchgArgs &X, MatchDev *ma
 __global__ void __launch_bounds__(64) exchange_collect_kernel(MatchDev *match, const XchgArgs X)
 {
     __shared__ unsigned int got[4 * XCHG_MAX_RANKS];
-    __shared__ unsigned int todo[2];
+    __shared__ unsigned int todo[3];
+    __shared__ unsigned int words_s[4];
     if (threadIdx.x == 0) {
         todo[0] = *reinterpret_cast<volatile unsigned int *>(&match->collected);
         todo[1] = *reinterpret_cast<volatile unsigned int *>(&match->epoch);
+        todo[2] = *reinterpret_cast<volatile unsigned int *>(&match->posted);
     }
     __syncthreads();
+    // results recorded in the outbox by a burst of deferred-post matches go out first
+    for (unsigned int e = todo[2] + 1; e <= todo[1]; ++e) {
+        const MatchDev::Outbox *ob = &match->outbox[e % XCHG_EPOCHS];
+        exchange_post(X, e, *reinterpret_cast<const volatile unsigned long long *>(&ob->key),
+                      *reinterpret_cast<const volatile int *>(&ob->best_hits),
+                      *reinterpret_cast<const volatile int *>(&ob->last_hits), words_s);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) match->posted = todo[1];
     for (unsigned int e = todo[0] + 1; e <= todo[1]; ++e) {      // everything posted so far
         exchange_collect(X, match, e, got);
         __syncthreads();
@@ -185,6 +196,7 @@ __global__ void __launch_bounds__(64) exchange_only_kernel(MatchDev *match, cons
         match->best_hits = 0;
         match->last_hits = 0;
         match->epoch = epoch_s;
+        match->posted = epoch_s;
     }
 }
 
@@ -273,6 +285,7 @@ struct LatticeArgs {
     int cb;                   // beams per shared-memory chunk
     unsigned total_ctas;
     int collect_prev;         // exchange: also merge the previous, still uncollected exchange in this tail
+    int post_deferred;        // exchange: record the result in the outbox, the next collect kernel posts it
     XchgArgs xchg;            // peers == nullptr: single GPU / no exchange
 };
 
@@ -497,9 +510,15 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     }
     const int best_hits = hits[0], last_hits = hits[1];
     const unsigned long long out_key = key;
-    if (A.xchg.peers) {
+    if (A.xchg.peers && A.post_deferred) {
+        if (tid == 0) {
+            MatchDev::Outbox *ob = &A.match->outbox[epoch_s % XCHG_EPOCHS];
+            ob->key = key; ob->best_hits = best_hits; ob->last_hits = last_hits;
+        }
+    } else if (A.xchg.peers) {
         __syncthreads();
         exchange_post(A.xchg, epoch_s, key, best_hits, last_hits, xchg_words);
+        if (tid == 0) A.match->posted = epoch_s;
         // merge the PREVIOUS exchange here (posted a whole step ago) when the caller deferred it
         if (A.collect_prev) {
             __shared__ unsigned int got[4 * XCHG_MAX_RANKS];
@@ -692,6 +711,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     A.tables = L.d_tables;
     A.xchg.peers = nullptr; A.xchg.nranks = 1; A.xchg.rank = 0;
     A.collect_prev = L.collect_prev ? 1 : 0;
+    A.post_deferred = L.post_deferred ? 1 : 0;
     if (L.exchange && ctx->p2p_ready) {
         A.xchg.peers = ctx->d_peers;
         A.xchg.nranks = ctx->nranks; A.xchg.rank = ctx->rank;

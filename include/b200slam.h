@@ -162,7 +162,13 @@ int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const floa
  * PREVIOUS post of a sequence of such calls in the same kernel tail -- the ranks drift by up to a
  * step instead of running in lockstep; b200slam_exchange_collect_async after the last call of
  * the sequence merges what is still pending, and b200slam_match_fetch then returns the global
- * result of that last match.  Posts and collects pair up in order on every rank. */
+ * result of that last match.  Posts and collects pair up in order on every rank.
+ * 3 = DEFERRED: the kernel only records this rank's result on its own GPU, so a burst of
+ * independent matches runs at single-GPU speed (no kernel has NVLink stores in flight when it
+ * completes, nothing waits for a peer); b200slam_exchange_collect_async must follow after at
+ * most 15 such calls: it sends the whole burst to the peers, merges every rank's results in
+ * order, and the result of the LAST match is what b200slam_match_fetch returns.  Without NVLink
+ * peer memory (NCCL fallback) 2 and 3 act like 1. */
 int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
                                  const float step[3], const int n[3], int64_t row_begin,
                                  int64_t row_end, int allreduce);

@@ -156,6 +156,14 @@ def run_gpu(mod, synth):
           np.float32(res.best_score).tobytes() == np.float32(o.best_score).tobytes(),
           f"global winner ({res.best_index}, {res.best_score}, {res.best_hits}, {res.last_hits}) != oracle "
           f"({o.best_index}, {o.best_score}, {o.best_hits}, {o.last_hits})")
+    # a burst of post-only matches (allreduce = 3: no kernel waits for a peer), merged by one collect
+    for burst in (9, 15):
+        for i in range(burst):
+            ctx.score_lattice_async(m, w["pose0"], w["step"], n, rb, re, 3)
+        ctx.exchange_collect_async()
+        resb = ctx.match_fetch()
+        check(resb.best_index == o.best_index and resb.best_hits == o.best_hits and resb.last_hits == o.last_hits,
+              f"post-only burst of {burst}: ({resb.best_index}, {resb.best_hits}) != oracle ({o.best_index}, {o.best_hits})")
     # an empty shard must not disturb the result
     res2 = ctx.score_lattice_rows(m, w["pose0"], w["step"], n, 0 if rank == 0 else nrows, nrows, allreduce=True)
     check(res2.best_index == o.best_index, "empty shard changed the winner")
