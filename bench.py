@@ -380,94 +380,106 @@ def measure_workload(args, synth, workload, dist, K, want_cpu):
     ctx.set_match_mode(mod.MATCH_LATENCY if args.latency_mode else mod.MATCH_THROUGHPUT)
 
     # ---- pass B: the timed region.  The step is two microsecond-scale kernels, so steps are
-    # captured as CUDA graphs: one graph holding a whole turn of the ring (`ring` consecutive
-    # steps) for the bulk, single-step graphs for the remainder; K steps are replayed exactly.
+    # captured as CUDA graphs: one graph holding a whole turn (`turn_len` consecutive steps) for the
+    # bulk and one holding the K % turn_len remaining steps; K steps are replayed exactly.
     # Consecutive steps are independent (each has its own map), so inside a turn the transforms
     # run on a second stream (a second context on the same GPU): the EDT of step i+1 executes
     # under the match of step i.  The un-pipelined graph is timed too (`serial_ms_per_step`).
-    graphs, turn, turn_serial, ctx_e = [], None, None, None
+    turn = turn_serial = rem = rem_serial = None
+    ctx_e = None
     use_graph = not args.no_graph
+    # a turn = two passes over the ring when that stays a short burst (config 1: 18 steps): the pipeline
+    # drain / fill at the graph boundary, and for N > 1 the collect that lines the ranks up, cost per turn
+    turn_len = ring * 2 if ring <= 15 else ring
+    # N > 1: inside a turn every match only RECORDS its per-rank best (allreduce = 3) and the collect at
+    # the end of the turn sends the whole burst to the peers over NVLink and merges every step's results:
+    # no scoring kernel waits for a peer or has peer stores in flight.  Turns too long for the exchange
+    # ring post from each kernel's tail and merge the previous step's posts there (allreduce = 2).
+    post = (3 if turn_len <= 31 else 2) if allreduce else 0
+
+    def capture_serial(nsteps):
+        ctx.graph_begin()
+        for k in range(nsteps):
+            i = k % ring
+            maps[i].edt(10.0)
+            ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n_global, row_b, row_e, post)
+        if allreduce:
+            ctx.exchange_collect_async()
+        return ctx.graph_end()
+
+    def capture_pipelined(nsteps):
+        ctx.graph_begin()
+        ctx.event_record(3000)
+        ctx_e.event_wait(ctx, 3000)                   # fork: the transform stream joins the capture
+        for k in range(nsteps):
+            i = k % ring
+            ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
+            ctx_e.event_record(3100 + k)
+            ctx.event_wait(ctx_e, 3100 + k)
+            ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n_global, row_b, row_e, post)
+        if allreduce:
+            ctx.exchange_collect_async()
+        ctx_e.event_record(3200)
+        ctx.event_wait(ctx_e, 3200)                   # join
+        return ctx.graph_end()
+
     if use_graph:
         try:
-            for i in range(ring):
-                ctx.graph_begin()
-                step_async(i)
-                graphs.append(ctx.graph_end())
-            # inside a turn every match POSTS its per-rank best to the peers and merges the PREVIOUS
-            # step's posts in the same kernel tail (allreduce = 2), so ranks are not held in
-            # lockstep; one collect at the end of the turn merges the last step
-            # ... or, when a whole turn fits the exchange ring (<= 15 steps), POSTS only (allreduce = 3) and
-            # the collect at the end of the turn merges every step's posts: no kernel waits for a peer
-            post = (3 if ring <= 15 else 2) if allreduce else 0
             if not args.no_pipeline:
                 ctx.set_match_mode(mod.MATCH_LATENCY)          # strictly sequential kernels: the default policy
-            ctx.graph_begin()
-            for i in range(ring):
-                maps[i].edt(10.0)
-                ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n_global, row_b, row_e, post)
-            if allreduce:
-                ctx.exchange_collect_async()
-            turn_serial = ctx.graph_end()
-            turn = turn_serial
+            turn_serial = capture_serial(turn_len)
+            rem_serial = capture_serial(K % turn_len) if K % turn_len else None
+            turn, rem = turn_serial, rem_serial
             ctx.set_match_mode(mod.MATCH_LATENCY if args.latency_mode else mod.MATCH_THROUGHPUT)
             if not args.no_pipeline:
                 ctx_e = mod.Context(local_rank)
                 for i in range(ring):                         # warm the second context's kernels
                     ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
                 ctx_e.sync()
-                ctx.graph_begin()
-                ctx.event_record(3000)
-                ctx_e.event_wait(ctx, 3000)                   # fork: the transform stream joins the capture
-                for i in range(ring):
-                    ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
-                    ctx_e.event_record(3100 + i)
-                    ctx.event_wait(ctx_e, 3100 + i)
-                    ctx.score_lattice_async(maps[i], w["pose0"], w["step"], n_global, row_b, row_e, post)
-                if allreduce:
-                    ctx.exchange_collect_async()
-                ctx_e.event_record(3200)
-                ctx.event_wait(ctx_e, 3200)                   # join
-                turn = ctx.graph_end()
+                turn = capture_pipelined(turn_len)
+                rem = capture_pipelined(K % turn_len) if K % turn_len else None
         except mod.B200SlamError as e:
             if rank == 0:
                 print(f"[bench] graph capture unavailable ({e}); timing eager launches", file=sys.stderr)
             use_graph = False
-            graphs, turn, turn_serial = [], None, None
+            turn = turn_serial = rem = rem_serial = None
 
-    def run_steps(n, turn_graph):
+    def run_steps(n, turn_graph, rem_graph=None):
+        """n steps: whole turns, then (n == K only) the graph holding the K % turn_len remaining steps."""
         if not use_graph:
             for i in range(n):
                 step_async(i)
             return
-        for _ in range(n // ring):
+        for _ in range(n // turn_len):
             ctx.graph_launch(turn_graph)
-        for i in range(n % ring):
-            ctx.graph_launch(graphs[i])
+        if n % turn_len:
+            assert rem_graph is not None and n == K
+            ctx.graph_launch(rem_graph)
 
     serial_ms = None
     if use_graph and turn is not turn_serial:
-        run_steps(max(W, ring), turn_serial)
+        run_steps(-(-max(W, turn_len) // turn_len) * turn_len, turn_serial)
         barrier()
         if world > 1 and allreduce:
-            run_steps(ring, turn_serial)
+            run_steps(turn_len, turn_serial)
         ctx.event_record(4002)
-        run_steps(K, turn_serial)
+        run_steps(K, turn_serial, rem_serial)
         ctx.event_record(4003)
         barrier()
         serial_ms = ctx.event_elapsed_ms(4002, 4003) / K
-    run_steps(max(W, ring), turn)
+    run_steps(-(-max(W, turn_len) // turn_len) * turn_len, turn)
     barrier()
     if world > 1 and use_graph and allreduce:
         # The ranks leave the host-side barrier hundreds of microseconds apart -- a quarter of a
         # 100-step timed region at 25 us per step.  One more untimed turn, which ends in the
         # device-side collect, lines the GPUs up; the start event follows it on the stream.
-        run_steps(ring, turn)
+        run_steps(turn_len, turn)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.event_record(4000)
-    run_steps(K, turn)
+    run_steps(K, turn, rem)
     ctx.event_record(4001)
     barrier()
-    launches = 2 * K + (K // ring if allreduce else 0)   # EDT + scan-matching kernel per step (+ one collect per turn when N > 1)
+    launches = 2 * K + (K // turn_len + (1 if K % turn_len else 0) if allreduce else 0)   # EDT + scan-matching kernel per step (+ one collect per turn when N > 1)
     dev_ms = ctx.event_elapsed_ms(4000, 4001)
     clocks = sampler.stop() if sampler else None
     last = ctx.match_fetch()
@@ -540,7 +552,7 @@ def measure_workload(args, synth, workload, dist, K, want_cpu):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(w, args, world), ring_maps=ring,
-                           timing=(f"cuda-graph replay ({ring} steps per graph"
+                           timing=(f"cuda-graph replay ({turn_len} steps per graph"
                                    + (", EDT of step i+1 on a second stream under the match of step i)" if ctx_e else ")"))
                            if use_graph else "eager launches"),
             "serial_ms_per_step": serial_ms,
@@ -557,7 +569,7 @@ def measure_workload(args, synth, workload, dist, K, want_cpu):
         if world == 1 and want_cpu:
             line["cpu_baseline"] = cpu_sample(w, synth, budget_s=args.cpu_seconds)
 
-    for g in graphs + [g for g in {id(turn): turn, id(turn_serial): turn_serial}.values() if g is not None]:
+    for g in {id(g): g for g in (turn, turn_serial, rem, rem_serial) if g is not None}.values():
         ctx.graph_destroy(g)
     if ctx_e is not None:
         ctx_e.close()

@@ -56,9 +56,9 @@ struct MatchDev {
     // deferred posts (allreduce = 3): a burst of matches records each result here; the collect
     // kernel at the end of the burst sends them all to the peers at once, so no scoring kernel has
     // NVLink stores in flight when it completes (measured: ~8 us per kernel on a 2-GPU box)
-    struct Outbox { unsigned long long key; int best_hits, last_hits; } outbox[32];
+    struct Outbox { unsigned long long key; int best_hits, last_hits; } outbox[64];
 };
-static_assert(sizeof(MatchDev::outbox) / sizeof(MatchDev::Outbox) == 32, "outbox ring == XCHG_EPOCHS");
+static_assert(sizeof(MatchDev::outbox) / sizeof(MatchDev::Outbox) == 64, "outbox ring == XCHG_EPOCHS");
 constexpr int MATCH_SMALL = 64;
 
 // Peer-memory exchange of per-rank match results (multi-GPU): every context owns one
@@ -67,14 +67,14 @@ constexpr int MATCH_SMALL = 64;
 // words of that epoch have landed in its own buffer, and merges.  The four 32-bit payload
 // words travel as 8-byte stores {data, epoch} (each store is atomic and carries its own
 // validity flag, like NCCL's LL protocol), so no fence and no separate flag are needed.
-// 32 epochs of slots.  With a merge in every kernel tail a rank runs at most two posts ahead of
+// 64 epochs of slots.  With a merge in every kernel tail a rank runs at most two posts ahead of
 // the slowest reader; with post-only bursts (allreduce = 3) a rank posts a burst only after its
 // blocking collect of the previous burst, which needed every peer's posts of that burst, which
 // the peers issued after collecting the burst before -- so slots at distance >= two bursts
-// (2 x XCHG_MAX_POSTED <= 32) have been consumed everywhere.
+// (2 x XCHG_MAX_POSTED <= 64) have been consumed everywhere.
 constexpr int XCHG_MAX_RANKS = 64;
-constexpr int XCHG_EPOCHS = 32;
-constexpr int XCHG_MAX_POSTED = 15;   // posts a rank may issue between two blocking collects (two bursts fit the ring)
+constexpr int XCHG_EPOCHS = 64;
+constexpr int XCHG_MAX_POSTED = 31;   // posts a rank may issue between two blocking collects (two bursts fit the ring)
 struct XchgSlot {
     unsigned long long w[4];          // {key lo, key hi, best_hits, last_hits}, each | (epoch << 32)
 };

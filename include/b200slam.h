@@ -166,7 +166,7 @@ int b200slam_score_lattice_rows(b200slam_ctx *ctx, b200slam_map *map, const floa
  * 3 = DEFERRED: the kernel only records this rank's result on its own GPU, so a burst of
  * independent matches runs at single-GPU speed (no kernel has NVLink stores in flight when it
  * completes, nothing waits for a peer); b200slam_exchange_collect_async must follow after at
- * most 15 such calls: it sends the whole burst to the peers, merges every rank's results in
+ * most 31 such calls: it sends the whole burst to the peers, merges every rank's results in
  * order, and the result of the LAST match is what b200slam_match_fetch returns.  Without NVLink
  * peer memory (NCCL fallback) 2 and 3 act like 1. */
 int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const float pose0[3],
