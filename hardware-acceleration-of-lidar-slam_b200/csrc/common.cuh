@@ -278,6 +278,39 @@ __device__ __forceinline__ void pdl_wait_prior_grids()
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Packed f32x2 arithmetic (sm_100: FMUL2 / FADD2 process two independent IEEE fp32 operations per
+// instruction).  Each half is rounded exactly like the scalar op (no contraction), so using them
+// changes the instruction count, never a bit of the result.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_mul_rn(f32x2_t a, f32x2_t b)
+{
+    f32x2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2_t f2_add_rn(f32x2_t a, f32x2_t b)
+{
+    f32x2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2_t f2_add_rz(f32x2_t a, f32x2_t b)
+{
+    f32x2_t d;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // packed arg-min key helpers (scores are sums of non-negative floats, so the IEEE bit
 // pattern orders like the value and uint64 min == (lowest score, then lowest index))
 __host__ __device__ inline unsigned long long pack_key(float score, unsigned int index)

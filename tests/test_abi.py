@@ -74,3 +74,29 @@ def test_lattice_value_matches_reference_triplet(b200slam):
         want = [np.float32(p - s), p, np.float32(p + s)]
         got = [np.float32(b200slam.lattice_value(float(p), float(s), k, 3)) for k in range(3)]
         assert [w.tobytes() for w in want] == [g.tobytes() for g in got]
+
+
+def test_scoring_kernels_contain_no_fused_multiply_add(b200slam):
+    """Bit-exactness rests on every float product and sum being rounded separately (the reference is built
+    without contraction).  nvcc -fmad=false and __fmul_rn / __fadd_rn guarantee that for
+    scalar code, but ptxas was caught contracting mul.rn.f32x2 + add.rn.f32x2 into FFMA2 -- so the SASS of the
+    kernels that compute cell indices and scores is checked for any FFMA / FFMA2."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([cuobjdump, "-sass", b200slam.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    # (raster_scatter_kernel is not on the list: its IEEE division, __fdiv_rn, is itself built from FFMAs)
+    watched = ("lattice_kernel", "poses_kernel", "scan_read_kernel", "scan_transform_kernel", "local_map_kernel")
+    current, seen, bad = None, set(), []
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            current = next((w for w in watched if w in m.group(1)), None)
+            if current:
+                seen.add(current)
+            continue
+        if current and re.search(r"\bFFMA2?\b", line):
+            bad.append((current, line.strip()[:80]))
+    assert seen == set(watched), f"kernels not found in the SASS dump: {set(watched) - seen}"
+    assert not bad, f"fused multiply-add in a bit-exact kernel: {bad[:3]}"
