@@ -541,6 +541,8 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
 
 // ---- arbitrary pose list (particles): one thread per pose, beams sequential ---------
 struct PosesArgs {
+    const float *field11;     // &field[1][1]
+    int zero_off;             // -(pitch + 2)
     const float *field;
     int pitch, rows, cols;
     const float *scan_x, *scan_y;
@@ -576,6 +578,10 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
     float score = 0.0f;
     int nh = 0;
     const unsigned cols_m2 = (unsigned)(A.cols - 2), rows_m2 = (unsigned)(A.rows - 2);
+    const f32x2_t magic2 = f2_pack(8388608.0f, 8388608.0f);
+    const unsigned upitch = (unsigned)A.pitch;
+    const float *field11 = A.field11;                    // &field[1][1] (from the host: one uniform base pointer)
+    const int zero_off = A.zero_off;                     // field11 + zero_off == field[-1] == 0
     for (int c0 = 0; c0 < A.nbeams; c0 += POSES_CB) {
         const int cb = min(POSES_CB, A.nbeams - c0);
         constexpr int U = 8, NBUF = 3;
@@ -601,13 +607,17 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
                     f2_unpack(f2_mul_rn(f2_pack(q.x, q.x), rot_a), ax, ay);         // x ct | x (-st)
                     f2_unpack(f2_mul_rn(f2_pack(q.y, q.y), rot_b), bx, by);         // y st | y ct
                     const f32x2_t f = f2_add_rn(f2_pack(__fadd_rn(ax, bx), __fadd_rn(ay, by)), shift);
+                    // (int)roundf(v) (main.c:483, 501) = truncate(v + 0.5 toward zero) for every v that can pass
+                    // the range test; the truncation is a second toward-zero add of 2^23, which leaves the
+                    // integer in the mantissa (no F2I: that pipe runs at a quarter rate).  Negative, huge and
+                    // NaN inputs give bit patterns that fail the unsigned test below (dimensions < 2^22).
                     float hx, hy;
-                    f2_unpack(f2_add_rz(f, half2), hx, hy);                         // round_cell: + 0.5 toward zero ...
-                    const int c = __float2int_rz(hx);                               // main.c:483
-                    const int r = __float2int_rz(hy);                               // main.c:501
-                    const bool in = ((unsigned)(c - 1) < cols_m2) & ((unsigned)(r - 1) < rows_m2);   // main.c:512
-                    const int off = in ? r * A.pitch + c : -1;
-                    dst[u] = __ldg(A.field + off);
+                    f2_unpack(f2_add_rz(f2_add_rz(f, half2), magic2), hx, hy);
+                    const unsigned cm1 = __float_as_uint(hx) - 0x4B000001u;         // column index - 1 (1-based S - 2)
+                    const unsigned rm1 = __float_as_uint(hy) - 0x4B000001u;
+                    const bool in = (cm1 < cols_m2) & (rm1 < rows_m2);              // 1 < S < n, main.c:512
+                    const int off = in ? (int)(rm1 * upitch + cm1) : zero_off;      // relative to field[1][1]
+                    dst[u] = __ldg(field11 + off);
                     nh += in ? 1 : 0;
                 }
             };
@@ -809,6 +819,7 @@ int poses_launch(b200slam_ctx *ctx, const b200slam_map *m, int64_t P, int64_t in
 {
     PosesArgs A;
     A.field = m->d_field; A.pitch = m->field_pitch; A.rows = m->rows; A.cols = m->cols;
+    A.field11 = m->d_field + m->field_pitch + 1; A.zero_off = -(m->field_pitch + 2);
     A.scan_x = ctx->d_scan_x; A.scan_y = ctx->d_scan_y; A.nbeams = ctx->nbeams;
     A.ipixel = 1 / m->pixel_size;
     A.min_x = m->top_left_x; A.min_y = m->top_left_y;
@@ -822,6 +833,9 @@ int poses_launch(b200slam_ctx *ctx, const b200slam_map *m, int64_t P, int64_t in
         CUDA_TRY(ctx, cudaMemsetAsync(&ctx->d_match->best_hits, 0, 2 * sizeof(int), ctx->stream));
         return B200SLAM_OK;
     }
+    if (m->rows >= (1 << 22) || m->cols >= (1 << 22))
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "pose-list scoring needs map dimensions below 2^22 (%d x %d)",
+                                  m->rows, m->cols);
     const unsigned grid = (unsigned)((P + POSES_THREADS - 1) / POSES_THREADS);
     A.total_ctas = grid;
     poses_kernel<<<grid, POSES_THREADS, 0, ctx->stream>>>(A);
