@@ -32,6 +32,7 @@
 // for the next launch -- so a match is exactly ONE kernel: no memset, no table upload (the
 // lattice axis tables travel as kernel parameters), no separate reduction pass.
 #include <climits>
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -259,10 +260,10 @@ struct LatticeTables {
 // Gather pipeline shape: U beams per group, NBUF register buffers (NBUF - 1 groups in flight);
 // GUARD = table rows appended for padding (a multiple of NBUF*U) and for the prefetches that
 // run past the end.
-template <int TYPT, int UM = 1>
+template <int TYPT, int UM = 1, int Q = 0>
 struct LatticePipe {
     static constexpr int U = UM * (TYPT >= 16 ? 1 : 16 / TYPT);      // UM: deeper groups for low-occupancy shapes
-    static constexpr int NBUF = TYPT >= 16 ? 2 : 3;
+    static constexpr int NBUF = (TYPT >= 16 && Q == 0) ? 2 : 3;      // row reuse: TYPT / Q + 1 loads per beam, 3 buffers
     static constexpr int PAD = NBUF * U;
     static constexpr int GUARD = PAD - 1 + (NBUF - 1) * U;
 };
@@ -292,22 +293,34 @@ struct LatticeArgs {
 // TYPT candidates (consecutive ty) per thread, WX warps along tx, WY warps along ty.
 // Dynamic shared memory: colT[cb][TXT] | rowT[cb][TYT] | Sx[cb] | Sy[cb]
 // COUNT (FastMatch-sized lattices only): every thread also counts its candidate's in-bounds beams.
-template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false>
+// Q > 0: ROW REUSE.  When the ty step is pixel / Q, the TYPT consecutive ty candidates of a thread fall
+// into only K = TYPT / Q + 1 consecutive rows of the field: row(ty_j) = r0 + floor((j + p) / Q) for one
+// "phase" p in [0, Q) that depends on the beam (and the warp's ty group) alone.  The row table then holds
+// {r0 * pitch, p} per (beam, ty group) instead of TYPT offsets, a thread gathers its column from the K rows
+// once -- K loads instead of TYPT, same 1-2 lines each -- and the adds pick the value by compile-time index
+// inside a warp-uniform switch on p.  Everything is decided from the exact per-candidate row indices: a
+// (beam, ty group) whose rows do not follow the pattern (float fuzz at a rounding boundary, rows at the edge
+// of the grid) is flagged and takes the per-candidate path for that beam, so results stay bit-identical.
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0>
 __global__ void __launch_bounds__(32 * WX * WY)
 lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ LatticeTables T)
 {
     static_assert(!COUNT || TYPT == 1, "per-candidate hit counts: one candidate per thread");
+    static_assert(Q == 0 || (TYPT % Q == 0 && !COUNT), "row reuse: TYPT a multiple of Q");
+    constexpr int K = Q > 0 ? TYPT / Q + 1 : TYPT;       // values a thread gathers per beam
+    constexpr int RW = Q > 0 ? 2 * WY : TYPT * WY;       // row-table ints per beam ({r0 * pitch, phase} per ty group)
     constexpr int TXT = 32 * WX;
     constexpr int TYT = TYPT * WY;
     constexpr int NT = 32 * WX * WY;
-    using P = LatticePipe<TYPT, UM>;
+    using P = LatticePipe<TYPT, UM, Q>;
     constexpr int U = P::U, NBUF = P::NBUF, GUARD = P::GUARD;
     static_assert(NT % TXT == 0 && NT % TYT == 0, "tile shape");
     extern __shared__ __align__(16) int lat_smem[];
     int *colT = lat_smem;
     int *rowT = colT + (A.cb + GUARD) * TXT;             // chunk rows + padding/guard rows
-    float *Sx_s = reinterpret_cast<float *>(rowT + (A.cb + GUARD) * TYT);
+    float *Sx_s = reinterpret_cast<float *>(rowT + (A.cb + GUARD) * RW);
     float *Sy_s = Sx_s + A.cb;
+    float *syt_s = Sy_s + A.cb;                          // Q > 0: this tile's TYT ty offsets (per-candidate path)
     __shared__ unsigned long long red[WX * WY];
     __shared__ int tail_red[2 * (NT / 32)];
     __shared__ int last_flag;
@@ -366,7 +379,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                     colT[i * TXT + t] = v;
                 }
             }
-            {
+            if constexpr (Q == 0) {
                 const int t = tid % TYT;
                 const bool tok = ty0 + t < A.nty;
                 const float sy = tok ? sytT[ty0 + t] : 0.0f;
@@ -379,13 +392,90 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                     }
                     rowT[i * TYT + t] = v;
                 }
+            } else {
+                if (c0 == 0) {
+                    for (int t = tid; t < TYT; t += NT) syt_s[t] = ty0 + t < A.nty ? sytT[ty0 + t] : 0.0f;
+                    __syncthreads();
+                }
+                // one entry per (beam, ty group): exact rows of the group's TYPT candidates -> {r0 * pitch, phase},
+                // phase == Q: the rows do not follow r0 + floor((j + p) / Q) (or leave the grid): per-candidate path
+                for (int e = tid; e < cbg * WY; e += NT) {
+                    const int i = e / WY, g = e % WY;
+                    int off0 = INVALID_OFF, phase = 0;
+                    if (i < cb) {
+                        const float sy = Sy_s[i];
+                        int r[TYPT];
+#pragma unroll
+                        for (int j = 0; j < TYPT; ++j) r[j] = cell_index(__fadd_rn(sy, syt_s[g * TYPT + j]), A.rows);   // main.c:501
+                        const int nj = min(TYPT, A.nty - (ty0 + g * TYPT));      // candidates of this group inside the lattice
+                        phase = Q;
+                        if (nj > 0 && r[0] >= 0 && r[0] + K - 1 < A.rows) {
+#pragma unroll
+                            for (int p = 0; p < Q; ++p) {
+                                bool ok = true;
+#pragma unroll
+                                for (int j = 0; j < TYPT; ++j) ok = ok && (j >= nj || r[j] == r[0] + (j + p) / Q);
+                                if (ok && phase == Q) phase = p;
+                            }
+                            if (phase < Q) off0 = r[0] * A.pitch;
+                        }
+                        if (nj <= 0) phase = 0;              // nothing to score here: adds +0.0f to unused sums
+                    }
+                    rowT[e * 2] = off0;
+                    rowT[e * 2 + 1] = phase;
+                }
             }
             __syncthreads();
             // Software-pipelined gather: warps issue in order, so the loads of the next group
             // of U beams are put in flight before the (sequential, in-order) additions of
             // the current group.  Table rows [cb, cbp) are INVALID and add +0.0f.
             const int *cp = colT + txl;
-            const int *rp = rowT + tyl;
+            const int *rp = rowT + (Q > 0 ? 2 * wy : tyl);
+            [[maybe_unused]] int phase_q[NBUF][U];           // Q > 0: phase of every beam in flight
+            [[maybe_unused]] auto gather_rr = [&](int i0, float (&dst)[U][K], int (&ph)[U]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u;
+                    const int c = cp[i * TXT];
+                    const int2 ri = *reinterpret_cast<const int2 *>(rp + i * RW);      // {r0 * pitch, phase}, warp uniform
+                    int idx = __viaddmax_s32(c, ri.x, -1);                           // column or row invalid: field[-1] == 0
+                    const int step = idx >= 0 ? A.pitch : 0;
+                    ph[u] = ri.y;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        dst[u][k] = ldg_ordered(A.field + idx);
+                        idx += step;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < TYPT; ++j) asm volatile("" : "+f"(acc[j]));
+            };
+            // adds of one beam: value k = (j + phase) / Q of the K gathered rows, beams in scan order (main.c:516)
+            [[maybe_unused]] auto accumulate_rr = [&](const float (&src)[U][K], const int (&ph)[U], int i0) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    bool done = false;
+#pragma unroll
+                    for (int p = 0; p < Q; ++p) {
+                        if (ph[u] == p) {                    // warp uniform
+#pragma unroll
+                            for (int j = 0; j < TYPT; ++j) acc[j] = __fadd_rn(acc[j], src[u][(j + p) / (Q > 0 ? Q : 1)]);
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        // per-candidate path for this beam (rows off the pattern or at the grid's edge)
+                        const int c = cp[(i0 + u) * TXT];
+                        const float sy = Sy_s[i0 + u];
+#pragma unroll
+                        for (int j = 0; j < TYPT; ++j) {
+                            const int r = cell_index(__fadd_rn(sy, syt_s[tyl + j]), A.rows);           // main.c:501
+                            const int off = (c >= 0 && r >= 0 && ty0 + tyl + j < A.nty) ? r * A.pitch + c : -1;
+                            acc[j] = __fadd_rn(acc[j], __ldg(A.field + off));
+                        }
+                    }
+                }
+            };
             auto gather = [&](int i0, float (&dst)[U][TYPT]) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -422,7 +512,18 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
 #pragma unroll
                     for (int j = 0; j < TYPT; ++j) acc[j] = __fadd_rn(acc[j], src[u][j]);      // main.c:516
             };
-            {
+            if constexpr (Q > 0) {
+                float v[NBUF][U][K];
+#pragma unroll
+                for (int b = 0; b < NBUF - 1; ++b) gather_rr(b * U, v[b], phase_q[b]);
+                for (int i0 = 0; i0 < cbp; i0 += NBUF * U) {
+#pragma unroll
+                    for (int b = 0; b < NBUF; ++b) {
+                        gather_rr(i0 + (b + NBUF - 1) * U, v[(b + NBUF - 1) % NBUF], phase_q[(b + NBUF - 1) % NBUF]);
+                        accumulate_rr(v[b], phase_q[b], i0 + b * U);
+                    }
+                }
+            } else {
                 // NBUF rotating register buffers: group g+NBUF-1 is requested before group g is added
                 float v[NBUF][U][TYPT];
 #pragma unroll
@@ -667,15 +768,15 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
     }
 }
 
-template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false>
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0>
 int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T, int nth_cover)
 {
     constexpr int TXT = 32 * WX, TYT = TYPT * WY;
-    auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT>;
+    auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT, Q>;
     // Beams per chunk: the whole scan when its tables fit the budget, else even chunks.
-    constexpr int GUARD = LatticePipe<TYPT, UM>::GUARD;
-    const int per_beam = (TXT + TYT + 2) * 4;
-    const int budget = TYPT >= 16 ? 56 * 1024 : 100 * 1024;
+    constexpr int GUARD = LatticePipe<TYPT, UM, Q>::GUARD;
+    const int per_beam = (TXT + (Q > 0 ? 2 * WY : TYT) + 2) * 4;
+    const int budget = (TYPT >= 16 ? 56 * 1024 : 100 * 1024) - (Q > 0 ? TYT * 4 : 0);
     int cb = A.nbeams > 0 ? A.nbeams : 1;
     const int cap = budget / per_beam - GUARD;
     if (cb > cap) {
@@ -684,7 +785,7 @@ int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T
     }
     cb = (cb + 3) & ~3;                                   // keeps the int4 row loads aligned
     A.cb = cb;
-    const size_t smem = (size_t)(cb + GUARD) * per_beam;
+    const size_t smem = (size_t)(cb + GUARD) * per_beam + (Q > 0 ? TYT * 4 : 0);
     // Opt in to large dynamic shared memory once per instantiation and device -- unconditionally: the
     // 48 KB default applies to static + dynamic together, so a chunk just under 48 KB needs it too.
     static bool smem_set[64] = {};
@@ -769,17 +870,32 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     if (!getenv("B200SLAM_LATTICE_CFG") && (long long)L.nth * L.ntx * L.nty <= MATCH_SMALL && L.row_begin == 0 &&
         L.row_end == (int64_t)L.nth * L.ntx && !A.xchg.peers && L.nth_tab == L.nth)
         return launch_lattice_cfg<1, 1, 4, 1, true>(ctx, A, T, nth_cover);
-    struct Shape { int typt, wx, wy, um; double per_eval; };
+    // Row reuse (template parameter Q): usable when the ty step is pixel / Q, measured on the ty axis table
+    // itself (host copy).  The kernel verifies every (beam, ty group) exactly, so a wrong guess here only
+    // costs time, never a bit of the result.
+    int q_ok = 0;
+    if (!getenv("B200SLAM_LATTICE_NO_RR") && L.nty >= 4 && L.h_tables) {
+        const float *syt = L.h_tables + 2 * (size_t)L.nth_tab + L.ntx;
+        const double d = ((double)syt[L.nty - 1] - (double)syt[0]) / (L.nty - 1);
+        for (int q : {2, 4})
+            if (d > 0 && fabs(d * q - 1.0) < 1e-3) q_ok = q;
+    }
+    struct Shape { int typt, wx, wy, um, q; double per_eval; };
     static const Shape shapes[] = {
-        {16, 2, 4, 1, 1.00}, {8, 1, 8, 1, 1.05}, {4, 1, 8, 1, 1.13}, {2, 1, 8, 2, 1.40}, {1, 1, 8, 1, 1.95}, {1, 1, 4, 1, 1.95},
+        {16, 2, 4, 1, 0, 1.00}, {8, 1, 8, 1, 0, 1.05}, {4, 1, 8, 1, 0, 1.13}, {2, 1, 8, 2, 0, 1.40}, {1, 1, 8, 1, 0, 1.95},
+        {1, 1, 4, 1, 0, 1.95},
+        // row reuse: K = TYPT / Q + 1 gathers per TYPT candidates
+        {16, 2, 4, 1, 2, 0.60}, {8, 1, 8, 1, 2, 0.70}, {4, 1, 8, 1, 2, 0.92},
+        {16, 2, 4, 1, 4, 0.55}, {8, 1, 8, 1, 4, 0.60}, {4, 1, 8, 1, 4, 0.72},
     };
-    int pick_t = 0, pick_x = 0, pick_y = 0, pick_m = 1;
-    if (const char *e = getenv("B200SLAM_LATTICE_CFG"))                   // tuning / test aid: "TYPT,WX,WY[,UM]"
-        if (sscanf(e, "%d,%d,%d,%d", &pick_t, &pick_x, &pick_y, &pick_m) < 3) pick_t = 0;
+    int pick_t = 0, pick_x = 0, pick_y = 0, pick_m = 1, pick_q = 0;
+    if (const char *e = getenv("B200SLAM_LATTICE_CFG"))                   // tuning / test aid: "TYPT,WX,WY[,UM[,Q]]"
+        if (sscanf(e, "%d,%d,%d,%d,%d", &pick_t, &pick_x, &pick_y, &pick_m, &pick_q) < 3) pick_t = 0;
     if (!pick_t) {
         const double covered = (double)(L.row_end - L.row_begin) / ((double)nth_cover * L.ntx);   // row shards: part of the grid
         double best_cost = 1e300;
         for (const Shape &sh : shapes) {
+            if (sh.q != 0 && sh.q != q_ok) continue;
             const int txt = 32 * sh.wx, tyt = sh.typt * sh.wy;
             double ctas = (double)nth_cover * ((L.ntx + txt - 1) / txt) * ((L.nty + tyt - 1) / tyt) * covered;
             if (ctas < 1.0) ctas = 1.0;
@@ -788,19 +904,22 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
             const double cost = units * txt * tyt * sh.per_eval;
             if (cost < best_cost * 0.999) {                                // ties: the bigger register tile
                 best_cost = cost;
-                pick_t = sh.typt; pick_x = sh.wx; pick_y = sh.wy; pick_m = sh.um;
+                pick_t = sh.typt; pick_x = sh.wx; pick_y = sh.wy; pick_m = sh.um; pick_q = sh.q;
             }
         }
     }
-#define B200SLAM_CFG(T_, X_, Y_, M_) \
-    if (pick_t == T_ && pick_x == X_ && pick_y == Y_ && pick_m == M_) return launch_lattice_cfg<T_, X_, Y_, M_>(ctx, A, T, nth_cover);
-    B200SLAM_CFG(16, 2, 4, 1)        // 64 x 64 tile, 256 threads
-    B200SLAM_CFG(8, 1, 8, 1)         // 32 x 64
-    B200SLAM_CFG(4, 1, 8, 1)         // 32 x 32
-    B200SLAM_CFG(2, 1, 8, 2)         // 32 x 16, groups of 16 beams
-    B200SLAM_CFG(2, 1, 8, 1)
-    B200SLAM_CFG(1, 1, 8, 1)         // 32 x 8
-    B200SLAM_CFG(1, 1, 4, 1)         // 32 x 4, 128 threads
+#define B200SLAM_CFG(T_, X_, Y_, M_, Q_) \
+    if (pick_t == T_ && pick_x == X_ && pick_y == Y_ && pick_m == M_ && pick_q == Q_) \
+        return launch_lattice_cfg<T_, X_, Y_, M_, false, Q_>(ctx, A, T, nth_cover);
+    B200SLAM_CFG(16, 2, 4, 1, 0)        // 64 x 64 tile, 256 threads
+    B200SLAM_CFG(8, 1, 8, 1, 0)         // 32 x 64
+    B200SLAM_CFG(4, 1, 8, 1, 0)         // 32 x 32
+    B200SLAM_CFG(2, 1, 8, 2, 0)         // 32 x 16, groups of 16 beams
+    B200SLAM_CFG(2, 1, 8, 1, 0)
+    B200SLAM_CFG(1, 1, 8, 1, 0)         // 32 x 8
+    B200SLAM_CFG(1, 1, 4, 1, 0)         // 32 x 4, 128 threads
+    B200SLAM_CFG(16, 2, 4, 1, 2) B200SLAM_CFG(8, 1, 8, 1, 2) B200SLAM_CFG(4, 1, 8, 1, 2)      // row reuse, step = pixel / 2
+    B200SLAM_CFG(16, 2, 4, 1, 4) B200SLAM_CFG(8, 1, 8, 1, 4) B200SLAM_CFG(4, 1, 8, 1, 4)      // row reuse, step = pixel / 4
 #undef B200SLAM_CFG
     return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "B200SLAM_LATTICE_CFG names no compiled tile shape");
 }

@@ -65,7 +65,11 @@ def test_lattice_matches_oracle_shapes(ctx, oracle, synth, n):
         m.close()
 
 
-@pytest.mark.parametrize("cfg", ["16,2,4", "8,1,8", "4,1,8", "2,1,8,2", "2,1,8", "1,1,8", "1,1,4"])
+@pytest.mark.parametrize("cfg", ["16,2,4", "8,1,8", "4,1,8", "2,1,8,2", "2,1,8", "1,1,8", "1,1,4",
+                                 # row reuse (5th field Q: ty step = pixel / Q).  The tiny workload steps by half a pixel:
+                                 # Q = 2 takes the fast path except at the grid's edge, Q = 4 never matches the pattern, so
+                                 # every beam goes down the per-candidate path -- both must be bit-exact
+                                 "16,2,4,1,2", "8,1,8,1,2", "4,1,8,1,2", "16,2,4,1,4", "8,1,8,1,4", "4,1,8,1,4"])
 def test_lattice_every_compiled_tile_shape(ctx, oracle, synth, monkeypatch, cfg):
     # the launcher picks a tile shape from a cost model; here every compiled shape is forced
     # in turn (B200SLAM_LATTICE_CFG is read at each launch) on lattices that leave partial tiles
@@ -75,6 +79,8 @@ def test_lattice_every_compiled_tile_shape(ctx, oracle, synth, monkeypatch, cfg)
         monkeypatch.setenv("B200SLAM_LATTICE_CFG", cfg)
         for n in [(3, 3, 3), (2, 33, 17), (3, 70, 67)]:
             _check_lattice(ctx, oracle, m, om, w, n)
+        # quarter-pixel ty steps (the reference's own ratio: 0.05 m on a 0.2 m grid, main.c:832-835)
+        _check_lattice(ctx, oracle, m, om, w, (2, 40, 70), step=np.array([0.05, 0.025, 0.008727], np.float32))
         monkeypatch.setenv("B200SLAM_LATTICE_CFG", "3,1,8")
         with pytest.raises(Exception):
             ctx.score_lattice(m, w["pose0"], w["step"], (3, 3, 3))

@@ -214,6 +214,14 @@ def main():
             bench_edt(mod, synth, ctx, [(8192, 8192)])
         if "lattice" in what:
             bench_lattice(mod, synth, ctx, ["tiny", "config1", "config3"])
+        if "latbig" in what:
+            for q in ("1", ""):
+                if q:
+                    os.environ["B200SLAM_LATTICE_NO_RR"] = q
+                else:
+                    os.environ.pop("B200SLAM_LATTICE_NO_RR", None)
+                print("row reuse", "off" if q else "on", flush=True)
+                bench_lattice(mod, synth, ctx, ["config1", "config3"])
         if "pipe" in what:
             bench_pipeline_ab(mod, synth, ctx)
         if "latsweep" in what:
