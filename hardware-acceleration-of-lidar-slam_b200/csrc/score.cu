@@ -302,7 +302,7 @@ struct LatticeArgs {
 // (beam, ty group) whose rows do not follow the pattern (float fuzz at a rounding boundary, rows at the edge
 // of the grid) is flagged and takes the per-candidate path for that beam, so results stay bit-identical.
 template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0>
-__global__ void __launch_bounds__(32 * WX * WY)
+__global__ void __launch_bounds__(32 * WX * WY, (Q > 0 && TYPT >= 16) ? 3 : 1)
 lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ LatticeTables T)
 {
     static_assert(!COUNT || TYPT == 1, "per-candidate hit counts: one candidate per thread");
@@ -438,14 +438,12 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                     const int i = i0 + u;
                     const int c = cp[i * TXT];
                     const int2 ri = *reinterpret_cast<const int2 *>(rp + i * RW);      // {r0 * pitch, phase}, warp uniform
-                    int idx = __viaddmax_s32(c, ri.x, -1);                           // column or row invalid: field[-1] == 0
+                    const int idx = __viaddmax_s32(c, ri.x, -1);                     // column or row invalid: field[-1] == 0
                     const int step = idx >= 0 ? A.pitch : 0;
                     ph[u] = ri.y;
+                    const float *p0 = A.field + idx;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        dst[u][k] = ldg_ordered(A.field + idx);
-                        idx += step;
-                    }
+                    for (int k = 0; k < K; ++k) dst[u][k] = ldg_ordered(p0 + (long)k * step);   // K independent addresses
                 }
 #pragma unroll
                 for (int j = 0; j < TYPT; ++j) asm volatile("" : "+f"(acc[j]));
@@ -454,16 +452,17 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
             [[maybe_unused]] auto accumulate_rr = [&](const float (&src)[U][K], const int (&ph)[U], int i0) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    bool done = false;
+                    constexpr int QQ = Q > 0 ? Q : 1;
+                    if (ph[u] < QQ) {                        // warp uniform; almost always
+                        // candidate j reads row floor((j + p) / Q) = j / Q, or one further iff j % Q + p >= Q:
+                        // one select per candidate that is not first in its row group, no branch on p
 #pragma unroll
-                    for (int p = 0; p < Q; ++p) {
-                        if (ph[u] == p) {                    // warp uniform
-#pragma unroll
-                            for (int j = 0; j < TYPT; ++j) acc[j] = __fadd_rn(acc[j], src[u][(j + p) / (Q > 0 ? Q : 1)]);
-                            done = true;
+                        for (int j = 0; j < TYPT; ++j) {
+                            const float lo = src[u][j / QQ];
+                            const float v = (j % QQ == 0) ? lo : (ph[u] >= QQ - j % QQ ? src[u][j / QQ + 1] : lo);
+                            acc[j] = __fadd_rn(acc[j], v);
                         }
-                    }
-                    if (!done) {
+                    } else {
                         // per-candidate path for this beam (rows off the pattern or at the grid's edge)
                         const int c = cp[(i0 + u) * TXT];
                         const float sy = Sy_s[i0 + u];
@@ -884,9 +883,12 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     static const Shape shapes[] = {
         {16, 2, 4, 1, 0, 1.00}, {8, 1, 8, 1, 0, 1.05}, {4, 1, 8, 1, 0, 1.13}, {2, 1, 8, 2, 0, 1.40}, {1, 1, 8, 1, 0, 1.95},
         {1, 1, 4, 1, 0, 1.95},
-        // row reuse: K = TYPT / Q + 1 gathers per TYPT candidates
-        {16, 2, 4, 1, 2, 0.60}, {8, 1, 8, 1, 2, 0.70}, {4, 1, 8, 1, 2, 0.92},
-        {16, 2, 4, 1, 4, 0.55}, {8, 1, 8, 1, 4, 0.60}, {4, 1, 8, 1, 4, 0.72},
+        // row reuse: K = TYPT / Q + 1 gathers per TYPT candidates.  Measured on config 3 (256 x 128 x 128 x 1080,
+        // step = pixel / 2): 64 x 64 tiles 775 us against 1059 us without reuse, 32 x 64 tiles 1033 us; with 4
+        // candidates per thread the per-beam bookkeeping outweighs the saved gathers (1503 us), so those
+        // shapes are compiled (and tested) but never chosen.  The Q = 4 factors are estimates.
+        {16, 2, 4, 1, 2, 0.73}, {8, 1, 8, 1, 2, 0.98},
+        {16, 2, 4, 1, 4, 0.62}, {8, 1, 8, 1, 4, 0.85},
     };
     int pick_t = 0, pick_x = 0, pick_y = 0, pick_m = 1, pick_q = 0;
     if (const char *e = getenv("B200SLAM_LATTICE_CFG"))                   // tuning / test aid: "TYPT,WX,WY[,UM[,Q]]"

@@ -214,6 +214,12 @@ def main():
             bench_edt(mod, synth, ctx, [(8192, 8192)])
         if "lattice" in what:
             bench_lattice(mod, synth, ctx, ["tiny", "config1", "config3"])
+        if "latcfg" in what:                 # config 3 under each B200SLAM_LATTICE_CFG in $SWEEP
+            for cfg in os.environ.get("SWEEP", "16,2,4,1,2 8,1,8,1,2 4,1,8,1,2 16,2,4").split():
+                os.environ["B200SLAM_LATTICE_CFG"] = cfg
+                print("cfg", cfg, flush=True)
+                bench_lattice(mod, synth, ctx, ["config3"])
+            os.environ.pop("B200SLAM_LATTICE_CFG", None)
         if "latbig" in what:
             for q in ("1", ""):
                 if q:
