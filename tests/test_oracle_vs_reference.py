@@ -152,3 +152,65 @@ def test_fastmatch_oracle_vs_compiled_reference(oracle, synth, which):
         m, _, _ = oracle.score_lattice(om, sx, sy, pose, [res[0], res[0], res[2]], [3, 3, 3])
         assert np.array_equal(bits(p1), bits(p2)) and n1 == n2
         assert np.array_equal(bits(h1[:m.last_hits]), bits(h2[:m.last_hits]))
+
+
+@pytest.mark.parametrize("which", ["accel", "main"])
+def test_besthits_global_is_left_exactly_as_the_reference_leaves_it(oracle, synth, which):
+    """FastMatchParameters.bestHits is a global that EVERY candidate overwrites from index 0 (main.c:515) and
+    nothing ever clears; main() reads it up to the WINNER's count (main.c:942-948), i.e. possibly past the last
+    candidate's hits.  The oracle (and the CUDA path, tests/test_score_gpu.py) must leave the whole array as the
+    reference does -- checked here over a sequence of calls against the compiled reference's own global,
+    with poses walking off the grid so that the 27 candidates' hit counts differ."""
+    from oracle import pyoracle
+    if not pyoracle.reference_available():
+        pytest.skip("oracle/_ref not built")
+    ref = pyoracle.Reference(which)
+    rows, cols = 150, 190
+    pixel, tl = synth.centred_geometry(rows, cols, 0.2)
+    # two vertical walls, one of them two cells from the right edge, and a scan that lies exactly on them
+    # when seen from `true`: the aligned candidate scores 0 with every beam in bounds and wins, while the
+    # last candidate (+t in x and y, main.c:422-438) pushes the outer wall's beams off the grid -- so the
+    # winner has MORE hits than the last candidate and main.c:942-948 reads the array's tail
+    occ = np.zeros((rows, cols), np.int32)
+    wall_rows = np.arange(20, 131)
+    occ[wall_rows, cols - 3] = 1
+    occ[wall_rows, 60] = 1
+    true = np.array([1.0, -0.6, 0.0], np.float32)
+    wx = np.concatenate([np.full(len(wall_rows), float(tl[0]) + (cols - 3) * 0.2), np.full(len(wall_rows), float(tl[0]) + 60 * 0.2)])
+    wy = np.concatenate([float(tl[1]) + wall_rows * 0.2] * 2)
+    sx, sy = (wx - true[0]).astype(np.float32), (wy - true[1]).astype(np.float32)
+    field = ref.edt(occ, fine=False)
+    ref.set_map(field, float(pixel), tl, fine=False)
+    ref.set_scan(sx, sy)
+    om = oracle.make_map(field, float(pixel), tl)
+    obuf = np.zeros(2500, np.float32)
+    res = np.array([0.3, 0.3, 0.05], np.float32)
+    saw_tail = False
+    for k in range(7):
+        pose = np.array([true[0] + 0.37 * (k % 3) - 0.2 * (k // 3), true[1] + 0.29 * (k // 2), 0.013 * k], np.float32)
+        rp, rhits, rn = ref.fastmatch(pose, res, fine=False)          # rhits: the reference's whole global array
+        op, _, on = oracle.fastmatch(om, sx, sy, pose, res, hits_buf=obuf)
+        assert np.array_equal(bits(rp), bits(op)) and rn == on
+        assert np.array_equal(bits(rhits), bits(obuf)), f"call {k}: bestHits differs at {np.flatnonzero(rhits != obuf)[:5]}"
+        lat, _, _ = oracle.score_lattice(om, sx, sy, pose, [res[0], res[0], res[2]], (3, 3, 3))
+        saw_tail |= lat.best_hits > lat.last_hits
+    assert saw_tail, "the sequence never had a winner with more hits than the last candidate"
+
+
+def test_clamped_edt_of_a_row_block_needs_only_a_nine_row_halo(oracle, synth):
+    """The claim behind the row-sharded transform: with max_dist = 10 a
+    block of output rows depends on the occupancy of those rows plus 9 above and below, nothing else."""
+    rows, cols = 300, 170
+    occ = synth.grid_bernoulli(rows, cols, 0.004, seed=0x5A4D)
+    full = oracle.edt(occ)
+    for rb, re in [(0, 97), (97, 98), (98, 211), (211, 300)]:
+        lo, hi = max(0, rb - 9), min(rows, re + 9)
+        part = oracle.edt(np.ascontiguousarray(occ[lo:hi]))
+        assert np.array_equal(bits(part[rb - lo:re - lo]), bits(full[rb:re]))
+        if rb >= 9 and re + 9 <= rows:                 # ... and 8 rows would not do
+            lo8, hi8 = rb - 8, re + 8
+            part8 = oracle.edt(np.ascontiguousarray(occ[lo8:hi8]))
+            if not np.array_equal(bits(part8[rb - lo8:re - lo8]), bits(full[rb:re])):
+                break
+    else:
+        pytest.skip("no block in this grid was sensitive to the 9th halo row")
