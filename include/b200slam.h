@@ -186,7 +186,14 @@ int b200slam_score_poses(b200slam_ctx *ctx, b200slam_map *map, const float *pose
 /* The reference call itself: 3x3x3 lattice around `pose` with t = search_resolution[0],
  * r = search_resolution[2]; pose_out / best_hits / best_hits_size are exactly what
  * FastMatch leaves in FastMatchParameters (main.c:374-379): the winner's pose, the winner's
- * hit count, and the LAST candidate's hit values. */
+ * hit count, and bestHits[] as the reference's loop leaves it.  Every candidate overwrites
+ * that array from index 0 in loop order (main.c:515) and nothing ever clears it, so pass the
+ * SAME best_hits array (at least as long as the scan, e.g. the reference's own
+ * FastMatchParameters.bestHits[2500]) to every call: the call rewrites the last candidate's
+ * hit values, behind them those of the most recent candidate that had more, and leaves the rest
+ * as earlier calls left it -- which is what main.c:942-948 reads when the winner has more hits
+ * than the last candidate.  (The device keeps its own copy of the array across calls;
+ * b200slam_mappoints_grow reads that one.)  best_hits / best_hits_size may be NULL. */
 int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3],
                        const float search_resolution[3], float pose_out[3], float *best_hits,
                        int *best_hits_size);
