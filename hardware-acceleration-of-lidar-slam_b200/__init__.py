@@ -100,6 +100,7 @@ def load_library() -> C.CDLL:
         "b200slam_score_lattice_async": (i, [vp, vp, c_float_p, c_float_p, c_int_p, C.c_int64, C.c_int64, i]),
         "b200slam_exchange_collect_async": (i, [vp]),
         "b200slam_match_fetch": (i, [vp, C.POINTER(Match)]),
+        "b200slam_match_fetch_hits": (i, [vp, vp, i]),
         "b200slam_score_poses": (i, [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.POINTER(Match)]),
         "b200slam_fastmatch": (i, [vp, vp, c_float_p, c_float_p, c_float_p, vp, c_int_p]),
         "b200slam_set_match_mode": (i, [vp, i]),
@@ -135,6 +136,7 @@ def load_library() -> C.CDLL:
         "b200slam_comm_unique_id": (i, [vp]),
         "b200slam_comm_init": (i, [vp, i, i, vp]),
         "b200slam_comm_destroy": (i, [vp]),
+        "b200slam_comm_barrier_async": (i, [vp]),
         "b200slam_shard_range": (None, [C.c_int64, i, i, c_i64_p, c_i64_p]),
         "b200slam_pack_key": (C.c_uint64, [f, C.c_uint32]),
         "b200slam_unpack_key": (None, [C.c_uint64, c_float_p, C.POINTER(C.c_uint32)]),
@@ -329,6 +331,10 @@ class Context:
 
     def close(self):
         if self.h:
+            self.L.b200slam_sync(self.h)
+            for p in self._pinned:                 # arrays handed out by pinned_empty die with the context
+                self.L.b200slam_host_free(self.h, p)
+            self._pinned = []
             self.L.b200slam_destroy(self.h)
             self.h = None
 
@@ -484,6 +490,11 @@ class Context:
         self._check(self.L.b200slam_match_fetch(self.h, C.byref(res)))
         return res
 
+    def match_fetch_hits(self, count: int = 2500) -> np.ndarray:
+        out = np.zeros(count, np.float32)
+        self._check(self.L.b200slam_match_fetch_hits(self.h, out.ctypes.data, count))
+        return out
+
     def score_poses(self, m: Map, poses, ct=None, st=None, index_base=0, want_hits=True):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 3)
         P = poses.shape[0]
@@ -590,6 +601,9 @@ class Context:
         if rc != OK:
             raise B200SlamError(rc, (self.L.b200slam_last_error(None) or b"").decode())
         return buf.raw
+
+    def comm_barrier_async(self):
+        self._check(self.L.b200slam_comm_barrier_async(self.h))
 
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         assert len(uid) == UNIQUE_ID_BYTES

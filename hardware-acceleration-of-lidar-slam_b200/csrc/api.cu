@@ -22,6 +22,18 @@ int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...)
     return code;
 }
 
+int device_error_check(b200slam_ctx *ctx, unsigned int bits)
+{
+    if (!bits) return B200SLAM_OK;
+    return b200slam_set_error(ctx, B200SLAM_ERR_STATE,
+                              "a bounded device-side wait gave up after %.0f ms:%s%s%s%s (sticky until b200slam_comm_init)",
+                              ctx->spin_timeout_ns * 1e-6,
+                              bits & DEV_ERR_EXCHANGE ? " a peer's match result never arrived;" : "",
+                              bits & DEV_ERR_BARRIER ? " a peer never reached a device barrier;" : "",
+                              bits & DEV_ERR_TMA ? " a TMA load of the EDT never completed;" : "",
+                              bits & DEV_ERR_PARTICLES ? " a peer's particle sums / offspring never arrived;" : "");
+}
+
 extern "C" {
 
 int b200slam_abi_version(void) { return B200SLAM_ABI_VERSION; }
@@ -44,6 +56,8 @@ int b200slam_create(b200slam_ctx **out, int device)
     if (!ctx) return B200SLAM_ERR_NOMEM;
     ctx->device = device;
     ctx->use_pdl = getenv("B200SLAM_NO_PDL") == nullptr;
+    if (const char *e = getenv("B200SLAM_SPIN_TIMEOUT_MS"))
+        if (atof(e) > 0) ctx->spin_timeout_ns = (unsigned long long)(atof(e) * 1e6);
 #define CREATE_TRY(expr)                                                                      \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
@@ -62,7 +76,8 @@ int b200slam_create(b200slam_ctx **out, int device)
     {
         MatchDev init;
         init.work_key = ~0ull; init.tickets = 0; init.epoch = 0; init.key = ~0ull;
-        init.best_hits = 0; init.last_hits = 0; init.collected = 0; init.pad = 0; init.gkey = ~0ull; init.gbest_hits = 0; init.glast_hits = 0;
+        init.best_hits = 0; init.last_hits = 0; init.collected = 0; init.error = 0; init.written_hits = 0; init.posted = 0;
+        memset(init.cand_hits, 0, sizeof init.cand_hits); memset(init.outbox, 0, sizeof init.outbox); init.gkey = ~0ull; init.gbest_hits = 0; init.glast_hits = 0;
         CREATE_TRY(cudaMemcpy(ctx->d_match, &init, sizeof init, cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaMalloc(&ctx->d_keys, sizeof(unsigned long long) * 256));
@@ -104,8 +119,11 @@ void b200slam_destroy(b200slam_ctx *ctx)
 int b200slam_sync(b200slam_ctx *ctx)
 {
     if (!ctx) return B200SLAM_ERR_ARG;
+    // the sticky device-side error word rides along: a bounded wait that gave up is reported here
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_match->error, &ctx->d_match->error, sizeof(unsigned int),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return B200SLAM_OK;
+    return device_error_check(ctx, ctx->h_match->error);
 }
 
 void *b200slam_stream(b200slam_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -449,10 +467,11 @@ int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[
     const size_t need = (size_t)2 * nth + ntx + nty;
     const bool capturing = is_capturing(ctx);
     const bool by_param = need <= LATTICE_PARAM_FLOATS;
-    if (need > ctx->lat_cap) {
-        if (capturing && !by_param)
+    static_assert(sizeof(ctx->h_param_tab) / sizeof(float) >= LATTICE_PARAM_FLOATS, "parameter-table scratch");
+    if (!by_param && need > ctx->lat_cap) {
+        if (capturing)
             return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "lattice larger than warmed-up scratch during graph capture");
-        if (!capturing) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
         ctx->h_lat = ctx->d_lat = nullptr;
         ctx->lat_cap = 0;
@@ -472,7 +491,11 @@ int stage_lattice(b200slam_ctx *ctx, const b200slam_map *map, const float pose0[
         if (!capturing) CUDA_TRY(ctx, cudaEventSynchronize(ctx->lat_event[slot]));
     }
     const float ipixel = 1 / map->pixel_size;                             // main.c:383
-    float *ct = ctx->h_lat + (size_t)slot * ctx->lat_cap, *st = ct + nth, *sxt = st + nth, *syt = sxt + ntx;
+    // By-parameter tables are copied into the launch at cudaLaunchKernelEx time, so plain host scratch will
+    // do; the pinned ring slots are only ever written here after waiting for the event behind the DMA that
+    // reads them (a small lattice queued behind a large one must not touch slot 0).
+    float *ct = by_param ? ctx->h_param_tab : ctx->h_lat + (size_t)slot * ctx->lat_cap, *st = ct + nth, *sxt = st + nth,
+          *syt = sxt + ntx;
     for (int i = 0; i < nth; ++i) {
         const float th = b200slam_lattice_value(pose0[2], step[2], th_first + i, nth_all);   // main.c:424
         ct[i] = cosf(th);                                                 // main.c:434
@@ -588,6 +611,7 @@ int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result)
     if (!ctx || !result) return B200SLAM_ERR_ARG;
     if (!ctx->last.valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no match queued");
     MatchDev m;
+    m.error = 0;
     if (ctx->last.gathered) {
         // merge the all-gathered per-rank results: lowest key wins; the last candidate of the
         // whole lattice belongs to the last rank that scored anything
@@ -611,6 +635,7 @@ int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result)
         }
     }
     memset(result, 0, sizeof(*result));
+    if (m.error) return device_error_check(ctx, m.error);
     if (m.key == ~0ull) {               // empty shard
         result->best_index = -1;
         result->best_score = INFINITY;
@@ -635,6 +660,18 @@ int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result)
         if (local >= 0 && local < ctx->last_P)
             for (int i = 0; i < 3; ++i) result->best_pose[i] = ctx->last_poses_host[3 * local + i];
     }
+    return B200SLAM_OK;
+}
+
+int b200slam_match_fetch_hits(b200slam_ctx *ctx, float *hits, int count)
+{
+    if (!ctx || count < 0 || (count > 0 && !hits)) return B200SLAM_ERR_ARG;
+    if (!ctx->d_hit_values) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan uploaded");
+    if (count > ctx->scan_cap) count = ctx->scan_cap;
+    if (count > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(hits, ctx->d_hit_values + ctx->scan_cap, sizeof(float) * (size_t)count,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return B200SLAM_OK;
 }
 

@@ -113,14 +113,24 @@ namespace {
 // every peer's buffer and waits until all the slots of its own buffer have reached it.  The
 // system-scope fences order the peer-memory stores of the kernels queued before the barrier
 // (the row-sharded EDT's remote rows) against the flag, and the loads of the kernels behind it.
-__global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, unsigned long long epoch)
+__global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, unsigned long long epoch, unsigned int *error)
 {
     const int r = threadIdx.x;
     __threadfence_system();
     if (r < X.nranks) {
         *reinterpret_cast<volatile unsigned long long *>(&X.peers[r]->bar[X.rank]) = epoch;
         const volatile unsigned long long *mine = &X.peers[X.rank]->bar[r];
-        while (*mine < epoch) {}
+        // bounded: a peer that never arrives sets a sticky error bit instead of hanging the GPU
+        const unsigned long long budget = *reinterpret_cast<volatile unsigned int *>(error) ? 0ull : X.timeout_ns;
+        if (*mine < epoch) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
+            while (*mine < epoch)
+                if ((++spins & 255u) == 0 && global_timer_ns() - t0 > budget) {
+                    atomicOr(error, DEV_ERR_BARRIER);
+                    break;
+                }
+        }
     }
     __threadfence_system();
 }
@@ -130,9 +140,7 @@ __global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, unsi
 int comm_peer_barrier(b200slam_ctx *ctx)
 {
     if (!ctx->p2p_ready) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "peer memory exchange is not set up");
-    XchgArgs X;
-    X.peers = ctx->d_peers; X.nranks = ctx->nranks; X.rank = ctx->rank;
-    peer_barrier_kernel<<<1, 64, 0, ctx->stream>>>(X, ++ctx->bar_epoch);
+    peer_barrier_kernel<<<1, 64, 0, ctx->stream>>>(xchg_args(ctx), ++ctx->bar_epoch, &ctx->d_match->error);
     LAUNCH_CHECK(ctx);
     return B200SLAM_OK;
 }
@@ -158,6 +166,8 @@ void teardown_peer_exchange(b200slam_ctx *ctx)
     cudaFree(ctx->d_xchg); ctx->d_xchg = nullptr;
     cudaFree(ctx->d_peers); ctx->d_peers = nullptr;
     ctx->p2p_ready = false;
+    ctx->bar_epoch = 0;               // a fresh XchgBuf starts with zeroed barrier slots
+    ctx->posted_uncollected = 0;
 }
 
 // Allocates this rank's exchange buffer, trades CUDA IPC handles with the other ranks (one
@@ -167,12 +177,15 @@ void setup_peer_exchange(b200slam_ctx *ctx)
 {
     const int n = ctx->nranks;
     if (n > XCHG_MAX_RANKS) return;
+    ctx->bar_epoch = 0;
+    ctx->posted_uncollected = 0;
     bool ok = cudaMalloc(&ctx->d_xchg, sizeof(XchgBuf)) == cudaSuccess &&
               cudaMemset(ctx->d_xchg, 0, sizeof(XchgBuf)) == cudaSuccess &&
               cudaMalloc(&ctx->d_peers, sizeof(XchgBuf *) * n) == cudaSuccess &&
               cudaMemset(&ctx->d_match->epoch, 0, sizeof(unsigned int)) == cudaSuccess &&
               cudaMemset(&ctx->d_match->collected, 0, sizeof(unsigned int)) == cudaSuccess &&
-              cudaMemset(&ctx->d_match->posted, 0, sizeof(unsigned int)) == cudaSuccess;
+              cudaMemset(&ctx->d_match->posted, 0, sizeof(unsigned int)) == cudaSuccess &&
+              cudaMemset(&ctx->d_match->error, 0, sizeof(unsigned int)) == cudaSuccess;
     // handle record: 64-byte IPC handle + 8-byte ok flag, padded to 80 bytes (10 x u64)
     constexpr int REC = 10;
     unsigned long long rec[REC] = {0};
@@ -254,10 +267,23 @@ int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id_i
     ctx->nccl_comm = comm;
     ctx->nranks = nranks;
     ctx->rank = rank;
+    if (const char *e = getenv("B200SLAM_SPIN_TIMEOUT_MS"))
+        if (atof(e) > 0) ctx->spin_timeout_ns = (unsigned long long)(atof(e) * 1e6);
     // NVLink peer exchange: best effort.  When CUDA IPC / P2P is unavailable the match results
     // are all-gathered with NCCL instead (same answers, ~20 us more latency per match).
     if (nranks > 1 && !getenv("B200SLAM_NO_P2P")) setup_peer_exchange(ctx);
     return B200SLAM_OK;
+}
+
+/* Collective, asynchronous: everything this rank queues behind it runs only once every rank has reached its
+ * own call (one 64-thread kernel exchanging flags through NVLink peer memory; a 16-byte ncclAllGather where
+ * CUDA IPC is unavailable).  No-op without a communicator. */
+int b200slam_comm_barrier_async(b200slam_ctx *ctx)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    if (!ctx->nccl_comm || ctx->nranks < 2) return B200SLAM_OK;
+    if (ctx->p2p_ready) return comm_peer_barrier(ctx);
+    return comm_allgather_u64(ctx, ctx->d_wsum, ctx->d_keys + 128, 1);
 }
 
 /* Collective: every rank calls it with its own copy of the (identically sized) map. */

@@ -42,7 +42,8 @@ struct MatchDev {
     int best_hits;
     int last_hits;
     unsigned int collected;     // peer exchanges this context has COLLECTED (merged)
-    unsigned int pad;
+    unsigned int error;         // sticky DEV_ERR_* bits: a bounded device-side wait gave up (b200slam_sync /
+                                // b200slam_match_fetch then return B200SLAM_ERR_STATE)
     unsigned long long gkey;    // GLOBAL result of the last collected exchange (all ranks merged)
     int gbest_hits;
     int glast_hits;
@@ -60,6 +61,12 @@ struct MatchDev {
 };
 static_assert(sizeof(MatchDev::outbox) / sizeof(MatchDev::Outbox) == 64, "outbox ring == XCHG_EPOCHS");
 constexpr int MATCH_SMALL = 64;
+// Every device-side wait is bounded (%globaltimer against b200slam_ctx::spin_timeout_ns, or an iteration
+// cap for the TMA barrier): a dead or mis-ordered peer costs a timeout and an error code, never a hung GPU.
+constexpr unsigned int DEV_ERR_EXCHANGE = 1u;   // exchange_collect: a peer's post never arrived
+constexpr unsigned int DEV_ERR_BARRIER = 2u;    // peer_barrier_kernel: a peer never reached the barrier
+constexpr unsigned int DEV_ERR_TMA = 4u;        // edt_tma_kernel: a TMA load never completed
+constexpr unsigned int DEV_ERR_PARTICLES = 8u;  // sharded particle filter: a peer's sums / offspring never arrived
 
 // Peer-memory exchange of per-rank match results (multi-GPU): every context owns one
 // XchgBuf; the last CTA of a scoring kernel stores its {key, best_hits, last_hits} into
@@ -85,7 +92,15 @@ struct XchgBuf {
 struct XchgArgs {                     // kernel-side view; peers == nullptr: no exchange
     XchgBuf *const *peers;            // [nranks] device pointers (own buffer at [rank])
     int nranks, rank;
+    unsigned long long timeout_ns;    // bound of every wait on a peer
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct b200slam_ctx {
     int device = 0;
@@ -190,6 +205,8 @@ struct b200slam_ctx {
     bool p2p_ready = false;
     unsigned long long bar_epoch = 0;     // peer barriers issued so far (same on every rank)
     int posted_uncollected = 0;           // post-only matches queued since the last blocking collect
+    unsigned long long spin_timeout_ns = 30ull * 1000 * 1000 * 1000;   // B200SLAM_SPIN_TIMEOUT_MS
+    float h_param_tab[960] = {};          // host copy of a by-parameter lattice's axis tables (no DMA reads it)
 };
 
 int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
@@ -237,6 +254,14 @@ struct LatticeLaunch {
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
 int exchange_collect_launch(b200slam_ctx *ctx);
+// B200SLAM_ERR_STATE (with a message) when a bounded device-side wait has given up since the last comm_init.
+int device_error_check(b200slam_ctx *ctx, unsigned int error_bits);
+inline XchgArgs xchg_args(const b200slam_ctx *ctx)
+{
+    XchgArgs X;
+    X.peers = ctx->d_peers; X.nranks = ctx->nranks; X.rank = ctx->rank; X.timeout_ns = ctx->spin_timeout_ns;
+    return X;
+}
 int poses_launch(b200slam_ctx *ctx, const b200slam_map *map, int64_t P, int64_t index_base,
                  float *d_scores, int32_t *d_hits);
 

@@ -57,19 +57,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// Bounded: try_wait suspends the warp for a hardware-defined slice per attempt; a load that has not
+// completed after 2^22 attempts (seconds) never will -> false, and the kernel reports DEV_ERR_TMA.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    uint32_t done = 0;
+    for (uint32_t tries = 0; tries < (1u << 22); ++tries) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y)
 {
@@ -167,7 +172,7 @@ template <int R, int NW, int NST, bool MULTI>
 __global__ void __launch_bounds__(EdtCfg<R, NW>::THREADS)
 edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out, uint32_t pitch_bytes,
                int row_begin, int row_end, int cols, int chunk_batches, int t2, float max_dist,
-               const __grid_constant__ EdtPeers peers)
+               const __grid_constant__ EdtPeers peers, unsigned int *__restrict__ error)
 {
     const int rows = row_end;
     using C = EdtCfg<R, NW>;
@@ -229,7 +234,10 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
 
     for (int t = 0; t < nbl; ++t) {
         const int s = t % NST;
-        mbar_wait(&full[s], (t / NST) & 1);
+        if (!mbar_wait(&full[s], (t / NST) & 1)) {
+            if (lane == 0) atomicOr(error, DEV_ERR_TMA);
+            return;
+        }
         const int *st = reinterpret_cast<const int *>(smem_raw + (size_t)s * C::STAGE_BYTES) + woff;
         // ---- pass 1: horizontal nearest-occupied distance from the ballots ------------
         int ld[B][3];
@@ -278,13 +286,14 @@ __global__ void edt_generic_cols(const int32_t *__restrict__ occ, long occ_pitch
                                  uint16_t *__restrict__ g, int rows, int cols, int R)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
     if (c >= cols) return;
-    int best = 0xffff;
-    const int lo = max(r - R, 0), hi = min(r + R, rows - 1);
-    for (int j = lo; j <= hi; ++j)
-        if (__ldg(occ + (long)j * occ_pitch + c)) best = min(best, abs(j - r));
-    g[(long)r * cols + c] = (uint16_t)best;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {          // gridDim.y is capped at 65535
+        int best = 0xffff;
+        const int lo = max(r - R, 0), hi = min(r + R, rows - 1);
+        for (int j = lo; j <= hi; ++j)
+            if (__ldg(occ + (long)j * occ_pitch + c)) best = min(best, abs(j - r));
+        g[(long)r * cols + c] = (uint16_t)best;
+    }
 }
 
 __global__ void edt_generic_rows(const uint16_t *__restrict__ g, float *__restrict__ out,
@@ -292,15 +301,16 @@ __global__ void edt_generic_rows(const uint16_t *__restrict__ g, float *__restri
                                  float max_dist)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
     if (c >= cols) return;
-    int best = INT_MAX;
     const int lo = max(c - R, 0), hi = min(c + R, cols - 1);
-    for (int i = lo; i <= hi; ++i) {
-        const int gv = g[(long)r * cols + i];
-        if (gv != 0xffff) best = min(best, (i - c) * (i - c) + gv * gv);
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        int best = INT_MAX;
+        for (int i = lo; i <= hi; ++i) {
+            const int gv = g[(long)r * cols + i];
+            if (gv != 0xffff) best = min(best, (i - c) * (i - c) + gv * gv);
+        }
+        out[(long)r * out_pitch + c] = best < t2 ? __fsqrt_rn((float)best) : max_dist;
     }
-    out[(long)r * out_pitch + c] = best < t2 ? __fsqrt_rn((float)best) : max_dist;
 }
 
 // ---- host side ----------------------------------------------------------------------
@@ -388,7 +398,7 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     if (const char *e = getenv("B200SLAM_EDT_CB")) best_cb = max(1, min(atoi(e), nbatch));   // tuning knob
     const int gy = (nbatch + best_cb - 1) / best_cb;
     kern<<<dim3(gx, gy), C::THREADS, smem, ctx->stream>>>(tmap, d_field, (uint32_t)field_pitch * 4u, row_begin, row_end, cols,
-                                                         best_cb, t2, max_dist, peers);
+                                                         best_cb, t2, max_dist, peers, &ctx->d_match->error);
     LAUNCH_CHECK(ctx);
     return B200SLAM_OK;
 }
@@ -467,7 +477,7 @@ int edt_launch_rows(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, floa
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_edt_scratch, need * sizeof(uint16_t)));
         ctx->edt_scratch_cap = need;
     }
-    dim3 block(128), grid((cols + 127) / 128, rows);
+    dim3 block(128), grid((cols + 127) / 128, rows < 65535 ? rows : 65535);
     edt_generic_cols<<<grid, block, 0, ctx->stream>>>(d_occ, occ_pitch, ctx->d_edt_scratch, rows, cols, R);
     LAUNCH_CHECK(ctx);
     edt_generic_rows<<<grid, block, 0, ctx->stream>>>(ctx->d_edt_scratch, d_field, field_pitch, rows,

@@ -335,6 +335,10 @@ int b200slam_mappoints_grow(b200slam_ctx *ctx, float threshold, int *added)
     if (!ctx) return B200SLAM_ERR_ARG;
     if (!ctx->scan_t_valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_scan_transform first");
     if (!ctx->last.valid || ctx->last.is_poses) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no lattice match to grow from");
+    // main.c:942-948 reads the winner's count and the LAST candidate's hit values of the WHOLE lattice; after a
+    // sharded match both may live on another rank
+    if (ctx->last.exchanged || ctx->last.gathered)
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map growth needs a match scored entirely on this GPU");
     int rc = ensure_map_points(ctx, ctx->mp_size + ctx->nbeams);
     if (!rc) rc = ensure_front(ctx);
     if (rc) return rc;

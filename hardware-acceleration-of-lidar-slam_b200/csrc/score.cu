@@ -134,12 +134,29 @@ __device__ __forceinline__ void exchange_collect(const XchgArgs &X, MatchDev *ma
 {
     const int tid = threadIdx.x;
     const int ring = (int)(epoch % XCHG_EPOCHS);
+    // Bounded wait: a peer that died or was queued out of order costs one timeout and a sticky error bit
+    // (B200SLAM_ERR_STATE from b200slam_match_fetch / b200slam_sync), not a GPU that spins forever.  Once
+    // the bit is set later collects do not wait at all.
+    const unsigned long long budget = *reinterpret_cast<volatile unsigned int *>(&match->error) ? 0ull : X.timeout_ns;
     for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
         const int r = i >> 2, w = i & 3;
         const volatile unsigned long long *src = &X.peers[X.rank]->slot[ring][r].w[w];
-        unsigned long long v;
-        do { v = *src; } while ((unsigned int)(v >> 32) != epoch);
-        got[i] = (unsigned int)v;
+        unsigned long long v = *src;
+        if ((unsigned int)(v >> 32) != epoch) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
+            for (;;) {
+                v = *src;
+                if ((unsigned int)(v >> 32) == epoch) break;
+                if ((++spins & 255u) == 0 && global_timer_ns() - t0 > budget) break;
+            }
+        }
+        if ((unsigned int)(v >> 32) == epoch) {
+            got[i] = (unsigned int)v;
+        } else {
+            got[i] = w < 2 ? 0xffffffffu : 0u;              // "nothing scored" for the missing rank
+            atomicOr(&match->error, DEV_ERR_EXCHANGE);
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -184,20 +201,37 @@ __global__ void __launch_bounds__(64) exchange_collect_kernel(MatchDev *match, c
     }
 }
 
-// Empty shard of a multi-GPU match: nothing to score, but the peers expect this rank's post.
-__global__ void __launch_bounds__(64) exchange_only_kernel(MatchDev *match, const XchgArgs X)
+// Empty shard of a multi-GPU match: nothing to score, but the peers expect this rank's post -- through the
+// same channel the scoring kernel's tail would have used: recorded in the outbox when the burst's posts are
+// deferred (the collect kernel sends the outbox in epoch order, so nothing recorded earlier is skipped), else
+// stored into the peers' buffers right away, merging the previous exchange here when the caller deferred
+// that to the next tail (so a rank that only ever posts stays within the ring like everybody else).
+__global__ void __launch_bounds__(64) exchange_only_kernel(MatchDev *match, const XchgArgs X, int post_deferred,
+                                                           int collect_prev)
 {
     __shared__ unsigned int words_s[4];
-    __shared__ unsigned int epoch_s;
-    if (threadIdx.x == 0) epoch_s = match->epoch + 1;
+    __shared__ unsigned int got[4 * XCHG_MAX_RANKS];
+    __shared__ unsigned int epoch_s, done_s;
+    if (threadIdx.x == 0) {
+        epoch_s = *reinterpret_cast<volatile unsigned int *>(&match->epoch) + 1;
+        done_s = *reinterpret_cast<volatile unsigned int *>(&match->collected);
+    }
     __syncthreads();
-    exchange_post(X, epoch_s, ~0ull, 0, 0, words_s);
+    if (post_deferred) {
+        if (threadIdx.x == 0) {
+            MatchDev::Outbox *ob = &match->outbox[epoch_s % XCHG_EPOCHS];
+            ob->key = ~0ull; ob->best_hits = 0; ob->last_hits = 0;
+        }
+    } else {
+        exchange_post(X, epoch_s, ~0ull, 0, 0, words_s);
+        if (threadIdx.x == 0) match->posted = epoch_s;
+        if (collect_prev && done_s + 1 < epoch_s) exchange_collect(X, match, done_s + 1, got);
+    }
     if (threadIdx.x == 0) {
         match->key = ~0ull;
         match->best_hits = 0;
         match->last_hits = 0;
         match->epoch = epoch_s;
-        match->posted = epoch_s;
     }
 }
 
@@ -338,6 +372,8 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     const int tx0 = blockIdx.y * TXT, ty0 = blockIdx.x * TYT;
 
     unsigned long long best = ~0ull;
+    [[maybe_unused]] int nhits = 0;                              // COUNT only: this thread's candidate's in-bounds beams
+    [[maybe_unused]] long long count_lin = -1;                   // COUNT only: that candidate's linear index
     // whole tile outside this shard's (theta, tx) row range?  (still takes a ticket)
     const long long r_lo = (long long)ith * A.ntx + tx0;
     const long long r_hi = r_lo + min(TXT, A.ntx - tx0);
@@ -349,7 +385,6 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
         float acc[TYPT];
 #pragma unroll
         for (int j = 0; j < TYPT; ++j) acc[j] = 0.0f;            // main.c:507
-        int nhits = 0;                                           // COUNT only
 
         for (int c0 = 0; c0 < A.nbeams; c0 += A.cb) {
             const int cb = min(A.cb, A.nbeams - c0);
@@ -547,7 +582,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                 if (ity < A.nty) {
                     const long long lin = row * A.nty + ity;
                     if (A.scores) A.scores[lin] = acc[j];
-                    if constexpr (COUNT) A.match->cand_hits[lin] = nhits;
+                    if constexpr (COUNT) count_lin = lin;
                     const unsigned long long k = pack_key(acc[j], (unsigned int)lin);
                     best = k < best ? k : best;
                 }
@@ -557,6 +592,10 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     // Scores and tables above depend on the scan, the launch parameters and the field only.  The
     // match state below is shared with the kernel in front (its last CTA resets it).
     pdl_wait_prior_grids();
+    // cand_hits[] belongs to the match state: the kernel in front may still be walking it in its
+    // bestHits staircase until it has completed, so it is written only behind the wait
+    if constexpr (COUNT)
+        if (count_lin >= 0) A.match->cand_hits[count_lin] = nhits;
     best = warp_min_u64(best);
     if (lane == 0) red[warp] = best;
     __syncthreads();
@@ -828,19 +867,16 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     A.hit_values = ctx->d_hit_values;
     A.hit_stride = ctx->scan_cap;
     A.tables = L.d_tables;
-    A.xchg.peers = nullptr; A.xchg.nranks = 1; A.xchg.rank = 0;
+    A.xchg.peers = nullptr; A.xchg.nranks = 1; A.xchg.rank = 0; A.xchg.timeout_ns = ctx->spin_timeout_ns;
     A.collect_prev = L.collect_prev ? 1 : 0;
     A.post_deferred = L.post_deferred ? 1 : 0;
-    if (L.exchange && ctx->p2p_ready) {
-        A.xchg.peers = ctx->d_peers;
-        A.xchg.nranks = ctx->nranks; A.xchg.rank = ctx->rank;
-    }
+    if (L.exchange && ctx->p2p_ready) A.xchg = xchg_args(ctx);
     LatticeTables T;                     // parameter block (copied at launch)
     A.nth_tab = L.nth_tab;
     if (!L.d_tables) memcpy(T.v, L.h_tables, sizeof(float) * (2 * (size_t)L.nth_tab + L.ntx + L.nty));
     if (L.row_end <= L.row_begin) {
         if (A.xchg.peers) {             // nothing to score, but the peers wait for this rank's post
-            exchange_only_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, A.xchg);
+            exchange_only_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, A.xchg, A.post_deferred, A.collect_prev);
             LAUNCH_CHECK(ctx);
             return B200SLAM_OK;
         }
@@ -928,9 +964,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
 
 int exchange_collect_launch(b200slam_ctx *ctx)
 {
-    XchgArgs X;
-    X.peers = ctx->d_peers; X.nranks = ctx->nranks; X.rank = ctx->rank;
-    exchange_collect_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, X);
+    exchange_collect_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, xchg_args(ctx));
     LAUNCH_CHECK(ctx);
     return B200SLAM_OK;
 }

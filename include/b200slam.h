@@ -60,7 +60,11 @@ int  b200slam_create(b200slam_ctx **out, int device);
 void b200slam_destroy(b200slam_ctx *ctx);
 /* Message of the last failure on this context (ctx == NULL: last create failure). */
 const char *b200slam_last_error(const b200slam_ctx *ctx);
-/* Blocks until everything queued on the context's stream has finished. */
+/* Blocks until everything queued on the context's stream has finished.  Every device-side wait of the
+ * library (peer exchange, peer barrier, TMA barrier) is bounded -- B200SLAM_SPIN_TIMEOUT_MS in the
+ * environment, default 30 000 -- and one that gave up (a peer died, or the ranks queued their collective
+ * calls in different orders) leaves a sticky error: this call and b200slam_match_fetch then return
+ * B200SLAM_ERR_STATE until b200slam_comm_init is called again.  The GPU is never left spinning. */
 int  b200slam_sync(b200slam_ctx *ctx);
 /* The context's cudaStream_t, for callers that time with CUDA events or interoperate. */
 void *b200slam_stream(b200slam_ctx *ctx);
@@ -174,6 +178,10 @@ int b200slam_score_lattice_async(b200slam_ctx *ctx, b200slam_map *map, const flo
                                  int64_t row_end, int allreduce);
 int b200slam_exchange_collect_async(b200slam_ctx *ctx);
 int b200slam_match_fetch(b200slam_ctx *ctx, b200slam_match *result);
+/* The device's twin of FastMatchParameters.bestHits[] (main.c:376) as the matches queued so far have left
+ * it: hits[0 .. count) (count is clipped to the buffer, >= 2500 floats).  For callers of the *_async
+ * entry points; b200slam_fastmatch returns the same data through its best_hits argument. */
+int b200slam_match_fetch_hits(b200slam_ctx *ctx, float *hits, int count);
 
 /* Arbitrary pose / particle list: poses[P][3] = {x, y, theta}; ct/st optional [P]
  * (cosf/sinf(theta) from the host libm when NULL).  scores (optional host [P]) and
@@ -312,6 +320,10 @@ int b200slam_pyramid_match(b200slam_ctx *ctx, b200slam_map *const *maps, int lev
 int b200slam_comm_unique_id(void *id_out /*[128]*/);            /* rank 0 */
 int b200slam_comm_init(b200slam_ctx *ctx, int nranks, int rank, const void *id /*[128]*/);
 int b200slam_comm_destroy(b200slam_ctx *ctx);
+/* Device-side barrier over the ranks, queued on the context's stream (nothing blocks on the host): the
+ * work queued behind it starts only when every rank's stream has reached its own barrier.  Lines the GPUs
+ * up before a timed region; the row-sharded transform uses the same kernel internally. */
+int b200slam_comm_barrier_async(b200slam_ctx *ctx);
 /* Row-sharded transform (BASELINE configs[3]: "8192x8192 grid EDT (row-sharded)").  The
  * transform is clamped at max_dist, so a block of output rows needs only a ceil(max_dist)-1 row
  * halo of the INPUT, which every rank already holds (the occupancy is replicated): nothing is
