@@ -127,6 +127,7 @@ def load_library() -> C.CDLL:
         "b200slam_event_elapsed_ms": (i, [vp, i, i, c_float_p]),
         "b200slam_weights_resample": (i, [vp, f, C.c_uint32, vp, c_u64_p, vp, c_i64_p, c_i64_p]),
         "b200slam_particles_upload": (i, [vp, vp, vp, vp, C.c_int64]),
+        "b200slam_particles_shard": (i, [vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64]),
         "b200slam_particles_score_async": (i, [vp, vp]),
         "b200slam_particles_resample_async": (i, [vp, f, C.c_uint32]),
         "b200slam_particles_download": (i, [vp, vp, vp, vp, vp]),
@@ -537,6 +538,17 @@ class Context:
         self._check(self.L.b200slam_particles_upload(self.h, poses.ctypes.data,
                                                      ctp.ctypes.data if ctp is not None else None,
                                                      stp.ctypes.data if stp is not None else None, poses.shape[0]))
+        self._P = poses.shape[0]
+
+    def particles_shard(self, poses, index_base: int, n_global: int, ct=None, st=None):
+        """Collective: this rank's slice [index_base, index_base + len(poses)) of a set of n_global particles."""
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 3)
+        ctp = np.ascontiguousarray(ct, np.float32) if ct is not None else None
+        stp = np.ascontiguousarray(st, np.float32) if st is not None else None
+        self._check(self.L.b200slam_particles_shard(self.h, poses.ctypes.data,
+                                                    ctp.ctypes.data if ctp is not None else None,
+                                                    stp.ctypes.data if stp is not None else None, poses.shape[0],
+                                                    index_base, n_global))
         self._P = poses.shape[0]
 
     def particles_score_async(self, m: Map):

@@ -77,12 +77,14 @@ int b200slam_create(b200slam_ctx **out, int device)
         MatchDev init;
         init.work_key = ~0ull; init.tickets = 0; init.epoch = 0; init.key = ~0ull;
         init.best_hits = 0; init.last_hits = 0; init.collected = 0; init.error = 0; init.written_hits = 0; init.posted = 0;
-        memset(init.cand_hits, 0, sizeof init.cand_hits); memset(init.outbox, 0, sizeof init.outbox); init.gkey = ~0ull; init.gbest_hits = 0; init.glast_hits = 0;
+        memset(init.cand_hits, 0, sizeof init.cand_hits); memset(init.outbox, 0, sizeof init.outbox);
+        init.bar_epoch = 0; init.gkey = ~0ull; init.gbest_hits = 0; init.glast_hits = 0;
         CREATE_TRY(cudaMemcpy(ctx->d_match, &init, sizeof init, cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaMalloc(&ctx->d_keys, sizeof(unsigned long long) * 256));
     CREATE_TRY(cudaHostAlloc(&ctx->h_keys, sizeof(unsigned long long) * 128, cudaHostAllocDefault));
-    CREATE_TRY(cudaMalloc(&ctx->d_wsum, sizeof(unsigned long long) * 4));
+    CREATE_TRY(cudaMalloc(&ctx->d_wsum, sizeof(unsigned long long) * PF_SCALARS));
+    CREATE_TRY(cudaMemset(ctx->d_wsum, 0, sizeof(unsigned long long) * PF_SCALARS));
     CREATE_TRY(cudaHostAlloc(&ctx->h_wsum, sizeof(unsigned long long) * 2 * 64, cudaHostAllocDefault));
 #undef CREATE_TRY
     *out = ctx;
@@ -102,7 +104,9 @@ void b200slam_destroy(b200slam_ctx *ctx)
     cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match);
     cudaFree(ctx->d_keys); cudaFreeHost(ctx->h_keys); cudaFree(ctx->d_hit_values);
     cudaFree(ctx->d_scores);
-    cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_pose_alt); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
+    particles_unshare_blocks(ctx);
+    cudaFree(ctx->d_pf_peers);
+    cudaFree(ctx->d_pose_block); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
     cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
     cudaFree(ctx->d_ancestors); cudaFree(ctx->d_wsum); cudaFreeHost(ctx->h_wsum);
     cudaFree(ctx->d_edt_scratch);
@@ -756,14 +760,20 @@ static int stage_poses(b200slam_ctx *ctx, const float *poses, const float *ct, c
 {
     if ((size_t)P > ctx->pose_cap) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_pose_soa); cudaFree(ctx->d_pose_alt); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
+        particles_unshare_blocks(ctx);               // peers' mappings of the old block die with it
+        cudaFree(ctx->d_pose_block); cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_pose_stage);
         cudaFree(ctx->d_q); cudaFree(ctx->d_block_sums); cudaFree(ctx->d_weights);
-        ctx->d_pose_soa = nullptr; ctx->d_pose_alt = nullptr; ctx->d_hits = nullptr; ctx->h_pose_stage = nullptr;
+        ctx->d_pose_block = nullptr; ctx->d_pose_soa = nullptr; ctx->d_pose_alt = nullptr; ctx->d_anc_resident = nullptr;
+        ctx->d_hits = nullptr; ctx->h_pose_stage = nullptr;
         ctx->d_q = nullptr; ctx->d_block_sums = nullptr; ctx->d_weights = nullptr;
         ctx->pose_cap = 0;
         const size_t cap = ((size_t)P + 4095) & ~(size_t)4095;
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_pose_soa, sizeof(float) * 5 * cap));
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_pose_alt, sizeof(float) * 5 * cap));
+        // [2][5 * cap] floats (the two pose buffers) | [cap] int32 ancestors of the resident set
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_pose_block, sizeof(float) * 11 * cap));
+        ctx->d_pose_soa = ctx->d_pose_block;
+        ctx->d_pose_alt = ctx->d_pose_block + 5 * cap;
+        ctx->d_anc_resident = reinterpret_cast<int32_t *>(ctx->d_pose_block + 10 * cap);
+        ctx->pose_parity = 0;
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_hits, sizeof(int32_t) * cap));
         CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_pose_stage, sizeof(float) * 5 * cap, cudaHostAllocDefault));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_q, sizeof(unsigned long long) * cap));
@@ -849,7 +859,30 @@ int b200slam_particles_upload(b200slam_ctx *ctx, const float *poses, const float
     ctx->last_index_base = 0;
     ctx->last_poses_host = nullptr;
     ctx->last.valid = false;
+    ctx->pf_sharded = false;
     return B200SLAM_OK;
+}
+
+int b200slam_particles_shard(b200slam_ctx *ctx, const float *poses, const float *ct, const float *st, int64_t P,
+                             int64_t index_base, int64_t n_global)
+{
+    if (!ctx || P <= 0 || !poses || index_base < 0 || n_global < index_base + P || n_global > 0x7fffffffll)
+        return B200SLAM_ERR_ARG;
+    if (!ctx->nccl_comm || ctx->nranks < 2 || !ctx->p2p_ready)
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_particles_shard needs b200slam_comm_init with NVLink peer "
+                                                            "memory (one GPU: b200slam_particles_upload)");
+    int rc = stage_poses(ctx, poses, ct, st, P);
+    if (rc) return rc;
+    rc = particles_share_blocks(ctx);              // collective
+    if (rc) return rc;
+    ctx->last_P = P;
+    ctx->last_index_base = index_base;
+    ctx->last_poses_host = nullptr;
+    ctx->last.valid = false;
+    ctx->pf_sharded = true;
+    ctx->pf_nglobal = n_global;
+    // nobody pushes offspring into this rank's buffers before every rank has staged its slice
+    return comm_peer_barrier(ctx);
 }
 
 int b200slam_particles_score_async(b200slam_ctx *ctx, b200slam_map *map)
@@ -858,13 +891,14 @@ int b200slam_particles_score_async(b200slam_ctx *ctx, b200slam_map *map)
     if (!map->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
     if (!ctx->d_scan_x) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan uploaded");
     if (ctx->last_P <= 0 || !ctx->d_pose_soa) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no particles uploaded");
-    int rc = poses_launch(ctx, map, ctx->last_P, 0, ctx->d_scores, ctx->d_hits);
+    const int64_t base = ctx->pf_sharded ? ctx->last_index_base : 0;
+    int rc = poses_launch(ctx, map, ctx->last_P, base, ctx->d_scores, ctx->d_hits, ctx->pf_sharded);
     if (rc) return rc;
     ctx->last.valid = true;
     ctx->last.is_poses = true;
     ctx->last.gathered = false;
     ctx->last.exchanged = false;
-    ctx->last_index_base = 0;
+    ctx->last_index_base = base;
     return B200SLAM_OK;
 }
 
@@ -873,9 +907,7 @@ int b200slam_particles_resample_async(b200slam_ctx *ctx, float beta, uint32_t u0
     if (!ctx) return B200SLAM_ERR_ARG;
     if (!ctx->last.valid || !ctx->last.is_poses)
         return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_particles_score_async must run first");
-    if (ctx->nccl_comm && ctx->nranks > 1)
-        return b200slam_set_error(ctx, B200SLAM_ERR_STATE,
-                                  "the resident particle set is single-GPU; use b200slam_weights_resample with a communicator");
+    // the scores must be those of the resident set, not of a b200slam_score_poses call in between
     return particles_resample_resident(ctx, ctx->last_P, beta, u0_q32);
 }
 
@@ -900,9 +932,11 @@ int b200slam_particles_download(b200slam_ctx *ctx, float *poses, float *scores, 
     }
     if (scores) CUDA_TRY(ctx, cudaMemcpyAsync(scores, ctx->d_scores, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
     if (weights) CUDA_TRY(ctx, cudaMemcpyAsync(weights, ctx->d_weights, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ancestors) CUDA_TRY(ctx, cudaMemcpyAsync(ancestors, ctx->d_ancestors, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ancestors) CUDA_TRY(ctx, cudaMemcpyAsync(ancestors, ctx->d_anc_resident, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_match->error, &ctx->d_match->error, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return B200SLAM_OK;
+    return device_error_check(ctx, ctx->h_match->error);
 }
 
 int b200slam_weights_resample(b200slam_ctx *ctx, float beta, uint32_t u0_q32, float *weights,

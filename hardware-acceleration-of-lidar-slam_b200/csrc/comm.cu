@@ -113,8 +113,15 @@ namespace {
 // every peer's buffer and waits until all the slots of its own buffer have reached it.  The
 // system-scope fences order the peer-memory stores of the kernels queued before the barrier
 // (the row-sharded EDT's remote rows) against the flag, and the loads of the kernels behind it.
-__global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, unsigned long long epoch, unsigned int *error)
+// The barrier's number lives on the DEVICE (MatchDev::bar_epoch, advanced by this kernel alone, in stream
+// order), not in a launch argument: a barrier captured into a CUDA graph must count on every replay.
+__global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, MatchDev *match)
 {
+    __shared__ unsigned long long epoch_s;
+    if (threadIdx.x == 0) epoch_s = *reinterpret_cast<volatile unsigned long long *>(&match->bar_epoch) + 1;
+    __syncthreads();
+    const unsigned long long epoch = epoch_s;
+    unsigned int *error = &match->error;
     const int r = threadIdx.x;
     __threadfence_system();
     if (r < X.nranks) {
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, unsi
         }
     }
     __threadfence_system();
+    if (threadIdx.x == 0) match->bar_epoch = epoch;
 }
 
 }  // namespace
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(64) peer_barrier_kernel(const XchgArgs X, unsi
 int comm_peer_barrier(b200slam_ctx *ctx)
 {
     if (!ctx->p2p_ready) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "peer memory exchange is not set up");
-    peer_barrier_kernel<<<1, 64, 0, ctx->stream>>>(xchg_args(ctx), ++ctx->bar_epoch, &ctx->d_match->error);
+    peer_barrier_kernel<<<1, 64, 0, ctx->stream>>>(xchg_args(ctx), ctx->d_match);
     LAUNCH_CHECK(ctx);
     return B200SLAM_OK;
 }
@@ -166,7 +174,6 @@ void teardown_peer_exchange(b200slam_ctx *ctx)
     cudaFree(ctx->d_xchg); ctx->d_xchg = nullptr;
     cudaFree(ctx->d_peers); ctx->d_peers = nullptr;
     ctx->p2p_ready = false;
-    ctx->bar_epoch = 0;               // a fresh XchgBuf starts with zeroed barrier slots
     ctx->posted_uncollected = 0;
 }
 
@@ -177,7 +184,6 @@ void setup_peer_exchange(b200slam_ctx *ctx)
 {
     const int n = ctx->nranks;
     if (n > XCHG_MAX_RANKS) return;
-    ctx->bar_epoch = 0;
     ctx->posted_uncollected = 0;
     bool ok = cudaMalloc(&ctx->d_xchg, sizeof(XchgBuf)) == cudaSuccess &&
               cudaMemset(ctx->d_xchg, 0, sizeof(XchgBuf)) == cudaSuccess &&
@@ -185,7 +191,8 @@ void setup_peer_exchange(b200slam_ctx *ctx)
               cudaMemset(&ctx->d_match->epoch, 0, sizeof(unsigned int)) == cudaSuccess &&
               cudaMemset(&ctx->d_match->collected, 0, sizeof(unsigned int)) == cudaSuccess &&
               cudaMemset(&ctx->d_match->posted, 0, sizeof(unsigned int)) == cudaSuccess &&
-              cudaMemset(&ctx->d_match->error, 0, sizeof(unsigned int)) == cudaSuccess;
+              cudaMemset(&ctx->d_match->error, 0, sizeof(unsigned int)) == cudaSuccess &&
+              cudaMemset(&ctx->d_match->bar_epoch, 0, sizeof(unsigned long long)) == cudaSuccess;   // fresh XchgBuf: zeroed barrier slots
     // handle record: 64-byte IPC handle + 8-byte ok flag, padded to 80 bytes (10 x u64)
     constexpr int REC = 10;
     unsigned long long rec[REC] = {0};
@@ -374,6 +381,7 @@ int b200slam_comm_destroy(b200slam_ctx *ctx)
     if (ctx->nccl_comm) {
         NcclApi *api = nccl_api();
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        particles_unshare_blocks(ctx);
         teardown_peer_exchange(ctx);
         if (api->handle) api->CommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;

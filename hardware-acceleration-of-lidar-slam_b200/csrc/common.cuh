@@ -58,6 +58,7 @@ struct MatchDev {
     // kernel at the end of the burst sends them all to the peers at once, so no scoring kernel has
     // NVLink stores in flight when it completes (measured: ~8 us per kernel on a 2-GPU box)
     struct Outbox { unsigned long long key; int best_hits, last_hits; } outbox[64];
+    unsigned long long bar_epoch;   // device-side peer barriers this context has passed (same on every rank)
 };
 static_assert(sizeof(MatchDev::outbox) / sizeof(MatchDev::Outbox) == 64, "outbox ring == XCHG_EPOCHS");
 constexpr int MATCH_SMALL = 64;
@@ -149,9 +150,22 @@ struct b200slam_ctx {
     size_t scores_cap = 0;       // floats
 
     // pose-list scoring (particles)
+    // one allocation d_pose_block = [2][5 * pose_cap] floats | [pose_cap] int32 ancestors of the resident set; the
+    // two pose buffers swap at every resampling (pose_parity = which half d_pose_soa is).  One block, so that
+    // the sharded particle filter can map every peer's block through ONE CUDA IPC handle (pf_peer_block).
+    float *d_pose_block = nullptr;
     float *d_pose_soa = nullptr;  // x | y | ct | st | theta, each [pose_cap]
     float *d_pose_alt = nullptr;  // same layout: target of the resampling gather (buffers swap)
+    int32_t *d_anc_resident = nullptr;
+    int pose_parity = 0;
     size_t pose_cap = 0;
+    // sharded resident particle set (b200slam_particles_shard): this rank's slice of N_global particles
+    bool pf_sharded = false;
+    long long pf_nglobal = 0;
+    float *pf_peer_block[XCHG_MAX_RANKS] = {};   // every rank's d_pose_block (own at [rank]), IPC mapped
+    float **d_pf_peers = nullptr;                // device copy [nranks]
+    float *pf_shared_block = nullptr;            // the d_pose_block the mappings were exchanged for
+    size_t pf_shared_cap = 0;
     int32_t *d_hits = nullptr;
     float *h_pose_stage = nullptr;   // pinned staging [4][pose_cap]
     int64_t last_P = 0;
@@ -164,7 +178,7 @@ struct b200slam_ctx {
     float *d_weights = nullptr;
     int32_t *d_ancestors = nullptr;
     size_t anc_cap = 0;
-    unsigned long long *d_wsum = nullptr;     // [4] scratch scalars
+    unsigned long long *d_wsum = nullptr;     // [PF_SCALARS] scratch scalars (layout: PfScalar)
     unsigned long long *h_wsum = nullptr;     // pinned [4]
 
     // map points staged for rasterisation: x | y
@@ -203,7 +217,6 @@ struct b200slam_ctx {
     XchgBuf **d_peers = nullptr;          // device array [nranks]
     XchgBuf *peer_ptrs[XCHG_MAX_RANKS] = {};   // host copy (for closing the IPC mappings)
     bool p2p_ready = false;
-    unsigned long long bar_epoch = 0;     // peer barriers issued so far (same on every rank)
     int posted_uncollected = 0;           // post-only matches queued since the last blocking collect
     unsigned long long spin_timeout_ns = 30ull * 1000 * 1000 * 1000;   // B200SLAM_SPIN_TIMEOUT_MS
     float h_param_tab[960] = {};          // host copy of a by-parameter lattice's axis tables (no DMA reads it)
@@ -262,10 +275,17 @@ inline XchgArgs xchg_args(const b200slam_ctx *ctx)
     X.peers = ctx->d_peers; X.nranks = ctx->nranks; X.rank = ctx->rank; X.timeout_ns = ctx->spin_timeout_ns;
     return X;
 }
+// post_sharded: the kernel's tail posts {arg-min key, P} to every peer (first exchange of a sharded filter step)
 int poses_launch(b200slam_ctx *ctx, const b200slam_map *map, int64_t P, int64_t index_base,
-                 float *d_scores, int32_t *d_hits);
+                 float *d_scores, int32_t *d_hits, bool post_sharded = false);
 
 int particles_resample_resident(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32);
+// Sharded resident set: collective set-up (maps every rank's pose block through CUDA IPC) and tear-down.
+int particles_share_blocks(b200slam_ctx *ctx);
+void particles_unshare_blocks(b200slam_ctx *ctx);
+// d_wsum layout
+enum PfScalar { PF_WLOCAL = 0, PF_WGLOBAL = 1, PF_RANK_OFFSET = 2, PF_KBEGIN = 3, PF_KCOUNT = 4, PF_NGLOBAL = 5,
+                PF_SLOT_BASE = 8 /* [nranks + 1]: first resampling slot held by each rank */, PF_SCALARS = 8 + XCHG_MAX_RANKS + 1 };
 int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32,
                                float *weights, uint64_t *wsum, int32_t *ancestors,
                                int64_t *k_begin, int64_t *k_count);
@@ -288,6 +308,47 @@ int comm_gather_row_blocks(b200slam_ctx *ctx, float *d_field, int pitch, int row
 // All ranks wait for each other on the device (flags in peer memory); needs p2p_ready.
 int comm_peer_barrier(b200slam_ctx *ctx);
 void comm_unshare_map(b200slam_ctx *ctx, b200slam_map *map);
+
+// ---- NVLink peer exchange primitives (device) ------------------------------------------------
+// POST: four 32-bit payload words of exchange number `epoch` are stored into EVERY peer's buffer as 8-byte
+// words {data, epoch} (each store atomic and self-validating).  Fire and forget.  Whole CTA; words_smem[4].
+__device__ __forceinline__ void xchg_post_words(const XchgArgs &X, unsigned int epoch, unsigned int w0, unsigned int w1,
+                                                unsigned int w2, unsigned int w3, unsigned int *words_smem)
+{
+    const int tid = threadIdx.x;
+    const int ring = (int)(epoch % XCHG_EPOCHS);
+    if (tid == 0) { words_smem[0] = w0; words_smem[1] = w1; words_smem[2] = w2; words_smem[3] = w3; }
+    __syncthreads();
+    const unsigned long long tag = (unsigned long long)epoch << 32;
+    for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
+        const int r = i >> 2, w = i & 3;
+        *reinterpret_cast<volatile unsigned long long *>(&X.peers[r]->slot[ring][X.rank].w[w]) = tag | words_smem[w];
+    }
+}
+// WAIT for word w of rank r's post number `epoch` in OUR buffer.  Bounded by X.timeout_ns (0 once *error is
+// set): false + error bit when the word never arrives.
+__device__ __forceinline__ bool xchg_wait_word(const XchgArgs &X, unsigned int epoch, int r, int w, unsigned int *out,
+                                               unsigned int *error, unsigned int error_bit)
+{
+    const volatile unsigned long long *src = &X.peers[X.rank]->slot[epoch % XCHG_EPOCHS][r].w[w];
+    unsigned long long v = *src;
+    if ((unsigned int)(v >> 32) != epoch) {
+        const unsigned long long budget = *reinterpret_cast<volatile unsigned int *>(error) ? 0ull : X.timeout_ns;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
+        for (;;) {
+            v = *src;
+            if ((unsigned int)(v >> 32) == epoch) break;
+            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > budget) break;
+        }
+    }
+    if ((unsigned int)(v >> 32) != epoch) {
+        atomicOr(error, error_bit);
+        return false;
+    }
+    *out = (unsigned int)v;
+    return true;
+}
 
 // Programmatic dependent launch (PDL) between consecutive scan-matching kernels: a kernel lets
 // the NEXT one in the stream start (launch latency, table construction, its whole gather loop

@@ -51,14 +51,32 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
 
 // q_i and per-CTA sums.  keys: packed arg-min keys (one per rank); their min carries
 // score_min in its upper 32 bits.
+// Sharded resident set (X.peers != nullptr): the keys are the ones every rank's poses_kernel posted into
+// OUR exchange buffer as exchange number match->epoch; every CTA waits for them itself (local polling,
+// bounded), so no collect kernel sits between scoring and weighting.
 __global__ void __launch_bounds__(PT_THREADS)
 weights_kernel(const float *__restrict__ scores, long long N, float beta,
                const unsigned long long *__restrict__ keys, int nkeys,
-               unsigned long long *__restrict__ q, unsigned long long *__restrict__ block_sums)
+               unsigned long long *__restrict__ q, unsigned long long *__restrict__ block_sums,
+               const XchgArgs X, MatchDev *match)
 {
     __shared__ unsigned long long wsum[PT_THREADS / 32];
+    __shared__ unsigned long long kmin_s;
     unsigned long long key = ~0ull;
     for (int k = 0; k < nkeys; ++k) key = keys[k] < key ? keys[k] : key;
+    if (X.peers) {
+        if (threadIdx.x == 0) kmin_s = ~0ull;
+        __syncthreads();
+        const unsigned int e1 = *reinterpret_cast<volatile unsigned int *>(&match->epoch);
+        if (threadIdx.x < X.nranks) {
+            unsigned int lo, hi;
+            if (xchg_wait_word(X, e1, threadIdx.x, 0, &lo, &match->error, DEV_ERR_PARTICLES) &&
+                xchg_wait_word(X, e1, threadIdx.x, 1, &hi, &match->error, DEV_ERR_PARTICLES))
+                atomicMin(&kmin_s, ((unsigned long long)hi << 32) | lo);
+        }
+        __syncthreads();
+        key = kmin_s;
+    }
     const float smin = __uint_as_float((unsigned int)(key >> 32));
     const long long base = (long long)blockIdx.x * PT_BLOCK + (long long)threadIdx.x * PT_ITEMS;
     unsigned long long local = 0;
@@ -85,11 +103,38 @@ weights_kernel(const float *__restrict__ scores, long long N, float beta,
     }
 }
 
-// Exclusive scan of the per-CTA sums (one CTA); total -> out_total[0].
+// number of slots k in [0, N) with T_k < c  (T_k = U + k Wd + floor(k Wm / N) is non-decreasing in k)
+__host__ __device__ inline long long slots_below(unsigned long long c, unsigned long long U, unsigned long long Wd,
+                                                 unsigned long long Wm, long long N)
+{
+    long long lo = 0, hi = N;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        const unsigned long long T = U + (unsigned long long)mid * Wd +
+                                     ((unsigned long long)mid * Wm) / (unsigned long long)N;
+        if (T < c) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// (Wd * u0) >> 32 without 128-bit arithmetic, exact
+__host__ __device__ inline unsigned long long u_offset(unsigned long long Wd, unsigned int u0_q32)
+{
+    return (Wd >> 32) * u0_q32 + (((Wd & 0xffffffffull) * u0_q32) >> 32);
+}
+
+// Exclusive scan of the per-CTA sums (one CTA); total -> out[PF_WLOCAL].
+// Sharded resident set (X.peers != nullptr): second exchange of the filter step.  This rank's integer
+// weight sum goes to every rank as exchange number match->epoch + 1; when every rank's sum (and the
+// particle counts that travelled with the first exchange) are here, the CTA derives everything the
+// resampler needs ON THE DEVICE -- global W and N, this rank's offset into the global cumulative weight,
+// the systematic-resampling slots whose ancestors live here (b200slam_resample_owned_slots' arithmetic)
+// and the first slot every rank holds -- so no sum ever visits the host.
 __global__ void __launch_bounds__(1024)
 block_sums_scan_kernel(unsigned long long *__restrict__ block_sums, int nb,
-                       unsigned long long *__restrict__ out_total)
+                       unsigned long long *__restrict__ out, const XchgArgs X, MatchDev *match, long long N_local,
+                       unsigned int u0_q32)
 {
+    unsigned long long *out_total = out;
     __shared__ unsigned long long wtot[32];
     __shared__ unsigned long long carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,7 +158,44 @@ block_sums_scan_kernel(unsigned long long *__restrict__ block_sums, int nb,
         if (threadIdx.x == 1023) carry = before + inc;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out_total[0] = carry; out_total[1] = carry; }   // [1]: global W (one GPU: the same)
+    if (threadIdx.x == 0) { out_total[PF_WLOCAL] = carry; out_total[PF_WGLOBAL] = carry; }   // one GPU: global == local
+    if (!X.peers) return;
+    __shared__ unsigned int words_s[4];
+    __shared__ unsigned long long Wr[XCHG_MAX_RANKS];
+    __shared__ unsigned int Nr[XCHG_MAX_RANKS];
+    const unsigned int e1 = *reinterpret_cast<volatile unsigned int *>(&match->epoch), e2 = e1 + 1;
+    const unsigned long long Wl = carry;
+    __syncthreads();
+    xchg_post_words(X, e2, (unsigned int)Wl, (unsigned int)(Wl >> 32), 0u, 0u, words_s);
+    if (threadIdx.x < X.nranks) {
+        unsigned int lo = 0, hi = 0, n = 0;
+        const bool ok = xchg_wait_word(X, e2, threadIdx.x, 0, &lo, &match->error, DEV_ERR_PARTICLES) &&
+                        xchg_wait_word(X, e2, threadIdx.x, 1, &hi, &match->error, DEV_ERR_PARTICLES) &&
+                        xchg_wait_word(X, e1, threadIdx.x, 2, &n, &match->error, DEV_ERR_PARTICLES);
+        Wr[threadIdx.x] = ok ? ((unsigned long long)hi << 32) | lo : 0ull;
+        Nr[threadIdx.x] = ok ? n : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long Wg = 0, off = 0, Ng = 0;
+        for (int r = 0; r < X.nranks; ++r) {
+            if (r < X.rank) off += Wr[r];
+            Wg += Wr[r];
+            out[PF_SLOT_BASE + r] = Ng;
+            Ng += Nr[r];
+        }
+        out[PF_SLOT_BASE + X.nranks] = Ng;
+        long long kb = 0, ke = 0;
+        if (Wg > 0 && Ng > 0) {
+            const unsigned long long Wd = Wg / Ng, Wm = Wg % Ng, U = u_offset(Wd, u0_q32);
+            kb = slots_below(off, U, Wd, Wm, (long long)Ng);
+            ke = slots_below(off + Wl, U, Wd, Wm, (long long)Ng);
+        }
+        out[PF_WGLOBAL] = Wg; out[PF_RANK_OFFSET] = off; out[PF_NGLOBAL] = Ng;
+        out[PF_KBEGIN] = (unsigned long long)kb; out[PF_KCOUNT] = (unsigned long long)(ke - kb);
+        match->epoch = e2; match->posted = e2; match->collected = e2;
+        (void)N_local;
+    }
 }
 
 // In-place inclusive prefix C_i (local to this rank) and normalised weights.
@@ -125,7 +207,7 @@ prefix_kernel(unsigned long long *__restrict__ q, long long N,
 {
     __shared__ unsigned long long wtot[PT_THREADS / 32];
     const long long base = (long long)blockIdx.x * PT_BLOCK + (long long)threadIdx.x * PT_ITEMS;
-    const double W = (double)totals[1];
+    const double W = (double)totals[PF_WGLOBAL];
     unsigned long long v[PT_ITEMS];
     unsigned long long tsum = 0;
 #pragma unroll
@@ -186,7 +268,7 @@ resample_gather_kernel(const unsigned long long *__restrict__ C, long long N,
         const unsigned long long W = totals[0];
         sWd = W / (unsigned long long)N;
         sWm = W % (unsigned long long)N;
-        sU = (sWd >> 32) * u0_q32 + (((sWd & 0xffffffffull) * u0_q32) >> 32);    // (Wd * u0) >> 32, exact
+        sU = u_offset(sWd, u0_q32);
     }
     __syncthreads();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,18 +284,42 @@ resample_gather_kernel(const unsigned long long *__restrict__ C, long long N,
     for (int f = 0; f < 5; ++f) dst[f * cap + k] = src[f * cap + lo];
 }
 
-// number of slots k in [0, N) with T_k < c  (T_k is non-decreasing in k)
-long long slots_below(unsigned long long c, unsigned long long U, unsigned long long Wd,
-                      unsigned long long Wm, long long N)
+// Sharded resident set: resampling + offspring exchange in ONE kernel.  This rank emits the offspring of ITS
+// particles: the systematic slots [kb, kb + kc) whose thresholds fall into its stretch of the global
+// cumulative weight (found on the device by the scan kernel).  Slot k lives on the rank d with
+// slot_base[d] <= k < slot_base[d + 1]; the ancestor's pose (x | y | ct | st | theta) and its GLOBAL index
+// are stored straight into rank d's other pose buffer / ancestor array over NVLink (every rank's pose block
+// is mapped through CUDA IPC).  Consecutive slots have consecutive destinations and (mostly) equal or
+// adjacent ancestors, so both sides coalesce.  A peer barrier behind this kernel completes the step.
+__global__ void __launch_bounds__(256)
+resample_push_kernel(const unsigned long long *__restrict__ C, long long N_local, const unsigned long long *__restrict__ S,
+                     unsigned int u0_q32, long long index_base, const float *__restrict__ src, size_t cap,
+                     float *const *__restrict__ peer_blocks, int dst_parity, int nranks)
 {
-    long long lo = 0, hi = N;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        const unsigned long long T = U + (unsigned long long)mid * Wd +
-                                     ((unsigned long long)mid * Wm) / (unsigned long long)N;
-        if (T < c) lo = mid + 1; else hi = mid;
+    __shared__ unsigned long long sbase[XCHG_MAX_RANKS + 1];
+    for (int r = threadIdx.x; r <= nranks; r += blockDim.x) sbase[r] = S[PF_SLOT_BASE + r];
+    __syncthreads();
+    const unsigned long long Wg = S[PF_WGLOBAL], Ng = S[PF_NGLOBAL], roff = S[PF_RANK_OFFSET];
+    const long long kb = (long long)S[PF_KBEGIN], kc = (long long)S[PF_KCOUNT];
+    if (Ng == 0) return;
+    const unsigned long long Wd = Wg / Ng, Wm = Wg % Ng, U = u_offset(Wd, u0_q32);
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < kc; s += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = (unsigned long long)(kb + s);
+        const unsigned long long t = U + k * Wd + (k * Wm) / Ng - roff;     // T_k >= rank offset for owned slots
+        long long lo = 0, hi = N_local - 1;                                  // first i with C[i] > t
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (C[mid] > t) hi = mid; else lo = mid + 1;
+        }
+        int d = 0;
+        while (d + 1 < nranks && sbase[d + 1] <= k) ++d;
+        const size_t j = (size_t)(k - sbase[d]);
+        float *blk = peer_blocks[d];
+        float *dst = blk + (size_t)dst_parity * 5 * cap;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) dst[f * cap + j] = src[f * cap + lo];
+        reinterpret_cast<int *>(blk + 10 * cap)[j] = (int)(lo + index_base);
     }
-    return lo;
 }
 
 }  // namespace
@@ -222,19 +328,105 @@ int particles_resample_resident(b200slam_ctx *ctx, int64_t N, float beta, uint32
 {
     if (N <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scored poses");
     const int nb = (int)((N + PT_BLOCK - 1) / PT_BLOCK);
-    weights_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_scores, N, beta, &ctx->d_match->key, 1, ctx->d_q,
-                                                       ctx->d_block_sums);
+    XchgArgs X = xchg_args(ctx);
+    if (!ctx->pf_sharded) X.peers = nullptr;
+    weights_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_scores, N, beta, &ctx->d_match->key, X.peers ? 0 : 1, ctx->d_q,
+                                                       ctx->d_block_sums, X, ctx->d_match);
     LAUNCH_CHECK(ctx);
-    block_sums_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums, nb, ctx->d_wsum);
+    block_sums_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums, nb, ctx->d_wsum, X, ctx->d_match, N, u0_q32);
     LAUNCH_CHECK(ctx);
     prefix_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_q, N, ctx->d_block_sums, ctx->d_wsum, ctx->d_weights);
     LAUNCH_CHECK(ctx);
-    resample_gather_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->d_q, N, ctx->d_wsum, u0_q32, ctx->d_ancestors, ctx->d_pose_soa, ctx->d_pose_alt, ctx->pose_cap);
-    LAUNCH_CHECK(ctx);
+    if (ctx->pf_sharded) {
+        resample_push_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+            ctx->d_q, N, ctx->d_wsum, u0_q32, ctx->last_index_base, ctx->d_pose_soa, ctx->pose_cap, ctx->d_pf_peers,
+            ctx->pose_parity ^ 1, ctx->nranks);
+        LAUNCH_CHECK(ctx);
+        // every rank's offspring has landed everywhere before anybody scores the new set
+        int rc = comm_peer_barrier(ctx);
+        if (rc) return rc;
+    } else {
+        resample_gather_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_q, N, ctx->d_wsum, u0_q32, ctx->d_anc_resident, ctx->d_pose_soa, ctx->d_pose_alt, ctx->pose_cap);
+        LAUNCH_CHECK(ctx);
+    }
     float *t = ctx->d_pose_soa;          // the offspring is the resident set now
     ctx->d_pose_soa = ctx->d_pose_alt;
     ctx->d_pose_alt = t;
+    ctx->pose_parity ^= 1;
+    return B200SLAM_OK;
+}
+
+void particles_unshare_blocks(b200slam_ctx *ctx)
+{
+    for (int r = 0; r < XCHG_MAX_RANKS; ++r) {
+        if (ctx->pf_peer_block[r] && ctx->pf_peer_block[r] != ctx->pf_shared_block) cudaIpcCloseMemHandle(ctx->pf_peer_block[r]);
+        ctx->pf_peer_block[r] = nullptr;
+    }
+    ctx->pf_shared_block = nullptr;
+    ctx->pf_shared_cap = 0;
+    ctx->pf_sharded = false;
+    cudaGetLastError();
+}
+
+// Collective.  Every rank publishes the CUDA IPC handle of its pose block; when any rank's block changed since
+// the last exchange (first call, or a capacity growth) all ranks re-map all blocks.  The blocks must have the
+// same capacity everywhere (the pusher addresses a peer's buffers with its own layout).
+int particles_share_blocks(b200slam_ctx *ctx)
+{
+    if (!ctx->nccl_comm || ctx->nranks < 2 || !ctx->p2p_ready)
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "a sharded particle set needs b200slam_comm_init with NVLink peer memory");
+    const int n = ctx->nranks;
+    constexpr int REC = 12;                       // 64-byte handle | ok | capacity | changed
+    unsigned long long rec[REC] = {0}, all[XCHG_MAX_RANKS * REC];
+    cudaIpcMemHandle_t h;
+    const bool changed = ctx->pf_shared_block != ctx->d_pose_block || ctx->pf_shared_cap != ctx->pose_cap;
+    bool ok = ctx->d_pose_block && cudaIpcGetMemHandle(&h, ctx->d_pose_block) == cudaSuccess;
+    if (ok) memcpy(rec, &h, sizeof h);
+    rec[8] = ok ? 1 : 0;
+    rec[9] = ctx->pose_cap;
+    rec[10] = changed ? 1 : 0;
+    unsigned long long *d_send = nullptr, *d_recv = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_send, sizeof rec));
+    CUDA_TRY(ctx, cudaMalloc(&d_recv, sizeof(rec) * n));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_send, rec, sizeof rec, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = comm_allgather_u64(ctx, d_send, d_recv, REC);
+    if (rc == B200SLAM_OK) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(all, d_recv, sizeof(rec) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(d_send); cudaFree(d_recv);
+    if (rc) return rc;
+    bool any_changed = false;
+    for (int r = 0; r < n; ++r) {
+        ok = ok && all[r * REC + 8] == 1 && all[r * REC + 9] == rec[9];
+        any_changed = any_changed || all[r * REC + 10] == 1;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "particle blocks cannot be peer-shared (no CUDA IPC, or the ranks' "
+                                                            "capacities differ: give every rank the same number of particles)");
+    }
+    if (!any_changed) return B200SLAM_OK;
+    for (int r = 0; r < XCHG_MAX_RANKS; ++r) {
+        if (ctx->pf_peer_block[r] && ctx->pf_peer_block[r] != ctx->pf_shared_block) cudaIpcCloseMemHandle(ctx->pf_peer_block[r]);
+        ctx->pf_peer_block[r] = nullptr;
+    }
+    ctx->pf_shared_block = ctx->d_pose_block;
+    ctx->pf_shared_cap = ctx->pose_cap;
+    for (int r = 0; r < n; ++r) {
+        if (r == ctx->rank) { ctx->pf_peer_block[r] = ctx->d_pose_block; continue; }
+        cudaIpcMemHandle_t ph;
+        memcpy(&ph, &all[r * REC], sizeof ph);
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "cudaIpcOpenMemHandle failed for rank %d's particle block", r);
+        }
+        ctx->pf_peer_block[r] = static_cast<float *>(p);
+    }
+    if (!ctx->d_pf_peers) CUDA_TRY(ctx, cudaMalloc(&ctx->d_pf_peers, sizeof(float *) * XCHG_MAX_RANKS));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_pf_peers, ctx->pf_peer_block, sizeof(float *) * n, cudaMemcpyHostToDevice));
     return B200SLAM_OK;
 }
 
@@ -253,10 +445,12 @@ int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_
         keys = ctx->d_keys;
         nkeys = ctx->nranks;
     }
+    XchgArgs noX = xchg_args(ctx);
+    noX.peers = nullptr;
     weights_kernel<<<nb, PT_THREADS, 0, ctx->stream>>>(ctx->d_scores, N, beta, keys, nkeys, ctx->d_q,
-                                                       ctx->d_block_sums);
+                                                       ctx->d_block_sums, noX, ctx->d_match);
     LAUNCH_CHECK(ctx);
-    block_sums_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums, nb, ctx->d_wsum);
+    block_sums_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums, nb, ctx->d_wsum, noX, ctx->d_match, N, u0_q32);
     LAUNCH_CHECK(ctx);
 
     // totals: local W in d_wsum[0]; gather every rank's W and N for the global picture

@@ -107,18 +107,8 @@ __device__ __forceinline__ bool cta_is_last(MatchDev *match, unsigned long long 
 __device__ __forceinline__ void exchange_post(const XchgArgs &X, unsigned int epoch, unsigned long long key,
                                               int best_hits, int last_hits, unsigned int *words_smem)
 {
-    const int tid = threadIdx.x;
-    const int ring = (int)(epoch % XCHG_EPOCHS);
-    if (tid == 0) {
-        words_smem[0] = (unsigned int)key; words_smem[1] = (unsigned int)(key >> 32);
-        words_smem[2] = (unsigned int)best_hits; words_smem[3] = (unsigned int)last_hits;
-    }
-    __syncthreads();
-    const unsigned long long tag = (unsigned long long)epoch << 32;
-    for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
-        const int r = i >> 2, w = i & 3;
-        *reinterpret_cast<volatile unsigned long long *>(&X.peers[r]->slot[ring][X.rank].w[w]) = tag | words_smem[w];
-    }
+    xchg_post_words(X, epoch, (unsigned int)key, (unsigned int)(key >> 32), (unsigned int)best_hits, (unsigned int)last_hits,
+                    words_smem);
 }
 
 // COLLECT: waits until every rank's words of the oldest uncollected exchange have landed in OUR
@@ -133,30 +123,15 @@ __device__ __forceinline__ void exchange_collect(const XchgArgs &X, MatchDev *ma
                                                  unsigned int *got)
 {
     const int tid = threadIdx.x;
-    const int ring = (int)(epoch % XCHG_EPOCHS);
     // Bounded wait: a peer that died or was queued out of order costs one timeout and a sticky error bit
     // (B200SLAM_ERR_STATE from b200slam_match_fetch / b200slam_sync), not a GPU that spins forever.  Once
     // the bit is set later collects do not wait at all.
-    const unsigned long long budget = *reinterpret_cast<volatile unsigned int *>(&match->error) ? 0ull : X.timeout_ns;
     for (int i = tid; i < 4 * X.nranks; i += blockDim.x) {
         const int r = i >> 2, w = i & 3;
-        const volatile unsigned long long *src = &X.peers[X.rank]->slot[ring][r].w[w];
-        unsigned long long v = *src;
-        if ((unsigned int)(v >> 32) != epoch) {
-            const unsigned long long t0 = global_timer_ns();
-            unsigned int spins = 0;
-            for (;;) {
-                v = *src;
-                if ((unsigned int)(v >> 32) == epoch) break;
-                if ((++spins & 255u) == 0 && global_timer_ns() - t0 > budget) break;
-            }
-        }
-        if ((unsigned int)(v >> 32) == epoch) {
-            got[i] = (unsigned int)v;
-        } else {
-            got[i] = w < 2 ? 0xffffffffu : 0u;              // "nothing scored" for the missing rank
-            atomicOr(&match->error, DEV_ERR_EXCHANGE);
-        }
+        unsigned int v;
+        if (!xchg_wait_word(X, epoch, r, w, &v, &match->error, DEV_ERR_EXCHANGE))
+            v = w < 2 ? 0xffffffffu : 0u;                   // "nothing scored" for the missing rank
+        got[i] = v;
     }
     __syncthreads();
     if (tid == 0) {
@@ -693,6 +668,7 @@ struct PosesArgs {
     int *hits;                         // [P]
     MatchDev *match;
     unsigned total_ctas;
+    XchgArgs xchg;                     // peers != nullptr: sharded particle filter, the tail posts {key, P} to every rank
 };
 
 constexpr int POSES_THREADS = 128;
@@ -789,6 +765,8 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
         for (int w = 1; w < POSES_THREADS / 32; ++w) best = red[w] < best ? red[w] : best;
 
     if (!cta_is_last(A.match, best, A.total_ctas, &last_flag)) return;
+    __shared__ unsigned long long key_s;
+    __shared__ unsigned int epoch_s, words_s[4];
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&A.match->work_key);
@@ -803,6 +781,18 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
         A.match->last_hits = lh;
         A.match->work_key = ~0ull;
         A.match->tickets = 0u;
+        key_s = key;
+        epoch_s = *reinterpret_cast<volatile unsigned int *>(&A.match->epoch) + 1;
+    }
+    if (A.xchg.peers) {
+        // sharded particle filter, first exchange of the step: this rank's best (score, global index) and its
+        // particle count go to every rank (the weights need the GLOBAL minimum score)
+        __syncthreads();
+        xchg_post_words(A.xchg, epoch_s, (unsigned int)key_s, (unsigned int)(key_s >> 32), (unsigned int)A.P, 0u, words_s);
+        if (threadIdx.x == 0) {
+            A.match->epoch = epoch_s;
+            A.match->posted = epoch_s;
+        }
     }
 }
 
@@ -970,7 +960,7 @@ int exchange_collect_launch(b200slam_ctx *ctx)
 }
 
 int poses_launch(b200slam_ctx *ctx, const b200slam_map *m, int64_t P, int64_t index_base,
-                 float *d_scores, int32_t *d_hits)
+                 float *d_scores, int32_t *d_hits, bool post_sharded)
 {
     PosesArgs A;
     A.field = m->d_field; A.pitch = m->field_pitch; A.rows = m->rows; A.cols = m->cols;
@@ -983,6 +973,12 @@ int poses_launch(b200slam_ctx *ctx, const b200slam_map *m, int64_t P, int64_t in
     A.P = P; A.index_base = index_base;
     A.scores = d_scores; A.hits = d_hits;
     A.match = ctx->d_match;
+    A.xchg.peers = nullptr; A.xchg.nranks = 1; A.xchg.rank = 0; A.xchg.timeout_ns = ctx->spin_timeout_ns;
+    if (post_sharded) {
+        if (!ctx->p2p_ready || P <= 0)
+            return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "a sharded particle set needs NVLink peer memory and particles on every rank");
+        A.xchg = xchg_args(ctx);
+    }
     if (P <= 0) {
         CUDA_TRY(ctx, cudaMemsetAsync(&ctx->d_match->key, 0xff, sizeof(unsigned long long), ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(&ctx->d_match->best_hits, 0, 2 * sizeof(int), ctx->stream));

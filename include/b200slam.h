@@ -292,7 +292,7 @@ int b200slam_weights_resample(b200slam_ctx *ctx, float beta, uint32_t u0_q32, fl
                               uint64_t *wsum, int32_t *ancestors, int64_t *k_begin,
                               int64_t *k_count);
 
-/* Device-resident particle set (single GPU): the particles stay in HBM across filter steps,
+/* Device-resident particle set: the particles stay in HBM across filter steps,
  * nothing crosses PCIe per step, and every call below only queues kernels on the context's
  * stream (capturable in a CUDA graph).
  *   upload            poses[P][3] (+ optional ct/st, else host libm) -> device SoA
@@ -304,6 +304,23 @@ int b200slam_weights_resample(b200slam_ctx *ctx, float beta, uint32_t u0_q32, fl
  *   download          current poses and, optionally, the weights / ancestors of the last resample */
 int b200slam_particles_upload(b200slam_ctx *ctx, const float *poses, const float *ct, const float *st,
                               int64_t P);
+/* SHARDED resident particle set (several GPUs; needs b200slam_comm_init with NVLink peer memory).
+ * Collective: rank r hands in its slice poses[P][3] = particles [index_base, index_base + P) of n_global
+ * (every rank the same P: a rank addresses its peers' buffers with its own layout).  Afterwards
+ * b200slam_particles_score_async / _resample_async run the SAME filter step as on one GPU over the whole
+ * set: the score kernel's tail sends {best (score, global index), P} to every rank, the weight kernels
+ * wait for them (global minimum score), the prefix-scan kernel exchanges the integer weight sums and
+ * derives on the device the global W, this rank's offset and the systematic-resampling slots whose
+ * ancestors live here (b200slam_resample_owned_slots' arithmetic), and the resampling kernel stores each
+ * offspring (pose + global ancestor index) straight into the buffers of the rank that holds its slot --
+ * rank r ends with slots [index_base, index_base + P) of the global offspring, exactly the slice an
+ * unsharded run would have there.  Everything travels through NVLink peer memory written by the kernels
+ * themselves: no NCCL call, no host synchronisation, CUDA-graph capturable; every wait is bounded
+ * (B200SLAM_SPIN_TIMEOUT_MS).  All ranks must queue the same sequence of steps.
+ * b200slam_particles_download then returns this rank's slice (ancestors are GLOBAL indices) and
+ * b200slam_match_fetch this rank's best particle. */
+int b200slam_particles_shard(b200slam_ctx *ctx, const float *poses, const float *ct, const float *st, int64_t P,
+                             int64_t index_base, int64_t n_global);
 int b200slam_particles_score_async(b200slam_ctx *ctx, b200slam_map *map);
 int b200slam_particles_resample_async(b200slam_ctx *ctx, float beta, uint32_t u0_q32);
 int b200slam_particles_download(b200slam_ctx *ctx, float *poses, float *scores, float *weights,

@@ -185,8 +185,92 @@ def run_gpu(mod, synth):
     check(parts[0][0] == 0 and sum(p[1] for p in parts) == P, "owned slot ranges do not tile [0, N)")
     allanc = np.array([a for p in parts for a in p[2]], np.int32)
     check(np.array_equal(allanc, pb["oanc"]), "sharded ancestors differ from the unsharded oracle")
+    # ---- SHARDED device-resident particle filter: sums and offspring through NVLink peer memory, no host
+    # round trip; every rank ends with ITS slots of the unsharded oracle's offspring (VERDICT r01 missing #1)
+    orc = pb["orc"]
+    poses0 = pb["poses"]
+    # oracle: two filter steps of the WHOLE set on the CPU
+    want = []
+    cur = poses0
+    for _ in range(2):
+        _, sc, _ = orc.score_poses(pb["om"], w["scan_x"], w["scan_y"], cur)
+        ow, _, oW, oanc = orc.weights_resample(sc, pb["beta"], pb["u0"])
+        cur = cur[oanc]
+        want.append((sc, ow, oanc, cur))
+    sl = slice(pbeg, pend)
+    for use_graph in (False, True):
+        ctx.particles_shard(poses0[sl], pbeg, P)
+        if use_graph:
+            # size every scratch buffer with one un-captured pair of steps, then reset the set
+            for _ in range(2):
+                ctx.particles_score_async(m); ctx.particles_resample_async(pb["beta"], pb["u0"])
+            ctx.sync()
+            ctx.particles_shard(poses0[sl], pbeg, P)
+            ctx.graph_begin()
+            for _ in range(2):
+                ctx.particles_score_async(m); ctx.particles_resample_async(pb["beta"], pb["u0"])
+            g = ctx.graph_end()
+            ctx.graph_launch(g)
+            steps_done = 2
+        else:
+            ctx.particles_score_async(m); ctx.particles_resample_async(pb["beta"], pb["u0"])
+            steps_done = 1
+        for extra in range(2 - steps_done + 1):
+            gp, gsc, gw, ganc = ctx.particles_download()
+            sc, ow, oanc, cur = want[steps_done - 1]
+            tag = f"sharded filter ({'graph' if use_graph else 'eager'}, step {steps_done})"
+            check(np.array_equal(ganc, oanc[sl]), f"{tag}: ancestors differ from the unsharded oracle")
+            check(np.array_equal(gp.view(np.uint32), cur[sl].view(np.uint32)), f"{tag}: offspring poses differ")
+            check(np.array_equal(gsc.view(np.uint32), sc[sl].view(np.uint32)), f"{tag}: scores differ")
+            check(np.array_equal(gw.view(np.uint32), ow[sl].view(np.uint32)), f"{tag}: normalised weights differ")
+            if steps_done == 2:
+                break
+            ctx.particles_score_async(m); ctx.particles_resample_async(pb["beta"], pb["u0"])
+            steps_done += 1
+        if use_graph:
+            # replays keep counting (barrier and exchange epochs live on the device): two more graph launches
+            # = steps 3-6 must equal four more oracle steps
+            cur4 = want[1][3]
+            for _ in range(4):
+                _, sc4, _ = orc.score_poses(pb["om"], w["scan_x"], w["scan_y"], cur4)
+                _, _, _, anc4 = orc.weights_resample(sc4, pb["beta"], pb["u0"])
+                cur4 = cur4[anc4]
+            ctx.graph_launch(g); ctx.graph_launch(g)
+            gp, _, _, ganc = ctx.particles_download()
+            check(np.array_equal(ganc, anc4[sl]) and np.array_equal(gp.view(np.uint32), cur4[sl].view(np.uint32)),
+                  "sharded filter: graph replays drift from the oracle")
+            ctx.graph_destroy(g)
+    dist.barrier()
     m.close()
     ctx.close()
+    # ---- a rank that never shows up: the bounded device-side wait gives up and the call reports it ------
+    os.environ["B200SLAM_SPIN_TIMEOUT_MS"] = "300"
+    c2 = mod.Context(local_rank)
+    uid = [c2.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    c2.comm_init(world, rank, uid[0])
+    m2 = c2.new_map(rows, cols)
+    m2.set_geometry(w["pixel"], w["top_left"]).upload_occupancy(w["occ"]).edt()
+    c2.scan_upload(w["scan_x"], w["scan_y"])
+    ok_first = c2.score_lattice_rows(m2, w["pose0"], w["step"], n, rb, re, allreduce=True)
+    check(ok_first.best_index == o.best_index, "fresh communicator: winner differs")
+    if rank == 0:
+        import time
+        t0 = time.perf_counter()
+        try:
+            c2.score_lattice_rows(m2, w["pose0"], w["step"], n, rb, re, allreduce=True)     # the peers never post
+            check(False, "a match whose peers never posted returned success")
+        except mod.B200SlamError as e:
+            check(e.code == mod.ERR_STATE and time.perf_counter() - t0 < 20, f"timeout not reported as ERR_STATE quickly: {e}")
+        try:
+            c2.sync()
+            check(False, "b200slam_sync did not report the sticky device error")
+        except mod.B200SlamError as e:
+            check(e.code == mod.ERR_STATE, f"sync: {e}")
+    dist.barrier()
+    m2.close()
+    c2.close()
+    os.environ.pop("B200SLAM_SPIN_TIMEOUT_MS", None)
 
 
 def main():
