@@ -66,6 +66,14 @@ L2_BYTES = 126 * 1024 * 1024
 ISSUE_FLOOR_LANE_INSTR_PER_EVAL = {"lattice_rr2": 34.0 / 16.0, "lattice": 3.0, "poses": 14.0}
 
 
+def lattice_floor(n, step, pixel):
+    """Floor of the kernel variant the launcher picks for this lattice: row reuse (9 gathers + 9 address ops + 16
+    adds per 16 candidates) when the ty step is half a pixel and the lattice is large enough for 64 x 64 tiles,
+    else one gather + one offset + one address op + one add... per candidate (3 with the loop's shared work)."""
+    rr = abs(float(step[1]) / float(pixel) * 2.0 - 1.0) < 1e-3 and n[1] >= 64 and n[2] >= 64
+    return ("lattice_rr2" if rr else "lattice"), ISSUE_FLOOR_LANE_INSTR_PER_EVAL["lattice_rr2" if rr else "lattice"]
+
+
 # ----------------------------------------------------------------------------------------
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -539,6 +547,7 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
             ctx.set_match_mode(policy)
             if not args.no_pipeline:
                 ctx_e = mod.Context(local_rank)
+                ctx_e.set_match_mode(policy)                  # the transform reads the same scheduling hint
                 for i in range(ring):                         # warm the second context's kernels
                     ctx_e._check(ctx_e.L.b200slam_map_edt(ctx_e.h, maps[i].h, 10.0))
                 ctx_e.sync()
@@ -704,7 +713,7 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
         edt_bytes = 8.0 * cells                                              # 8 B / cell
         lat_bytes = 4.0 * evals_per_rank + 4.0 * nth * ntx * nty + 8.0 * nbeams   # 4 B / eval + 4 B / pose
         issue_peak = 4.0 * info["sm_count"] * sm_mhz * 1e6 / 1e9                 # G warp-instructions / s
-        floor = ISSUE_FLOOR_LANE_INSTR_PER_EVAL["lattice_rr2"]
+        floor_kind, floor = lattice_floor(w["n"], w["step"], w["pixel"])
         alg_winstr = floor * evals_per_rank / 32.0
         meas_winstr = ncu_counter(f"lattice_kernel:{workload}:warp_instructions")
         roofs = {
@@ -715,7 +724,7 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
             "lattice_kernel": {"bound": "issue", "achieved": alg_winstr / (lat_ms * 1e-3) / 1e9, "peak": issue_peak,
                                "unit": "Gwarp-inst/s", "ms": lat_ms, "ms_eager_alone": lat_ms_avg,
                                "algorithmic_warp_instructions": alg_winstr,
-                               "floor_lane_instr_per_eval": floor,
+                               "floor_lane_instr_per_eval": floor, "floor_kind": floor_kind,
                                "measured_warp_instructions": meas_winstr,
                                "measured_lane_instr_per_eval": (meas_winstr * 32.0 / evals_per_rank) if meas_winstr else None,
                                "issue_utilisation": (meas_winstr / (lat_ms * 1e-3) / 1e9 / issue_peak) if meas_winstr else None,

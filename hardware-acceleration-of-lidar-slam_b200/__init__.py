@@ -18,7 +18,8 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "libb200slam.so")
+# B200SLAM_LIB: development aid (A/B of two builds of the same ABI on the GPU box); never a fallback
+LIB_PATH = os.environ.get("B200SLAM_LIB") or os.path.join(PKG_DIR, "libb200slam.so")
 DROPIN_PATH = os.path.join(PKG_DIR, "libb200slam_dropin.so")
 HEADER_PATH = os.path.join(REPO_ROOT, "include", "b200slam.h")
 

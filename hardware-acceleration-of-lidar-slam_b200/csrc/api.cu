@@ -189,9 +189,9 @@ int b200slam_map_create(b200slam_ctx *ctx, int rows, int cols, b200slam_map **ou
     cudaError_t e = cudaMalloc(&m->d_occ, sizeof(int32_t) * (size_t)m->occ_pitch * rows);
     if (e == cudaSuccess)
         e = cudaMalloc(&m->d_field_alloc,
-                       sizeof(float) * ((size_t)m->field_pitch * rows + B200SLAM_FIELD_PAD));
+                       sizeof(float) * ((size_t)m->field_pitch * rows + field_pad_floats(m->field_pitch)));
     if (e == cudaSuccess)
-        e = cudaMemsetAsync(m->d_field_alloc, 0, sizeof(float) * B200SLAM_FIELD_PAD, ctx->stream);
+        e = cudaMemsetAsync(m->d_field_alloc, 0, sizeof(float) * field_pad_floats(m->field_pitch), ctx->stream);
     if (e != cudaSuccess) {
         cudaFree(m->d_occ);
         cudaFree(m->d_field_alloc);
@@ -199,7 +199,7 @@ int b200slam_map_create(b200slam_ctx *ctx, int rows, int cols, b200slam_map **ou
         return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "map alloc %d x %d -> %s", rows, cols,
                                   cudaGetErrorString(e));
     }
-    m->d_field = m->d_field_alloc + B200SLAM_FIELD_PAD;
+    m->d_field = m->d_field_alloc + field_pad_floats(m->field_pitch);
     *out = m;
     return B200SLAM_OK;
 }

@@ -365,7 +365,7 @@ int b200slam_map_edt_sharded(b200slam_ctx *ctx, b200slam_map *map, float max_dis
     float *peers[7];
     int np = 0;
     for (int r = 0; r < ctx->nranks; ++r)
-        if (r != ctx->rank) peers[np++] = map->peer_alloc[r] + B200SLAM_FIELD_PAD;
+        if (r != ctx->rank) peers[np++] = map->peer_alloc[r] + field_pad_floats(map->field_pitch);
     // nobody may still be reading the old field of a peer when its new rows arrive
     int rc = comm_peer_barrier(ctx);
     if (rc) return rc;

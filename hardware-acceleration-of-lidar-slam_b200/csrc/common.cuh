@@ -9,9 +9,12 @@
 
 #include "../../include/b200slam.h"
 
-// Cells of padding in front of every distance field: field[-1] is a zero the scoring
-// kernels read for out-of-bounds beams (adding +0.0f leaves a score unchanged).
-#define B200SLAM_FIELD_PAD 32
+// Rows of zeros in front of every distance field.  field[-1] is a zero the scoring kernels read for
+// out-of-bounds beams (adding +0.0f leaves a score unchanged); the row-reuse matcher reads K <= 9 consecutive
+// rows of one column per beam and sends an invalid beam to index -(8 * pitch + 1), from where all of them
+// land in this region -- no select on the row stride, no branch.
+#define B200SLAM_FIELD_PAD_ROWS 9
+inline size_t field_pad_floats(int pitch) { return (size_t)B200SLAM_FIELD_PAD_ROWS * (size_t)pitch; }
 #define LAT_SLOTS 4
 
 struct b200slam_map {
@@ -111,6 +114,7 @@ struct b200slam_ctx {
     uint64_t launches = 0;
     bool use_pdl = true;         // programmatic dependent launch between consecutive scan-matching kernels
     bool prev_launch_was_lattice = false;   // the last kernel queued on the stream was a scan-matching kernel
+    bool prev_launch_was_edt = false;       // ... was a distance transform (the next transform may start under its tail)
     int match_mode = B200SLAM_MATCH_LATENCY; // tile-shape policy of the lattice kernel (b200slam_set_match_mode)
 
     // scan (sensor frame), device resident
@@ -236,6 +240,7 @@ int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
     do {                                                                                     \
         (ctx)->launches++;                                                                   \
         (ctx)->prev_launch_was_lattice = false;                                              \
+        (ctx)->prev_launch_was_edt = false;                                                  \
         CUDA_TRY((ctx), cudaGetLastError());                                                 \
     } while (0)
 

@@ -36,6 +36,7 @@
 
 #include <climits>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -110,25 +111,36 @@ struct EdtPeers {
     long long delta[7];
     int n;                       // number of EXTRA destinations (0 = this GPU only)
 };
-template <int R, bool CHECK, bool MULTI>
-__device__ __forceinline__ void edt_emit_rows(const uint32_t (&win)[3 * R], const unsigned char *lut,
-                                              uint32_t lane4, uint32_t clampv, unsigned char *pb,
-                                              uint32_t pitch_bytes, int rows_left, bool s0, bool s1,
+template <int R>
+struct EdtRowMask {                      // one bit per window row (3R rows)
+    using type = typename std::conditional<(3 * R > 32), unsigned long long, uint32_t>::type;
+};
+
+// SKIP: rowmask has bit i set <=> window row i has an occupied cell within this warp's reach (warp uniform).
+// An output row whose 2R+1 window rows are all empty is max_dist everywhere: no arithmetic at all.  When every
+// window row is occupied (dense maps) the caller takes the SKIP = false copy, which has no branches.
+template <int R, bool CHECK, bool MULTI, bool SKIP>
+__device__ __forceinline__ void edt_emit_rows(const uint32_t (&win)[3 * R], typename EdtRowMask<R>::type rowmask,
+                                              const unsigned char *lut, uint32_t lane4, uint32_t clampv, float max_dist,
+                                              unsigned char *pb, uint32_t pitch_bytes, int rows_left, bool s0, bool s1,
                                               const EdtPeers &peers)
 {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        uint32_t a0 = win[r + R];
-        uint32_t a1 = 0xffffffffu;
+        float f0 = max_dist, f1 = max_dist;
+        if (!SKIP || ((uint32_t)(rowmask >> r) & ((1u << (2 * R + 1)) - 1u))) {           // warp uniform
+            uint32_t a0 = win[r + R];
+            uint32_t a1 = 0xffffffffu;
 #pragma unroll
-        for (int d = 1; d <= R; ++d) {
-            const uint32_t k = (uint32_t)(EDT_SCALE * d * d) * 0x00010001u;
-            a0 = __viaddmin_u16x2(win[r + R - d], k, a0);
-            a1 = __viaddmin_u16x2(win[r + R + d], k, a1);
+            for (int d = 1; d <= R; ++d) {
+                const uint32_t k = (uint32_t)(EDT_SCALE * d * d) * 0x00010001u;
+                a0 = __viaddmin_u16x2(win[r + R - d], k, a0);
+                a1 = __viaddmin_u16x2(win[r + R + d], k, a1);
+            }
+            const uint32_t a = __vimin3_u16x2(a0, a1, clampv);
+            f0 = *reinterpret_cast<const float *>(lut + ((a & 0xffffu) | lane4));
+            f1 = *reinterpret_cast<const float *>(lut + (__umulhi(a, 65536u) + lane4));
         }
-        const uint32_t a = __vimin3_u16x2(a0, a1, clampv);
-        const float f0 = *reinterpret_cast<const float *>(lut + ((a & 0xffffu) | lane4));
-        const float f1 = *reinterpret_cast<const float *>(lut + (__umulhi(a, 65536u) + lane4));
         float *o = reinterpret_cast<float *>(pb + (uint64_t)pitch_bytes * (uint32_t)r);
         if (CHECK) {
             if (r < rows_left) {
@@ -184,6 +196,11 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
     uint64_t *full = reinterpret_cast<uint64_t *>(lut + (size_t)(t2 + 1) * EDT_SCALE);
     int *arrivals = reinterpret_cast<int *>(full + NST);      // per stage, monotonically increasing
 
+    // Consecutive transforms are independent of each other (each reads an occupancy no transform writes and
+    // writes its own field), so the next one in the stream may start -- launch latency, table fill, its first
+    // TMA loads -- while this one drains: programmatic dependent launch.  Every thread waits for the grid in
+    // front right before it exits, so completion order (what later kernels in the stream rely on) is kept.
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * (64 * NW);
@@ -213,7 +230,10 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
         }
     }
     __syncthreads();
-    if (warp >= nactive) return;
+    if (warp >= nactive) {
+        pdl_wait_prior_grids();
+        return;
+    }
 
     // ---- consumers: warp j owns output columns [x0 + 64j, x0 + 64j + 64) ---------------
     // Stage column q is grid column x0 - SH + q.  Strip j ballots the three 32-cell words
@@ -228,14 +248,18 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
     const uint32_t lane4 = (uint32_t)(lane & 15) * 4u;
     const uint32_t clampv = (uint32_t)(EDT_SCALE * t2) * 0x00010001u;
 
+    // h = R + 2 ("nothing within reach", what h2scaled returns for an empty window): clamps in pass 2
+    constexpr uint32_t NONE2 = (uint32_t)(EDT_SCALE * (R + 2) * (R + 2)) * 0x00010001u;
     uint32_t win[WN];
 #pragma unroll
-    for (int i = 0; i < WN; ++i) win[i] = 0;
+    for (int i = 0; i < WN; ++i) win[i] = NONE2;
+    typename EdtRowMask<R>::type rowmask = 0;     // bit i: window row i has an occupied cell in this warp's three words
 
     for (int t = 0; t < nbl; ++t) {
         const int s = t % NST;
         if (!mbar_wait(&full[s], (t / NST) & 1)) {
             if (lane == 0) atomicOr(error, DEV_ERR_TMA);
+            pdl_wait_prior_grids();
             return;
         }
         const int *st = reinterpret_cast<const int *>(smem_raw + (size_t)s * C::STAGE_BYTES) + woff;
@@ -251,9 +275,16 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
             const uint32_t w0 = __ballot_sync(0xffffffffu, ld[r][0] != 0);
             const uint32_t w1 = __ballot_sync(0xffffffffu, ld[r][1] != 0);
             const uint32_t w2 = __ballot_sync(0xffffffffu, ld[r][2] != 0);
-            const uint32_t X0 = __funnelshift_r(w0, w1, lane);
-            const uint32_t X1 = __funnelshift_r(w1, w2, lane);
-            win[2 * R + r] = h2scaled<R>(X0) + (h2scaled<R>(X1) << 16);
+            // Occupancy grids are sparse (walls): most rows of a 64-column strip hold nothing.  The ballots are
+            // warp uniform, so an empty row costs the loads and the three votes and nothing else.
+            uint32_t v = NONE2;
+            if ((w0 | w1 | w2) != 0u) {
+                const uint32_t X0 = __funnelshift_r(w0, w1, lane);
+                const uint32_t X1 = __funnelshift_r(w1, w2, lane);
+                v = h2scaled<R>(X0) + (h2scaled<R>(X1) << 16);
+                rowmask |= (typename EdtRowMask<R>::type)1 << (2 * R + r);
+            }
+            win[2 * R + r] = v;
         }
         // ---- stage consumed: the last warp to get here refills it ----------------------
         __syncwarp();
@@ -270,15 +301,22 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
         if (t >= 2) {
             const int yb = y0 + (t - 2) * B;
             unsigned char *pb = obase + (size_t)(uint32_t)yb * pitch_bytes;
-            if (interior && yb + B <= rows)
-                edt_emit_rows<R, false, MULTI>(win, lut, lane4, clampv, pb, pitch_bytes, 0, true, true, peers);
-            else
-                edt_emit_rows<R, true, MULTI>(win, lut, lane4, clampv, pb, pitch_bytes, rows - yb, s0, s1, peers);
+            constexpr typename EdtRowMask<R>::type FULL = ((typename EdtRowMask<R>::type)1 << (3 * R)) - 1;
+            if (interior && yb + B <= rows) {
+                if (rowmask == FULL)
+                    edt_emit_rows<R, false, MULTI, false>(win, rowmask, lut, lane4, clampv, max_dist, pb, pitch_bytes, 0, true, true, peers);
+                else
+                    edt_emit_rows<R, false, MULTI, true>(win, rowmask, lut, lane4, clampv, max_dist, pb, pitch_bytes, 0, true, true, peers);
+            } else {
+                edt_emit_rows<R, true, MULTI, true>(win, rowmask, lut, lane4, clampv, max_dist, pb, pitch_bytes, rows - yb, s0, s1, peers);
+            }
         }
+        rowmask >>= B;
         // ---- slide the window down by B rows ------------------------------------------
 #pragma unroll
         for (int i = 0; i < 2 * R; ++i) win[i] = win[i + B];
     }
+    pdl_wait_prior_grids();
 }
 
 // ---- generic path for any radius: two plain passes through a u16 intermediate -------
@@ -395,11 +433,32 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
         if (cost < best_cost - 1e-9) { best_cost = cost; best_cb = cb; }
     }
     if (nbatch >= 14 && (long)gx * ((nbatch + 13) / 14) * 2 >= 5 * resident) best_cb = 14;
+    else if (ctx->match_mode == B200SLAM_MATCH_THROUGHPUT) {
+        // Many independent transforms in flight (they overlap through programmatic dependent launch): what
+        // counts is the work per cell, i.e. the halo overhead (cb + 2) / cb, as long as one launch still
+        // spreads over every SM a few times.  Measured at 2048^2, back to back: cb = 3 (the latency choice)
+        // 7.6 us, cb = 5 6.6 us; one launch alone: 18.8 us either way.
+        for (int cb = 14; cb >= 1; --cb)
+            if (cb <= nbatch && (long)gx * ((nbatch + cb - 1) / cb) >= 3L * ctx->sm_count) { best_cb = cb > best_cb ? cb : best_cb; break; }
+    }
     if (const char *e = getenv("B200SLAM_EDT_CB")) best_cb = max(1, min(atoi(e), nbatch));   // tuning knob
     const int gy = (nbatch + best_cb - 1) / best_cb;
-    kern<<<dim3(gx, gy), C::THREADS, smem, ctx->stream>>>(tmap, d_field, (uint32_t)field_pitch * 4u, row_begin, row_end, cols,
-                                                         best_cb, t2, max_dist, peers, &ctx->d_match->error);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, gy);
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // only directly behind another transform, and never for the multi-GPU variant (its peer stores are bracketed
+    // by barrier kernels)
+    cfg.numAttrs = (ctx->use_pdl && ctx->prev_launch_was_edt && !MULTI) ? 1 : 0;
+    CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, tmap, d_field, (uint32_t)field_pitch * 4u, row_begin, row_end, cols, best_cb, t2,
+                                     max_dist, peers, &ctx->d_match->error));
     LAUNCH_CHECK(ctx);
+    ctx->prev_launch_was_edt = !MULTI;
     return B200SLAM_OK;
 }
 

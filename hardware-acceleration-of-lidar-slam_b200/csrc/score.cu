@@ -34,6 +34,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -272,14 +273,19 @@ struct LatticeTables {
 template <int TYPT, int UM = 1, int Q = 0>
 struct LatticePipe {
     static constexpr int U = UM * (TYPT >= 16 ? 1 : 16 / TYPT);      // UM: deeper groups for low-occupancy shapes
-    static constexpr int NBUF = (TYPT >= 16 && Q == 0) ? 2 : 3;      // row reuse: TYPT / Q + 1 loads per beam, 3 buffers
+    // 16 candidates per thread: two buffers.  With row reuse that is 16 sums + 2 x 9 gathered values in 64
+    // registers = 4 CTAs (32 warps) per SM; the kernel is latency bound, and measured on config 3 occupancy beats
+    // a third buffer: 648 us against 684 us with three buffers at 3 CTAs per SM (80 registers), 1386 us with three
+    // buffers squeezed into 64 registers (spills), 1011 us at 2 CTAs per SM.
+    static constexpr int NBUF = TYPT >= 16 ? 2 : 3;
     static constexpr int PAD = NBUF * U;
     static constexpr int GUARD = PAD - 1 + (NBUF - 1) * U;
 };
 
 struct LatticeArgs {
-    const float *field;       // [0][0]; field[-1] == 0
+    const float *field;       // [0][0]; field[-1] == 0, and so are the B200SLAM_FIELD_PAD_ROWS rows of floats in front of it
     int pitch, rows, cols;
+    int rr_clamp;             // row reuse: index of an invalid beam, -(8 * pitch + 1): its K <= 9 row reads all land in the zero region
     const float *scan_x, *scan_y;
     int nbeams;
     float ipixel;
@@ -311,13 +317,13 @@ struct LatticeArgs {
 // (beam, ty group) whose rows do not follow the pattern (float fuzz at a rounding boundary, rows at the edge
 // of the grid) is flagged and takes the per-candidate path for that beam, so results stay bit-identical.
 template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0>
-__global__ void __launch_bounds__(32 * WX * WY, (Q > 0 && TYPT >= 16) ? 3 : 1)
+__global__ void __launch_bounds__(32 * WX * WY, TYPT >= 16 ? (Q > 0 ? 4 : 3) : 1)
 lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ LatticeTables T)
 {
     static_assert(!COUNT || TYPT == 1, "per-candidate hit counts: one candidate per thread");
     static_assert(Q == 0 || (TYPT % Q == 0 && !COUNT), "row reuse: TYPT a multiple of Q");
     constexpr int K = Q > 0 ? TYPT / Q + 1 : TYPT;       // values a thread gathers per beam
-    constexpr int RW = Q > 0 ? 2 * WY : TYPT * WY;       // row-table ints per beam ({r0 * pitch, phase} per ty group)
+    constexpr int RW = Q > 0 ? WY : TYPT * WY;           // row-table ints per beam (Q > 0: r0 * pitch | phase per ty group)
     constexpr int TXT = 32 * WX;
     constexpr int TYT = TYPT * WY;
     constexpr int NT = 32 * WX * WY;
@@ -431,8 +437,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                         }
                         if (nj <= 0) phase = 0;              // nothing to score here: adds +0.0f to unused sums
                     }
-                    rowT[e * 2] = off0;
-                    rowT[e * 2 + 1] = phase;
+                    rowT[e] = off0 | phase;                  // the pitch is a multiple of 32 and INVALID_OFF of 2^30: low bits free
                 }
             }
             __syncthreads();
@@ -440,37 +445,44 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
             // of U beams are put in flight before the (sequential, in-order) additions of
             // the current group.  Table rows [cb, cbp) are INVALID and add +0.0f.
             const int *cp = colT + txl;
-            const int *rp = rowT + (Q > 0 ? 2 * wy : tyl);
+            const int *rp = rowT + (Q > 0 ? wy : tyl);
             [[maybe_unused]] int phase_q[NBUF][U];           // Q > 0: phase of every beam in flight
-            [[maybe_unused]] auto gather_rr = [&](int i0, float (&dst)[U][K], int (&ph)[U]) {
+            // cq / rq: this thread's column-table / row-table entries of the group's first beam.  An invalid column
+            // or row makes the sum hugely negative -> clamped to rr_clamp, from where all K row reads hit the zero
+            // rows in front of the field: no select on the row stride, no branch.
+            [[maybe_unused]] auto gather_rr = [&](const int *cq, const int *rq, float (&dst)[U][K], int (&ph)[U]) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int i = i0 + u;
-                    const int c = cp[i * TXT];
-                    const int2 ri = *reinterpret_cast<const int2 *>(rp + i * RW);      // {r0 * pitch, phase}, warp uniform
-                    const int idx = __viaddmax_s32(c, ri.x, -1);                     // column or row invalid: field[-1] == 0
-                    const int step = idx >= 0 ? A.pitch : 0;
-                    ph[u] = ri.y;
+                    const int c = cq[u * TXT];
+                    const int rv = rq[u * RW];                                           // r0 * pitch | phase, warp uniform
+                    const int idx = __viaddmax_s32(c, rv & ~7, A.rr_clamp);
+                    ph[u] = rv & 7;
                     const float *p0 = A.field + idx;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) dst[u][k] = ldg_ordered(p0 + (long)k * step);   // K independent addresses
+                    for (int k = 0; k < K; ++k) dst[u][k] = ldg_ordered(p0 + (long)k * A.pitch);
                 }
 #pragma unroll
                 for (int j = 0; j < TYPT; ++j) asm volatile("" : "+f"(acc[j]));
             };
-            // adds of one beam: value k = (j + phase) / Q of the K gathered rows, beams in scan order (main.c:516)
+            // adds of one beam, in scan order (main.c:516): candidate j takes row (j + phase) / Q of the K gathered
+            // ones.  The phase is warp uniform, so each phase gets its own copy of the adds with compile-time row
+            // indices -- no selects: measured on config 3, 684 us against 692 us with FSELs and 784 us with packed
+            // FADD2 adds (whose even-aligned register pairs made the allocator spill).
             [[maybe_unused]] auto accumulate_rr = [&](const float (&src)[U][K], const int (&ph)[U], int i0) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     constexpr int QQ = Q > 0 ? Q : 1;
                     if (ph[u] < QQ) {                        // warp uniform; almost always
-                        // candidate j reads row floor((j + p) / Q) = j / Q, or one further iff j % Q + p >= Q:
-                        // one select per candidate that is not first in its row group, no branch on p
+                        auto add_phase = [&](auto pc) {
+                            constexpr int p = decltype(pc)::value;
 #pragma unroll
-                        for (int j = 0; j < TYPT; ++j) {
-                            const float lo = src[u][j / QQ];
-                            const float v = (j % QQ == 0) ? lo : (ph[u] >= QQ - j % QQ ? src[u][j / QQ + 1] : lo);
-                            acc[j] = __fadd_rn(acc[j], v);
+                            for (int j = 0; j < TYPT; ++j) acc[j] = __fadd_rn(acc[j], src[u][(j + p) / QQ]);
+                        };
+                        switch (ph[u]) {
+                            case 0: add_phase(std::integral_constant<int, 0>()); break;
+                            case 1: add_phase(std::integral_constant<int, 1 % QQ>()); break;
+                            case 2: add_phase(std::integral_constant<int, 2 % QQ>()); break;
+                            default: add_phase(std::integral_constant<int, 3 % QQ>()); break;
                         }
                     } else {
                         // per-candidate path for this beam (rows off the pattern or at the grid's edge)
@@ -523,12 +535,14 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
             };
             if constexpr (Q > 0) {
                 float v[NBUF][U][K];
+                const int *cq = cp, *rq = rp;                // table entries of beam i0: every load below is [register + immediate]
 #pragma unroll
-                for (int b = 0; b < NBUF - 1; ++b) gather_rr(b * U, v[b], phase_q[b]);
-                for (int i0 = 0; i0 < cbp; i0 += NBUF * U) {
+                for (int b = 0; b < NBUF - 1; ++b) gather_rr(cq + b * U * TXT, rq + b * U * RW, v[b], phase_q[b]);
+                for (int i0 = 0; i0 < cbp; i0 += NBUF * U, cq += NBUF * U * TXT, rq += NBUF * U * RW) {
 #pragma unroll
                     for (int b = 0; b < NBUF; ++b) {
-                        gather_rr(i0 + (b + NBUF - 1) * U, v[(b + NBUF - 1) % NBUF], phase_q[(b + NBUF - 1) % NBUF]);
+                        gather_rr(cq + (b + NBUF - 1) * U * TXT, rq + (b + NBUF - 1) * U * RW, v[(b + NBUF - 1) % NBUF],
+                                  phase_q[(b + NBUF - 1) % NBUF]);
                         accumulate_rr(v[b], phase_q[b], i0 + b * U);
                     }
                 }
@@ -803,8 +817,9 @@ int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T
     auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT, Q>;
     // Beams per chunk: the whole scan when its tables fit the budget, else even chunks.
     constexpr int GUARD = LatticePipe<TYPT, UM, Q>::GUARD;
-    const int per_beam = (TXT + (Q > 0 ? 2 * WY : TYT) + 2) * 4;
-    const int budget = (TYPT >= 16 ? 56 * 1024 : 100 * 1024) - (Q > 0 ? TYT * 4 : 0);
+    const int per_beam = (TXT + (Q > 0 ? WY : TYT) + 2) * 4;
+    // 16 candidates per thread: chunks that leave room for 4 (row reuse) / 3 resident CTAs per SM
+    const int budget = (TYPT >= 16 ? (Q > 0 ? 50 : 56) * 1024 : 100 * 1024) - (Q > 0 ? TYT * 4 : 0);
     int cb = A.nbeams > 0 ? A.nbeams : 1;
     const int cap = budget / per_beam - GUARD;
     if (cb > cap) {
@@ -848,6 +863,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     const b200slam_map *m = L.map;
     LatticeArgs A;
     A.field = m->d_field; A.pitch = m->field_pitch; A.rows = m->rows; A.cols = m->cols;
+    A.rr_clamp = -((B200SLAM_FIELD_PAD_ROWS - 1) * m->field_pitch + 1);
     A.scan_x = ctx->d_scan_x; A.scan_y = ctx->d_scan_y; A.nbeams = ctx->nbeams;
     A.ipixel = 1 / m->pixel_size;                                        // main.c:383
     A.nth = L.nth; A.ntx = L.ntx; A.nty = L.nty;
@@ -910,11 +926,11 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
         {16, 2, 4, 1, 0, 1.00}, {8, 1, 8, 1, 0, 1.05}, {4, 1, 8, 1, 0, 1.13}, {2, 1, 8, 2, 0, 1.40}, {1, 1, 8, 1, 0, 1.95},
         {1, 1, 4, 1, 0, 1.95},
         // row reuse: K = TYPT / Q + 1 gathers per TYPT candidates.  Measured on config 3 (256 x 128 x 128 x 1080,
-        // step = pixel / 2): 64 x 64 tiles 775 us against 1059 us without reuse, 32 x 64 tiles 1033 us; with 4
+        // step = pixel / 2): 64 x 64 tiles 648 us against 1059 us without reuse, 32 x 64 tiles 1033 us; with 4
         // candidates per thread the per-beam bookkeeping outweighs the saved gathers (1503 us), so those
         // shapes are compiled (and tested) but never chosen.  The Q = 4 factors are estimates.
-        {16, 2, 4, 1, 2, 0.73}, {8, 1, 8, 1, 2, 0.98},
-        {16, 2, 4, 1, 4, 0.62}, {8, 1, 8, 1, 4, 0.85},
+        {16, 2, 4, 1, 2, 0.61}, {8, 1, 8, 1, 2, 0.98},
+        {16, 2, 4, 1, 4, 0.55}, {8, 1, 8, 1, 4, 0.85},
     };
     int pick_t = 0, pick_x = 0, pick_y = 0, pick_m = 1, pick_q = 0;
     if (const char *e = getenv("B200SLAM_LATTICE_CFG"))                   // tuning / test aid: "TYPT,WX,WY[,UM[,Q]]"

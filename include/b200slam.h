@@ -245,7 +245,9 @@ int b200slam_local_map_download(b200slam_ctx *ctx, float *x, float *y, int *size
 int b200slam_map_rasterise_local(b200slam_ctx *ctx, b200slam_map *map, float pixel_size, int *rows, int *cols,
                                  float top_left[2]);
 
-/* ---- scheduling hint for the scan matcher ---------------------------------------------
+/* ---- scheduling hint -------------------------------------------------------------------
+ * (Also read by the distance transform: with many independent transforms in flight it takes taller
+ * row chunks per CTA -- less halo work per cell -- where a single transform prefers more, shorter CTAs.)
  * The lattice kernel comes in several tile shapes (candidates per thread x warps per CTA).
  * B200SLAM_MATCH_LATENCY (default): one match at a time, as FastMatch is called per scan
  * (main.c:902-918) -- pick the shape whose busiest SM finishes first.  B200SLAM_MATCH_THROUGHPUT:

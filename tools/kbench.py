@@ -66,6 +66,38 @@ def bench_edt(mod, synth, ctx, sizes):
                 m.close()
 
 
+def bench_edt_cb(mod, synth, ctx):
+    """Chunk-height sweep (B200SLAM_EDT_CB, read at every launch) of the 8192^2 / 2048^2 transform, back to back
+    (consecutive transforms overlap through programmatic dependent launch) and isolated (event pair per launch)."""
+    for rows in (2048, 8192):
+        cells = rows * rows
+        ring = 8 if rows == 2048 else 2
+        for kind in ("rooms", "bern0.05"):
+            maps = []
+            for i in range(ring):
+                occ = synth.grid_rooms(rows, rows, synth.SEED_GRID + i) if kind == "rooms" else \
+                    synth.grid_bernoulli(rows, rows, 0.05, synth.SEED_GRID + i)
+                m = ctx.new_map(rows, rows)
+                m.upload_occupancy(occ)
+                maps.append(m)
+            for cb in os.environ.get("SWEEP", "0 3 4 5 7 9 14 20").split():
+                if cb == "0":
+                    os.environ.pop("B200SLAM_EDT_CB", None)
+                else:
+                    os.environ["B200SLAM_EDT_CB"] = cb
+                ms = time_loop(ctx, lambda i: maps[i % ring].edt(10.0), 40)
+                K = 30
+                for i in range(K):
+                    ctx.event_record(100 + 2 * i); maps[i % ring].edt(10.0); ctx.event_record(101 + 2 * i)
+                ctx.sync()
+                iso = sorted(ctx.event_elapsed_ms(100 + 2 * i, 101 + 2 * i) for i in range(K))[K // 2]
+                print(f"edt {rows}^2 {kind:8s} cb={cb:>2s}: back-to-back {ms * 1e3:8.2f} us (frac {cells * 8 / ms / 1e6 / PEAK:.3f})   "
+                      f"isolated median {iso * 1e3:8.2f} us (frac {cells * 8 / iso / 1e6 / PEAK:.3f})", flush=True)
+            os.environ.pop("B200SLAM_EDT_CB", None)
+            for m in maps:
+                m.close()
+
+
 def bench_lattice(mod, synth, ctx, names):
     for name in names:
         w = synth.make_workload(name)
@@ -210,6 +242,8 @@ def main():
         print(ctx.device_info(), flush=True)
         if "edt" in what:
             bench_edt(mod, synth, ctx, [(400, 400), (2048, 2048), (8192, 8192)])
+        if "edtcb" in what:
+            bench_edt_cb(mod, synth, ctx)
         if "edtbig" in what:
             bench_edt(mod, synth, ctx, [(8192, 8192)])
         if "lattice" in what:
