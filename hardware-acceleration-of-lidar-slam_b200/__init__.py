@@ -107,6 +107,13 @@ def load_library() -> C.CDLL:
         "b200slam_set_match_mode": (i, [vp, i]),
         "b200slam_lidar_set": (i, [vp, c_float_p, c_float_p, i, f]),
         "b200slam_scan_read": (i, [vp, c_float_p, i, c_int_p]),
+        "b200slam_scan_read_async": (i, [vp, c_float_p, i]),
+        "b200slam_scan_read_resident_async": (i, [vp, C.c_int64, i]),
+        "b200slam_fastmatch_pair_async": (i, [vp, vp, vp, c_float_p, c_float_p, c_float_p]),
+        "b200slam_fastmatch_pair_fetch": (i, [vp, c_float_p, c_float_p, c_int_p, c_int_p]),
+        "b200slam_mappoints_grow_async": (i, [vp, f]),
+        "b200slam_csv_ingest": (i, [vp, vp, C.c_size_t, vp, C.c_int64, c_i64_p]),
+        "b200slam_csv_values": (i, [vp, C.POINTER(vp), c_i64_p]),
         "b200slam_scan_transform": (i, [vp, c_float_p]),
         "b200slam_scan_download": (i, [vp, c_float_p, c_float_p, c_float_p, c_float_p, c_int_p]),
         "b200slam_mappoints_upload": (i, [vp, c_float_p, c_float_p, i, i]),
@@ -373,6 +380,38 @@ class Context:
         self._check(self.L.b200slam_scan_read(self.h, _fptr(r), int(max_range), C.byref(n)))
         self._nbeams = n.value
         return n.value
+
+    def scan_read_async(self, ranges, max_range: int = 24):
+        r = np.ascontiguousarray(ranges, np.float32)
+        assert len(r) == self._lidar_n
+        self._check(self.L.b200slam_scan_read_async(self.h, _fptr(r), int(max_range)))
+        self._nbeams = self._lidar_n
+
+    def scan_read_resident_async(self, first_value: int, max_range: int = 24):
+        self._check(self.L.b200slam_scan_read_resident_async(self.h, int(first_value), int(max_range)))
+        self._nbeams = self._lidar_n
+
+    def csv_ingest(self, text: bytes, max_values: int | None = None) -> np.ndarray:
+        """The reference's CSV reader (main.c:22-30) on the GPU: raw text -> float32 values (also resident)."""
+        buf = np.frombuffer(text, np.uint8)
+        cap = len(buf) // 2 + 1 if max_values is None else int(max_values)
+        out = np.empty(max(cap, 1), np.float32)
+        n = C.c_int64(0)
+        self._check(self.L.b200slam_csv_ingest(self.h, buf.ctypes.data, len(buf), out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def fastmatch_pair_async(self, map_a: Map, map_b: Map, pose, res_a, res_b):
+        self._check(self.L.b200slam_fastmatch_pair_async(self.h, map_a.h, map_b.h, _f3(pose), _f3(res_a), _f3(res_b)))
+
+    def fastmatch_pair_fetch(self):
+        pa, pb = (C.c_float * 3)(), (C.c_float * 3)()
+        n, bh = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.b200slam_fastmatch_pair_fetch(self.h, pa, pb, C.byref(n), C.byref(bh)))
+        self._nbeams = n.value
+        return np.array(list(pa), np.float32), np.array(list(pb), np.float32), n.value, bh.value
+
+    def mappoints_grow_async(self, threshold: float = 1.5):
+        self._check(self.L.b200slam_mappoints_grow_async(self.h, threshold))
 
     def scan_transform(self, pose):
         self._check(self.L.b200slam_scan_transform(self.h, _f3(pose)))

@@ -78,7 +78,7 @@ int b200slam_create(b200slam_ctx **out, int device)
         init.work_key = ~0ull; init.tickets = 0; init.epoch = 0; init.key = ~0ull;
         init.best_hits = 0; init.last_hits = 0; init.collected = 0; init.error = 0; init.written_hits = 0; init.posted = 0;
         memset(init.cand_hits, 0, sizeof init.cand_hits); memset(init.outbox, 0, sizeof init.outbox);
-        init.bar_epoch = 0; init.gkey = ~0ull; init.gbest_hits = 0; init.glast_hits = 0;
+        init.bar_epoch = 0; init.seed_key = ~0ull; init.gkey = ~0ull; init.gbest_hits = 0; init.glast_hits = 0;
         CREATE_TRY(cudaMemcpy(ctx->d_match, &init, sizeof init, cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaMalloc(&ctx->d_keys, sizeof(unsigned long long) * 256));
@@ -425,6 +425,7 @@ int b200slam_scan_upload(b200slam_ctx *ctx, const float *x, const float *y, int 
     int rc = ensure_scan_capacity(ctx, nbeams);
     if (rc) return rc;
     ctx->scan_t_valid = false;
+    ctx->scan_n_dev = false;              // the host's count is exact again
     if (nbeams > 0) {
         // one pinned, truly asynchronous copy of x | y (callers hand in pageable arrays)
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->scan_event));
@@ -749,6 +750,93 @@ int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3]
     pose_out[1] = m.best_pose[1];
     pose_out[2] = m.best_pose[2];
     if (best_hits_size) *best_hits_size = m.best_hits;                    // main.c:557
+    return B200SLAM_OK;
+}
+
+/* ---- FastMatch + FastMatch2 without a host round trip in between ------------------------ */
+
+int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200slam_map *map_b, const float pose[3],
+                                  const float res_a[3], const float res_b[3])
+{
+    if (!ctx || !map_a || !map_b || !pose || !res_a || !res_b) return B200SLAM_ERR_ARG;
+    const float step_a[3] = {res_a[0], res_a[0], res_a[2]};               // main.c:386-387
+    const float step_b[3] = {res_b[0], res_b[0], res_b[2]};
+    const int n[3] = {3, 3, 3};
+    int rc = queue_lattice(ctx, map_a, pose, step_a, n, 0, 9, false, 0);  // FastMatch (main.c:902 / :909)
+    if (rc) return rc;
+    rc = check_lattice_args(ctx, map_b, pose, step_b, n);
+    if (rc) return rc;
+    // FastMatch2 starts from FastMatch's result (main.c:918), which is one of 3 x 3 x 3 lattice points: the axis
+    // tables of every possible centre, computed here exactly as stage_lattice would from the fetched pose
+    // (main.c:424-437: the centre is itself a lattice value of the first match)
+    float *t = ctx->h_param_tab;
+    const float ipixel = 1 / map_b->pixel_size;                          // main.c:383
+    for (int s1 = 0; s1 < 3; ++s1) {
+        const float th1 = b200slam_lattice_value(pose[2], step_a[2], s1, 3);
+        const float tx1 = b200slam_lattice_value(pose[0], step_a[0], s1, 3);
+        const float ty1 = b200slam_lattice_value(pose[1], step_a[1], s1, 3);
+        for (int k = 0; k < 3; ++k) {
+            const float th = b200slam_lattice_value(th1, step_b[2], k, 3);        // main.c:424
+            t[3 * s1 + k] = cosf(th);                                             // main.c:434
+            t[9 + 3 * s1 + k] = sinf(th);                                         // main.c:435
+            const float tx = b200slam_lattice_value(tx1, step_b[0], k, 3);        // main.c:425
+            volatile float dx = tx - map_b->top_left_x;
+            t[18 + 3 * s1 + k] = dx * ipixel;                                     // main.c:436
+            const float ty = b200slam_lattice_value(ty1, step_b[1], k, 3);        // main.c:426
+            volatile float dy = ty - map_b->top_left_y;
+            t[27 + 3 * s1 + k] = dy * ipixel;                                     // main.c:437
+        }
+    }
+    LatticeLaunch L;
+    L.map = map_b;
+    L.nth = L.ntx = L.nty = 3;
+    L.th_first = 0; L.nth_tab = 3;
+    L.h_tables = t; L.d_tables = nullptr;
+    L.row_begin = 0; L.row_end = 9;
+    L.d_scores = nullptr;
+    L.exchange = L.collect_prev = L.post_deferred = false;
+    L.seeded = true;
+    rc = lattice_launch(ctx, L);
+    if (rc) return rc;
+    ctx->last.valid = true; ctx->last.is_poses = false; ctx->last.gathered = false; ctx->last.exchanged = false;
+    for (int i = 0; i < 3; ++i) {
+        ctx->last.n[i] = 3;
+        ctx->last.step[i] = step_b[i];
+        ctx->pair.guess[i] = pose[i]; ctx->pair.step_a[i] = step_a[i]; ctx->pair.step_b[i] = step_b[i];
+    }
+    ctx->pair.valid = true;
+    return B200SLAM_OK;
+}
+
+int b200slam_fastmatch_pair_fetch(b200slam_ctx *ctx, float pose_a[3], float pose_b[3], int *scan_size, int *best_hits_size)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    if (!ctx->pair.valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no b200slam_fastmatch_pair_async queued");
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_match, ctx->d_match, sizeof(MatchDev), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->d_front)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_front, ctx->d_front, sizeof(*ctx->d_front), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const MatchDev &m = *ctx->h_match;
+    if (m.error) return device_error_check(ctx, m.error);
+    if (ctx->d_front) {
+        if (ctx->scan_n_dev) ctx->nbeams = ctx->h_front->scan_n;
+        if (ctx->mp_n_dev) ctx->mp_size = ctx->h_front->mp_n;
+    }
+    if (m.key == ~0ull || m.seed_key == ~0ull) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "pair match scored nothing");
+    const int l1 = (int)(m.seed_key & 0xffffffffull), l2 = (int)(m.key & 0xffffffffull);
+    float pa[3];
+    pa[0] = b200slam_lattice_value(ctx->pair.guess[0], ctx->pair.step_a[0], (l1 / 3) % 3, 3);   // main.c:592-594
+    pa[1] = b200slam_lattice_value(ctx->pair.guess[1], ctx->pair.step_a[1], l1 % 3, 3);
+    pa[2] = b200slam_lattice_value(ctx->pair.guess[2], ctx->pair.step_a[2], l1 / 9, 3);
+    if (pose_a) for (int i = 0; i < 3; ++i) pose_a[i] = pa[i];
+    if (pose_b) {
+        pose_b[0] = b200slam_lattice_value(pa[0], ctx->pair.step_b[0], (l2 / 3) % 3, 3);
+        pose_b[1] = b200slam_lattice_value(pa[1], ctx->pair.step_b[1], l2 % 3, 3);
+        pose_b[2] = b200slam_lattice_value(pa[2], ctx->pair.step_b[2], l2 / 9, 3);
+    }
+    for (int i = 0; i < 3; ++i) ctx->last.pose0[i] = pa[i];     // b200slam_match_fetch then describes the second match
+    if (scan_size) *scan_size = ctx->nbeams;
+    if (best_hits_size) *best_hits_size = m.best_hits;           // main.c:557
     return B200SLAM_OK;
 }
 

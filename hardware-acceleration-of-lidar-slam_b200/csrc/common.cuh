@@ -62,6 +62,7 @@ struct MatchDev {
     // NVLink stores in flight when it completes (measured: ~8 us per kernel on a 2-GPU box)
     struct Outbox { unsigned long long key; int best_hits, last_hits; } outbox[64];
     unsigned long long bar_epoch;   // device-side peer barriers this context has passed (same on every rank)
+    unsigned long long seed_key;    // b200slam_fastmatch_pair_async: the FIRST match's key, saved by the second (seeded) one
 };
 static_assert(sizeof(MatchDev::outbox) / sizeof(MatchDev::Outbox) == 64, "outbox ring == XCHG_EPOCHS");
 constexpr int MATCH_SMALL = 64;
@@ -202,7 +203,19 @@ struct b200slam_ctx {
     int mp_cap = 0, mp_size = 0;
     int local_n = -1;                    // points of the resident local map (-1: none)
     float local_bbox[4] = {0, 0, 0, 0};  // min x, min y, max x, max y of the local map
-    struct FrontOut { int count; int pad; float bbox[4]; } *d_front = nullptr, *h_front = nullptr;
+    // count / bbox: result of the last front-end kernel; scan_n / mp_n: the scan's and the map points' sizes as the
+    // DEVICE knows them -- authoritative while scan_n_dev / mp_n_dev is set (asynchronous scan loop: the host then
+    // only holds upper bounds in nbeams / mp_size until the next call that reads them back)
+    struct FrontOut { int count; int scan_n; int mp_n; int pad; float bbox[4]; } *d_front = nullptr, *h_front = nullptr;
+    bool scan_n_dev = false, mp_n_dev = false;
+    // CSV ingest (csv.cu): raw text, parsed values (resident), scratch
+    char *d_csv_text = nullptr;
+    float *d_csv_values = nullptr;
+    unsigned long long *d_csv_scratch = nullptr, *h_csv_scratch = nullptr;
+    size_t csv_text_cap = 0, csv_values_cap = 0;
+    int64_t csv_count = 0;
+    // b200slam_fastmatch_pair_async bookkeeping (host side)
+    struct { bool valid = false; float guess[3], step_a[3], step_b[3]; } pair;
 
     // generic EDT scratch (u16 column distances)
     uint16_t *d_edt_scratch = nullptr;
@@ -268,6 +281,8 @@ struct LatticeLaunch {
     bool exchange;     // post the result to the other ranks through peer memory from the kernel's tail
     bool collect_prev; // ... and merge the previous, deferred exchange in the same tail
     bool post_deferred; // record the result in the outbox only; the next collect kernel posts it
+    bool seeded = false;   // 3 x 3 x 3 lattice centred on the winner of the match in front: h_tables holds all three
+                           // candidate table sets (36 floats), the kernel picks by the previous key
 };
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
@@ -303,6 +318,9 @@ int rasterise_from_bbox(b200slam_ctx *ctx, b200slam_map *map, int npoints, const
 int ensure_points_capacity(b200slam_ctx *ctx, size_t npoints);
 int ensure_scan_capacity(b200slam_ctx *ctx, int nbeams);
 void frontend_free(b200slam_ctx *ctx);
+void csv_free(b200slam_ctx *ctx);
+int ensure_front(b200slam_ctx *ctx);
+int fetch_front(b200slam_ctx *ctx);
 
 int comm_allgather_u64(b200slam_ctx *ctx, const unsigned long long *d_send,
                        unsigned long long *d_recv, int count_per_rank);

@@ -64,14 +64,18 @@ scan_read_kernel(const float *__restrict__ ranges, const float *__restrict__ cos
             y[slot] = __fmul_rn(r, sin_a[i]);          // main.c:91
         }
     }
-    if (threadIdx.x == 0) out->count = base;           // scan.size, main.c:94
+    if (threadIdx.x == 0) { out->count = base; out->scan_n = base; }           // scan.size, main.c:94
 }
+
+__global__ void set_int_kernel(int *p, int v) { *p = v; }
+__global__ void copy_int_kernel(int *dst, const int *src) { *dst = *src; }
 
 // main.c:97-118
 __global__ void __launch_bounds__(256)
 scan_transform_kernel(const float *__restrict__ x, const float *__restrict__ y, int n, float ct, float st, float px,
-                      float py, float *__restrict__ tx, float *__restrict__ ty)
+                      float py, float *__restrict__ tx, float *__restrict__ ty, const int *__restrict__ n_dev)
 {
+    if (n_dev) n = *n_dev;                             // the device's own count (asynchronous scan loop)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float sx = x[i], sy = y[i];
@@ -101,10 +105,12 @@ __device__ __forceinline__ float block_reduce(float v, bool want_min, float *red
 __global__ void __launch_bounds__(FE_THREADS)
 local_map_kernel(const float *__restrict__ tx, const float *__restrict__ ty, int nscan, float border,
                  const float *__restrict__ mx, const float *__restrict__ my, int nmap, float *__restrict__ lx,
-                 float *__restrict__ ly, b200slam_ctx::FrontOut *out)
+                 float *__restrict__ ly, b200slam_ctx::FrontOut *out, bool nscan_dev, bool nmap_dev)
 {
     __shared__ int warp_counts[FE_THREADS / 32];
     __shared__ float red[FE_THREADS / 32];
+    if (nscan_dev) nscan = out->scan_n;
+    if (nmap_dev) nmap = out->mp_n;
     float lo_x = INFINITY, lo_y = INFINITY, hi_x = -INFINITY, hi_y = -INFINITY;
     for (int i = threadIdx.x; i < nscan; i += FE_THREADS) {
         const float a = tx[i], b = ty[i];
@@ -145,10 +151,12 @@ local_map_kernel(const float *__restrict__ tx, const float *__restrict__ ty, int
 __global__ void __launch_bounds__(FE_THREADS)
 map_grow_kernel(const float *__restrict__ hit_values, const MatchDev *__restrict__ match, const float *__restrict__ tx,
                 const float *__restrict__ ty, float threshold, float *__restrict__ mx, float *__restrict__ my,
-                int map_size, int map_cap, b200slam_ctx::FrontOut *out)
+                int map_size, int map_cap, b200slam_ctx::FrontOut *out, bool size_dev)
 {
     __shared__ int warp_counts[FE_THREADS / 32];
     const int n = match->key == ~0ull ? 0 : match->best_hits;
+    if (size_dev) map_size = out->mp_n;
+    __syncthreads();                                   // every thread has read mp_n before thread 0 rewrites it
     int base = map_size;
     for (int j0 = 0; j0 < n; j0 += FE_THREADS) {
         const int j = j0 + threadIdx.x;
@@ -156,23 +164,34 @@ map_grow_kernel(const float *__restrict__ hit_values, const MatchDev *__restrict
         const int slot = compact_slot(keep, base, warp_counts);
         if (keep && slot < map_cap) { mx[slot] = tx[j]; my[slot] = ty[j]; }
     }
-    if (threadIdx.x == 0) out->count = base - map_size;                          // newPointSize
+    if (threadIdx.x == 0) {
+        out->count = base - map_size;                                            // newPointSize
+        out->mp_n = base < map_cap ? base : map_cap;
+    }
 }
+
+}  // namespace
 
 int ensure_front(b200slam_ctx *ctx)
 {
     if (ctx->d_front) return B200SLAM_OK;
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_front, sizeof(*ctx->d_front)));
+    CUDA_TRY(ctx, cudaMemset(ctx->d_front, 0, sizeof(*ctx->d_front)));
     CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_front, sizeof(*ctx->h_front), cudaHostAllocDefault));
     return B200SLAM_OK;
 }
 
+// Reads the front-end block back; the device's scan / map-point counts replace the host's upper bounds.
 int fetch_front(b200slam_ctx *ctx)
 {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_front, ctx->d_front, sizeof(*ctx->d_front), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->scan_n_dev) ctx->nbeams = ctx->h_front->scan_n;
+    if (ctx->mp_n_dev) ctx->mp_size = ctx->h_front->mp_n;
     return B200SLAM_OK;
 }
+
+namespace {
 
 int ensure_scan_t(b200slam_ctx *ctx)
 {
@@ -208,6 +227,7 @@ int ensure_map_points(b200slam_ctx *ctx, int need)
 
 void frontend_free(b200slam_ctx *ctx)
 {
+    csv_free(ctx);
     cudaFree(ctx->d_lidar); cudaFree(ctx->d_ranges); cudaFreeHost(ctx->h_ranges);
     cudaFree(ctx->d_scan_t); cudaFree(ctx->d_mp); cudaFree(ctx->d_front); cudaFreeHost(ctx->h_front);
 }
@@ -231,25 +251,53 @@ int b200slam_lidar_set(b200slam_ctx *ctx, const float *cos_a, const float *sin_a
     return B200SLAM_OK;
 }
 
-int b200slam_scan_read(b200slam_ctx *ctx, const float *ranges, int max_range, int *size)
+// d_src: ranges already on the device (CSV ingest), else `ranges` (host) go through the pinned staging buffer
+static int scan_read_queue(b200slam_ctx *ctx, const float *ranges, const float *d_src, int max_range)
 {
-    if (!ctx || !ranges) return B200SLAM_ERR_ARG;
     if (ctx->lidar_n <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_lidar_set first");
     int rc = ensure_scan_capacity(ctx, ctx->lidar_n);
     if (!rc) rc = ensure_front(ctx);
     if (rc) return rc;
     const int n = ctx->lidar_n;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));                 // pinned staging free again
-    memcpy(ctx->h_ranges, ranges, sizeof(float) * n);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ranges, ctx->h_ranges, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
-    scan_read_kernel<<<1, FE_THREADS, 0, ctx->stream>>>(ctx->d_ranges, ctx->d_lidar, ctx->d_lidar + n, n,
-                                                        ctx->lidar_range_min, max_range, ctx->d_scan_x, ctx->d_scan_y,
-                                                        ctx->d_front);
+    if (!d_src) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->scan_event));              // pinned staging free again
+        memcpy(ctx->h_ranges, ranges, sizeof(float) * n);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ranges, ctx->h_ranges, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->scan_event, ctx->stream));
+        d_src = ctx->d_ranges;
+    }
+    scan_read_kernel<<<1, FE_THREADS, 0, ctx->stream>>>(d_src, ctx->d_lidar, ctx->d_lidar + n, n, ctx->lidar_range_min,
+                                                        max_range, ctx->d_scan_x, ctx->d_scan_y, ctx->d_front);
     LAUNCH_CHECK(ctx);
-    rc = fetch_front(ctx);                                              // the host sizes the matcher's launches by it
-    if (rc) return rc;
-    ctx->nbeams = ctx->h_front->count;
+    ctx->nbeams = n;                       // upper bound until somebody reads the count back
+    ctx->scan_n_dev = true;
     ctx->scan_t_valid = false;
+    return B200SLAM_OK;
+}
+
+int b200slam_scan_read_async(b200slam_ctx *ctx, const float *ranges, int max_range)
+{
+    if (!ctx || !ranges) return B200SLAM_ERR_ARG;
+    return scan_read_queue(ctx, ranges, nullptr, max_range);
+}
+
+int b200slam_scan_read_resident_async(b200slam_ctx *ctx, int64_t first_value, int max_range)
+{
+    if (!ctx || first_value < 0) return B200SLAM_ERR_ARG;
+    if (ctx->lidar_n <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_lidar_set first");
+    if (!ctx->d_csv_values || first_value + ctx->lidar_n > ctx->csv_count)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "values [%lld, %lld) are not in the ingested CSV (%lld values)",
+                                  (long long)first_value, (long long)(first_value + ctx->lidar_n), (long long)ctx->csv_count);
+    return scan_read_queue(ctx, nullptr, ctx->d_csv_values + first_value, max_range);
+}
+
+int b200slam_scan_read(b200slam_ctx *ctx, const float *ranges, int max_range, int *size)
+{
+    if (!ctx || !ranges) return B200SLAM_ERR_ARG;
+    int rc = scan_read_queue(ctx, ranges, nullptr, max_range);
+    if (rc) return rc;
+    rc = fetch_front(ctx);                                              // ctx->nbeams <- the device's count
+    if (rc) return rc;
     if (size) *size = ctx->nbeams;
     return B200SLAM_OK;
 }
@@ -264,7 +312,7 @@ int b200slam_scan_transform(b200slam_ctx *ctx, const float pose[3])
     if (ctx->nbeams > 0) {
         scan_transform_kernel<<<(ctx->nbeams + 255) / 256, 256, 0, ctx->stream>>>(
             ctx->d_scan_x, ctx->d_scan_y, ctx->nbeams, ct, st, pose[0], pose[1], ctx->d_scan_t,
-            ctx->d_scan_t + ctx->scan_t_cap);
+            ctx->d_scan_t + ctx->scan_t_cap, ctx->scan_n_dev ? &ctx->d_front->scan_n : nullptr);
         LAUNCH_CHECK(ctx);
     }
     ctx->scan_t_valid = true;
@@ -275,6 +323,10 @@ int b200slam_scan_download(b200slam_ctx *ctx, float *x, float *y, float *tx, flo
 {
     if (!ctx) return B200SLAM_ERR_ARG;
     if (!ctx->d_scan_x || ctx->nbeams < 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no scan on the device");
+    if (ctx->scan_n_dev) {
+        int rc = fetch_front(ctx);
+        if (rc) return rc;
+    }
     const size_t b = sizeof(float) * (size_t)ctx->nbeams;
     if ((tx || ty) && !ctx->scan_t_valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_scan_transform first");
     if (b) {
@@ -299,6 +351,7 @@ int b200slam_mappoints_upload(b200slam_ctx *ctx, const float *x, const float *y,
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));             // x / y may be pageable: done with them
     }
     ctx->mp_size = offset + n;
+    ctx->mp_n_dev = false;
     return B200SLAM_OK;
 }
 
@@ -314,12 +367,21 @@ int b200slam_mappoints_from_scan(b200slam_ctx *ctx)
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_mp + ctx->mp_cap, ctx->d_scan_t + ctx->scan_t_cap, b, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     ctx->mp_size = ctx->nbeams;
+    ctx->mp_n_dev = ctx->scan_n_dev;       // the device's scan count is the map's size now
+    if (ctx->mp_n_dev) {
+        copy_int_kernel<<<1, 1, 0, ctx->stream>>>(&ctx->d_front->mp_n, &ctx->d_front->scan_n);
+        LAUNCH_CHECK(ctx);
+    }
     return B200SLAM_OK;
 }
 
 int b200slam_mappoints_download(b200slam_ctx *ctx, float *x, float *y, int *size)
 {
     if (!ctx) return B200SLAM_ERR_ARG;
+    if (ctx->mp_n_dev) {
+        int rc = fetch_front(ctx);
+        if (rc) return rc;
+    }
     if (ctx->mp_size > 0) {
         const size_t b = sizeof(float) * (size_t)ctx->mp_size;
         if (x) CUDA_TRY(ctx, cudaMemcpyAsync(x, ctx->d_mp, b, cudaMemcpyDeviceToHost, ctx->stream));
@@ -330,9 +392,8 @@ int b200slam_mappoints_download(b200slam_ctx *ctx, float *x, float *y, int *size
     return B200SLAM_OK;
 }
 
-int b200slam_mappoints_grow(b200slam_ctx *ctx, float threshold, int *added)
+static int mappoints_grow_queue(b200slam_ctx *ctx, float threshold)
 {
-    if (!ctx) return B200SLAM_ERR_ARG;
     if (!ctx->scan_t_valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_scan_transform first");
     if (!ctx->last.valid || ctx->last.is_poses) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no lattice match to grow from");
     // main.c:942-948 reads the winner's count and the LAST candidate's hit values of the WHOLE lattice; after a
@@ -344,12 +405,39 @@ int b200slam_mappoints_grow(b200slam_ctx *ctx, float threshold, int *added)
     if (rc) return rc;
     map_grow_kernel<<<1, FE_THREADS, 0, ctx->stream>>>(ctx->d_hit_values + ctx->scan_cap, ctx->d_match, ctx->d_scan_t,
                                                        ctx->d_scan_t + ctx->scan_t_cap, threshold, ctx->d_mp,
-                                                       ctx->d_mp + ctx->mp_cap, ctx->mp_size, ctx->mp_cap, ctx->d_front);
+                                                       ctx->d_mp + ctx->mp_cap, ctx->mp_size, ctx->mp_cap, ctx->d_front,
+                                                       ctx->mp_n_dev);
     LAUNCH_CHECK(ctx);
-    rc = fetch_front(ctx);
+    return B200SLAM_OK;
+}
+
+int b200slam_mappoints_grow(b200slam_ctx *ctx, float threshold, int *added)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    const int before = ctx->mp_size;
+    const bool dev = ctx->mp_n_dev;
+    int rc = mappoints_grow_queue(ctx, threshold);
     if (rc) return rc;
-    ctx->mp_size += ctx->h_front->count;
+    rc = fetch_front(ctx);                  // device-side size: ctx->mp_size <- exact
+    if (rc) return rc;
+    if (!dev) ctx->mp_size = before + ctx->h_front->count;
     if (added) *added = ctx->h_front->count;
+    return B200SLAM_OK;
+}
+
+int b200slam_mappoints_grow_async(b200slam_ctx *ctx, float threshold)
+{
+    if (!ctx) return B200SLAM_ERR_ARG;
+    int rc = ensure_front(ctx);
+    if (rc) return rc;
+    if (!ctx->mp_n_dev) {                   // from here on the device keeps the size
+        set_int_kernel<<<1, 1, 0, ctx->stream>>>(&ctx->d_front->mp_n, ctx->mp_size);
+        LAUNCH_CHECK(ctx);
+        ctx->mp_n_dev = true;
+    }
+    rc = mappoints_grow_queue(ctx, threshold);
+    if (rc) return rc;
+    ctx->mp_size += ctx->nbeams;            // upper bound until the size is read back
     return B200SLAM_OK;
 }
 
@@ -363,9 +451,10 @@ int b200slam_local_map_extract(b200slam_ctx *ctx, float border, int *size)
     if (rc) return rc;
     local_map_kernel<<<1, FE_THREADS, 0, ctx->stream>>>(ctx->d_scan_t, ctx->d_scan_t + ctx->scan_t_cap, ctx->nbeams, border,
                                                         ctx->d_mp, ctx->d_mp + ctx->mp_cap, ctx->mp_size, ctx->d_points,
-                                                        ctx->d_points + ctx->points_cap, ctx->d_front);
+                                                        ctx->d_points + ctx->points_cap, ctx->d_front, ctx->scan_n_dev,
+                                                        ctx->mp_n_dev);
     LAUNCH_CHECK(ctx);
-    rc = fetch_front(ctx);
+    rc = fetch_front(ctx);                  // also replaces the host's upper bounds of the scan / map sizes
     if (rc) return rc;
     ctx->local_n = ctx->h_front->count;
     for (int i = 0; i < 4; ++i) ctx->local_bbox[i] = ctx->h_front->bbox[i];

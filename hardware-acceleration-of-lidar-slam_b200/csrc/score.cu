@@ -288,6 +288,9 @@ struct LatticeArgs {
     int rr_clamp;             // row reuse: index of an invalid beam, -(8 * pitch + 1): its K <= 9 row reads all land in the zero region
     const float *scan_x, *scan_y;
     int nbeams;
+    const int *nbeams_dev;    // not null: the scan's size as the device knows it (asynchronous scan loop; nbeams is an upper bound)
+    int seeded;               // 3 x 3 x 3 lattice centred on the winner of the match in front (b200slam_fastmatch_pair_async):
+                              // the parameter block holds ct[3][3] | st[3][3] | sxt[3][3] | syt[3][3], one row per possible seed
     float ipixel;
     const float *tables;      // device copy of ct|st|sxt|syt, or nullptr: use the parameter block
     int nth, ntx, nty;
@@ -345,6 +348,21 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     pdl_launch_dependents();                      // the next scan-matching kernel may start
     const float *tab = A.tables ? A.tables : T.v;
     const float *ctT = tab, *stT = tab + A.nth_tab, *sxtT = tab + 2 * A.nth_tab, *sytT = sxtT + A.ntx;
+    const int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
+    if constexpr (COUNT) {
+        if (A.seeded) {
+            // The lattice is centred on the winner of the match in front (main.c:909-918: FastMatch2 starts from
+            // FastMatch's result).  Each axis of that winner is one of three values, so the host has sent the axis
+            // tables of all three; wait for the match in front, read its winner and pick.  Its key stays in
+            // match->seed_key (this kernel's tail overwrites match->key).
+            pdl_wait_prior_grids();
+            const unsigned long long k1 = *reinterpret_cast<volatile unsigned long long *>(&A.match->key);
+            const int lin1 = k1 == ~0ull ? 13 : (int)(k1 & 0xffffffffull);          // nothing scored cannot happen for a full lattice
+            const int ith1 = lin1 / 9, itx1 = (lin1 / 3) % 3, ity1 = lin1 % 3;
+            ctT = tab + 3 * ith1; stT = tab + 9 + 3 * ith1; sxtT = tab + 18 + 3 * itx1; sytT = tab + 27 + 3 * ity1;
+            if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) A.match->seed_key = k1;
+        }
+    }
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -367,8 +385,8 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
 #pragma unroll
         for (int j = 0; j < TYPT; ++j) acc[j] = 0.0f;            // main.c:507
 
-        for (int c0 = 0; c0 < A.nbeams; c0 += A.cb) {
-            const int cb = min(A.cb, A.nbeams - c0);
+        for (int c0 = 0; c0 < nbeams; c0 += A.cb) {
+            const int cb = min(A.cb, nbeams - c0);
             __syncthreads();
             for (int i = tid; i < cb; i += NT) {
                 const float psx = __fmul_rn(A.scan_x[c0 + i], A.ipixel);     // main.c:418
@@ -608,7 +626,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
             cand[which].ct = ctT[jth - A.th_first]; cand[which].st = stT[jth - A.th_first];
             cand[which].sxt = sxtT[itx]; cand[which].syt = sytT[ity];
         }
-        trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand,
+        trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, nbeams, A.ipixel, cand,
                        A.hit_values, A.hit_values + A.hit_stride, tail_red, hits);
     }
     int written = hits[1];
@@ -630,7 +648,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                 int n2[2];
                 float *tail = A.hit_values + A.hit_stride;
                 __syncthreads();
-                trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, A.nbeams, A.ipixel, cand, tail,
+                trace_pair<NT>(A.field, A.pitch, A.rows, A.cols, A.scan_x, A.scan_y, nbeams, A.ipixel, cand, tail,
                                tail, tail_red, n2, written, written);
                 written = nc;
             }
@@ -675,6 +693,7 @@ struct PosesArgs {
     int pitch, rows, cols;
     const float *scan_x, *scan_y;
     int nbeams;
+    const int *nbeams_dev;    // not null: the device's own scan size
     float ipixel, min_x, min_y;
     const float *px, *py, *ct, *st;    // [P]
     long long P, index_base;
@@ -711,8 +730,9 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
     const unsigned upitch = (unsigned)A.pitch;
     const float *field11 = A.field11;                    // &field[1][1] (from the host: one uniform base pointer)
     const int zero_off = A.zero_off;                     // field11 + zero_off == field[-1] == 0
-    for (int c0 = 0; c0 < A.nbeams; c0 += POSES_CB) {
-        const int cb = min(POSES_CB, A.nbeams - c0);
+    const int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
+    for (int c0 = 0; c0 < nbeams; c0 += POSES_CB) {
+        const int cb = min(POSES_CB, nbeams - c0);
         constexpr int U = 8, NBUF = 3;
         const int cbp = (cb + NBUF * U - 1) / (NBUF * U) * (NBUF * U);
         __syncthreads();
@@ -865,6 +885,8 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     A.field = m->d_field; A.pitch = m->field_pitch; A.rows = m->rows; A.cols = m->cols;
     A.rr_clamp = -((B200SLAM_FIELD_PAD_ROWS - 1) * m->field_pitch + 1);
     A.scan_x = ctx->d_scan_x; A.scan_y = ctx->d_scan_y; A.nbeams = ctx->nbeams;
+    A.nbeams_dev = ctx->scan_n_dev ? &ctx->d_front->scan_n : nullptr;
+    A.seeded = L.seeded ? 1 : 0;
     A.ipixel = 1 / m->pixel_size;                                        // main.c:383
     A.nth = L.nth; A.ntx = L.ntx; A.nty = L.nty;
     A.row_begin = L.row_begin; A.row_end = L.row_end;
@@ -879,7 +901,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     if (L.exchange && ctx->p2p_ready) A.xchg = xchg_args(ctx);
     LatticeTables T;                     // parameter block (copied at launch)
     A.nth_tab = L.nth_tab;
-    if (!L.d_tables) memcpy(T.v, L.h_tables, sizeof(float) * (2 * (size_t)L.nth_tab + L.ntx + L.nty));
+    if (!L.d_tables) memcpy(T.v, L.h_tables, sizeof(float) * (L.seeded ? 36 : 2 * (size_t)L.nth_tab + L.ntx + L.nty));
     if (L.row_end <= L.row_begin) {
         if (A.xchg.peers) {             // nothing to score, but the peers wait for this rank's post
             exchange_only_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_match, A.xchg, A.post_deferred, A.collect_prev);
@@ -908,9 +930,10 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     // groups 24.9 / 31.6 us, 32 x 8 tiles 27.1 / 27.4 us, 32 x 32 tiles 33.3 / 23.2 us.
     // FastMatch-sized lattices (the reference's 3 x 3 x 3): one candidate per thread with per-candidate
     // hit counts, so that the tail can leave bestHits[] exactly as the reference's loop does.
-    if (!getenv("B200SLAM_LATTICE_CFG") && (long long)L.nth * L.ntx * L.nty <= MATCH_SMALL && L.row_begin == 0 &&
+    if ((L.seeded || !getenv("B200SLAM_LATTICE_CFG")) && (long long)L.nth * L.ntx * L.nty <= MATCH_SMALL && L.row_begin == 0 &&
         L.row_end == (int64_t)L.nth * L.ntx && !A.xchg.peers && L.nth_tab == L.nth)
         return launch_lattice_cfg<1, 1, 4, 1, true>(ctx, A, T, nth_cover);
+    if (L.seeded) return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "a seeded match is a whole 3 x 3 x 3 lattice on one GPU");
     // Row reuse (template parameter Q): usable when the ty step is pixel / Q, measured on the ty axis table
     // itself (host copy).  The kernel verifies every (beam, ty group) exactly, so a wrong guess here only
     // costs time, never a bit of the result.
@@ -982,6 +1005,7 @@ int poses_launch(b200slam_ctx *ctx, const b200slam_map *m, int64_t P, int64_t in
     A.field = m->d_field; A.pitch = m->field_pitch; A.rows = m->rows; A.cols = m->cols;
     A.field11 = m->d_field + m->field_pitch + 1; A.zero_off = -(m->field_pitch + 2);
     A.scan_x = ctx->d_scan_x; A.scan_y = ctx->d_scan_y; A.nbeams = ctx->nbeams;
+    A.nbeams_dev = ctx->scan_n_dev ? &ctx->d_front->scan_n : nullptr;
     A.ipixel = 1 / m->pixel_size;
     A.min_x = m->top_left_x; A.min_y = m->top_left_y;
     A.px = ctx->d_pose_soa; A.py = A.px + ctx->pose_cap; A.ct = A.py + ctx->pose_cap;

@@ -6,16 +6,29 @@
  * first scan initialises the map, then per scan readAScan -> (after a mini update: Transform,
  * ExtractLocalMap, OccupationalGrid + both distance transforms) -> constant-velocity guess ->
  * FastMatch on the coarse or FastMatch2 on the fine grid -> FastMatch2 refinement -> mini-update
- * test -> map growth.  The scan, the map points, the local map, both grids and both distance
- * fields never leave the GPU: per scan 4 bytes per beam go up, and the scan size, the matched
- * poses and the local-map / growth counts come back.  Output is the reference's, byte for byte:
- * "scan N" / "pose = ..." lines (main.c:860, 965) and the map dump "%f,%f\n" (main.c:983-985).
+ * test -> map growth.
+ *
+ * Nothing but poses crosses PCIe in the steady state:
+ *   - the dataset is read once, uploaded as raw text and parsed ON THE GPU (b200slam_csv_ingest: the
+ *     reference's fscanf("%f,") loop, main.c:22-30, bit for bit); readAScan then reads its ranges from
+ *     the resident values;
+ *   - per scan the host queues readAScan and the FastMatch / FastMatch2 pair (three kernels, no host step
+ *     between them: scan.size stays on the device, and the second match picks its lattice by the first
+ *     one's winner) and synchronises ONCE to fetch the two poses it needs for the motion model, the
+ *     mini-update test (main.c:875-898, 928-940) and the next lattice's cosf / sinf;
+ *   - map growth (main.c:942-948) is queued without reading its count back; only a map rebuild (2 % of
+ *     the scans) reads sizes, because the grid geometry is computed with the reference's host float
+ *     operations (main.c:272-305).
+ * Output is the reference's, byte for byte: "scan N" / "pose = ..." lines (main.c:860, 965) and the map
+ * dump "%f,%f\n" (main.c:983-985).
  *
  *     b200slam_replay <lidar.csv> <map_out.csv> [nscans = 3480]
+ *     B200SLAM_REPLAY_HOST_PARSE=1: parse with the host's fscanf and upload 4 bytes per beam per scan instead
  */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 
 #include "b200slam.h"
@@ -66,6 +79,7 @@ int main(int argc, char **argv)
         return 2;
     }
     const int row = argc > 3 ? atoi(argv[3]) : 3480;          /* main_accelerated.c:6 */
+    const int host_parse = getenv("B200SLAM_REPLAY_HOST_PARSE") != NULL;
     clock_t start = clock();
 
     float pose[3] = {0, 0, 0};
@@ -96,30 +110,58 @@ int main(int argc, char **argv)
     must(b200slam_map_create(ctx, 200, 200, &coarse), "map_create");     /* main.c:201 */
     must(b200slam_map_create(ctx, 400, 400, &fine), "map_create");       /* main.c:207 */
 
+    /* the dataset: raw text -> GPU -> floats (readDatasetLineByLine, main.c:22-30, for every row at once) */
+    double t_parse = 0.0;
+    int64_t nvalues = 0;
+    if (!host_parse) {
+        const double tp = now_s();
+        fseek(fp, 0, SEEK_END);
+        const long nbytes = ftell(fp);
+        fseek(fp, 0, SEEK_SET);
+        char *text = NULL;
+        must(b200slam_host_alloc(ctx, (size_t)(nbytes > 0 ? nbytes : 1), (void **)&text), "host_alloc");
+        if (nbytes > 0 && fread(text, 1, (size_t)nbytes, fp) != (size_t)nbytes) { fprintf(stderr, "short read\n"); return 1; }
+        must(b200slam_csv_ingest(ctx, text, (size_t)nbytes, NULL, (int64_t)row * COLUMN, &nvalues), "csv_ingest");
+        must(b200slam_host_free(ctx, text), "host_free");
+        t_parse = now_s() - tp;
+        if (nvalues < COLUMN) { fprintf(stderr, "empty dataset\n"); return 1; }
+    }
+
     float (*path)[3] = malloc(sizeof(float[3]) * (size_t)(row > 0 ? row : 1));
     float map_pose[3];
     int size = 0;
 
     /* scan 0 (main.c:843-853) */
-    if (read_row(fp, ranges) != 1) { fprintf(stderr, "empty dataset\n"); return 1; }
-    must(b200slam_scan_read(ctx, ranges, 24, &size), "scan_read");
+    if (host_parse) {
+        if (read_row(fp, ranges) != 1) { fprintf(stderr, "empty dataset\n"); return 1; }
+        must(b200slam_scan_read_async(ctx, ranges, 24), "scan_read");
+    } else {
+        must(b200slam_scan_read_resident_async(ctx, 0, 24), "scan_read");
+    }
     must(b200slam_scan_transform(ctx, pose), "scan_transform");
     must(b200slam_mappoints_from_scan(ctx), "mappoints_from_scan");      /* Initialise */
     for (int i = 0; i < 3; i++) { map_pose[i] = pose[i]; path[0][i] = pose[i]; }
 
     int miniUpdated = 1, path_iter = 1, rebuilds = 0;
-    double t_parse = 0.0;
     const double t_loop = now_s();
     for (int scan_iter = 1; scan_iter < row; scan_iter++) {
         printf("scan %d\n", scan_iter + 1);
-        const double tp = now_s();
-        const int got = read_row(fp, ranges);
-        t_parse += now_s() - tp;
-        if (got != 1) {
-            fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
-            return 1;
+        if (host_parse) {
+            const double tp = now_s();
+            const int got = read_row(fp, ranges);
+            t_parse += now_s() - tp;
+            if (got != 1) {
+                fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
+                return 1;
+            }
+            must(b200slam_scan_read_async(ctx, ranges, 24), "scan_read");
+        } else {
+            if ((int64_t)(scan_iter + 1) * COLUMN > nvalues) {
+                fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
+                return 1;
+            }
+            must(b200slam_scan_read_resident_async(ctx, (int64_t)scan_iter * COLUMN, 24), "scan_read");
         }
-        must(b200slam_scan_read(ctx, ranges, 24, &size), "scan_read");
         int scan_transform_flag = 0;
         if (miniUpdated) {                                                /* main.c:865-872 */
             must(b200slam_scan_transform(ctx, pose), "scan_transform");
@@ -138,18 +180,18 @@ int main(int argc, char **argv)
         } else {
             for (int i = 0; i < 3; i++) pose_guess[i] = pose[i];
         }
-        /* main.c:901-922 */
-        float matched[3];
-        must(b200slam_fastmatch(ctx, miniUpdated ? coarse : fine, pose_guess, fastResolution, matched, NULL, NULL),
-             "fastmatch");
-        must(b200slam_fastmatch(ctx, fine, matched, fastResolution2, pose, NULL, NULL), "fastmatch2");
+        /* main.c:901-922: FastMatch (coarse grid after a rebuild, else the fine one) then FastMatch2 from its
+         * result -- two kernels back to back, one synchronisation */
+        must(b200slam_fastmatch_pair_async(ctx, miniUpdated ? coarse : fine, fine, pose_guess, fastResolution,
+                                           fastResolution2), "fastmatch pair");
+        must(b200slam_fastmatch_pair_fetch(ctx, NULL, pose, &size, NULL), "fastmatch pair fetch");
         /* mini update, main.c:928-961 */
         float dp[3];
         for (int i = 0; i < 3; i++) dp[i] = fabsf(pose[i] - map_pose[i]);
         if (dp[0] > miniUpdateDT || dp[1] > miniUpdateDT || dp[2] > miniUpdateDR) {
             miniUpdated = 1;
             if (!scan_transform_flag) must(b200slam_scan_transform(ctx, pose), "scan_transform");
-            must(b200slam_mappoints_grow(ctx, 1.5f, NULL), "mappoints_grow");
+            must(b200slam_mappoints_grow_async(ctx, 1.5f), "mappoints_grow");
             for (int i = 0; i < 3; i++) map_pose[i] = pose[i];
         } else {
             miniUpdated = 0;
@@ -171,10 +213,11 @@ int main(int argc, char **argv)
     if (!fp1) { fprintf(stderr, "cannot write %s\n", argv[2]); return 1; }
     for (int j = 0; j < n; j++) fprintf(fp1, "%f,%f\n", mx[j], my[j]);   /* main.c:983-985 */
     fclose(fp1);
-    fprintf(stderr, "b200slam_replay: %d scans, %d map points, %d map rebuilds, %llu kernel launches; loop %.3f s wall "
-                    "of which CSV parsing %.3f s -> %.1f us per scan on the device path\n", row, n, rebuilds,
-            (unsigned long long)b200slam_launch_count(ctx), loop_s, t_parse,
-            row > 1 ? 1e6 * (loop_s - t_parse) / (row - 1) : 0.0);
+    const double dev_s = loop_s - (host_parse ? t_parse : 0.0);
+    fprintf(stderr, "b200slam_replay: %d scans, %d map points, %d map rebuilds, %llu kernel launches; dataset %s in %.4f s; "
+                    "loop %.3f s wall -> %.1f us per scan on the device path\n", row, n, rebuilds,
+            (unsigned long long)b200slam_launch_count(ctx), host_parse ? "parsed by fscanf" : "read + parsed on the GPU",
+            t_parse, loop_s, row > 1 ? 1e6 * dev_s / (row - 1) : 0.0);
     free(mx); free(my); free(path);
     b200slam_map_destroy(ctx, coarse);
     b200slam_map_destroy(ctx, fine);

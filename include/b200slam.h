@@ -245,6 +245,47 @@ int b200slam_local_map_download(b200slam_ctx *ctx, float *x, float *y, int *size
 int b200slam_map_rasterise_local(b200slam_ctx *ctx, b200slam_map *map, float pixel_size, int *rows, int *cols,
                                  float top_left[2]);
 
+/* ---- the per-scan loop without host round trips -------------------------
+ * The reference's loop (main.c:859-970) needs the host only where glibc's cosf / sinf define the bits: the lattice
+ * tables of the two matches and Transform.  Everything else can stay queued:
+ *
+ *   b200slam_scan_read_async        readAScan without reading scan.size back: the size stays on the device
+ *                                   and every kernel that needs it (Transform, ExtractLocalMap, the matchers)
+ *                                   reads it there; the host keeps an upper bound until a call returns it
+ *   b200slam_scan_read_resident_async  the same from the values of b200slam_csv_ingest (nothing crosses PCIe)
+ *   b200slam_fastmatch_pair_async   FastMatch on map_a around `pose` with res_a, then FastMatch2 on map_b
+ *                                   around FastMatch's result with res_b (main.c:902-918), as two kernels
+ *                                   with no host step between them: the result of the first is one of
+ *                                   3 x 3 x 3 lattice points, so the host sends the second lattice's axis tables
+ *                                   for each of the three possible centres per axis (27 cosf / sinf calls,
+ *                                   the same float operations as b200slam_fastmatch would do after fetching)
+ *                                   and the second kernel picks by the first one's winner.  bestHits[] /
+ *                                   bestHits_size are left as after FastMatch2 (what main.c:942-948 reads).
+ *   b200slam_fastmatch_pair_fetch   ONE synchronisation per scan: both poses, scan.size, bestHits_size
+ *   b200slam_mappoints_grow_async   main.c:942-948 without reading newPointSize back (the map's size stays
+ *                                   on the device, like the scan's)
+ * b200slam_scan_transform, b200slam_local_map_extract, b200slam_mappoints_download, ... work on either kind
+ * of state; the ones that return a size also refresh the host's copy. */
+int b200slam_scan_read_async(b200slam_ctx *ctx, const float *ranges, int max_range);
+int b200slam_scan_read_resident_async(b200slam_ctx *ctx, int64_t first_value, int max_range);
+int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200slam_map *map_b, const float pose[3],
+                                  const float res_a[3], const float res_b[3]);
+int b200slam_fastmatch_pair_fetch(b200slam_ctx *ctx, float pose_a[3], float pose_b[3], int *scan_size, int *best_hits_size);
+int b200slam_mappoints_grow_async(b200slam_ctx *ctx, float threshold);
+
+/* ---- scan ingest -----------------------------------------------------------
+ * Replaces readDatasetLineByLine (Subsystem_1/main.c:22-30): `column` x fscanf(fp, "%f,", &value).  The whole
+ * CSV text (values separated by ',' and / or white space) is parsed ON THE GPU: one upload of the raw bytes,
+ * then every value is converted in parallel -- bit-identical to glibc's correctly rounded %f conversion (the
+ * few tokens a double division cannot settle, and anything that is not a plain decimal, are converted by the
+ * host's strtof, the function fscanf itself calls).  values_out (optional, host, max_values floats) receives
+ * the values; they also stay on the device for b200slam_scan_read_resident_async.  B200SLAM_ERR_ARG for a
+ * token that is not a number. */
+int b200slam_csv_ingest(b200slam_ctx *ctx, const char *text, size_t nbytes, float *values_out, int64_t max_values,
+                        int64_t *count);
+/* Device pointer and count of the ingested values. */
+int b200slam_csv_values(b200slam_ctx *ctx, const float **device_values, int64_t *count);
+
 /* ---- scheduling hint -------------------------------------------------------------------
  * (Also read by the distance transform: with many independent transforms in flight it takes taller
  * row chunks per CTA -- less halo work per cell -- where a single transform prefers more, shorter CTAs.)

@@ -77,6 +77,8 @@ class Oracle:
         L.orc_lidar_angles.argtypes = [C.c_float, C.c_float, C.c_int, c_float_p]
         L.orc_read_scan.restype = C.c_int
         L.orc_read_scan.argtypes = [c_float_p, c_float_p, C.c_int, C.c_float, C.c_int, c_float_p, c_float_p]
+        L.orc_read_csv.restype = C.c_long
+        L.orc_read_csv.argtypes = [C.c_char_p, c_float_p, C.c_long]
         L.orc_transform.restype = None
         L.orc_transform.argtypes = [c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, c_float_p]
         L.orc_extract_local_map.restype = C.c_int
@@ -139,6 +141,13 @@ class Oracle:
         x, y = np.empty(len(r), np.float32), np.empty(len(r), np.float32)
         n = self.lib.orc_read_scan(_fp(r), _fp(a), len(r), range_min, int(max_range), _fp(x), _fp(y))
         return x[:n].copy(), y[:n].copy()
+
+    def read_csv(self, path: str, max_values: int) -> np.ndarray:
+        """fscanf("%f,") over the whole file (main.c:22-30)."""
+        out = np.empty(max(max_values, 1), np.float32)
+        n = self.lib.orc_read_csv(path.encode(), _fp(out), max_values)
+        assert n >= 0, path
+        return out[:n].copy()
 
     def transform(self, x, y, pose):
         x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
@@ -299,6 +308,26 @@ class Reference:
             self.scan = RefScanData.in_dll(self.lib, "scan")
             self.occ_grid = RefMyGrid.in_dll(self.lib, "occ_grid")
             self.fmp = RefFastMatchParameters.in_dll(self.lib, "FastMatchParameters")
+
+    def read_dataset_rows(self, path: str, nrows: int) -> np.ndarray:
+        """The reference's own readDatasetLineByLine (main.c:22-30) on `path`, nrows times: each call fills the
+        global test_input_memory[1079] from a libc FILE*."""
+        libc = C.CDLL("libc.so.6")
+        libc.fopen.restype = C.c_void_p
+        libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+        libc.fclose.argtypes = [C.c_void_p]
+        fn = self.lib.readDatasetLineByLine
+        fn.restype = None
+        fn.argtypes = [C.c_void_p]
+        mem = (C.c_float * 1079).in_dll(self.lib, "test_input_memory")
+        fp = libc.fopen(path.encode(), b"r")
+        assert fp, path
+        rows = np.empty((nrows, 1079), np.float32)
+        for r in range(nrows):
+            fn(fp)
+            rows[r] = np.frombuffer(mem, np.float32)
+        libc.fclose(fp)
+        return rows
 
     def edt(self, occ: np.ndarray, fine: bool = False) -> np.ndarray:
         """Reference EDT on a rows x cols grid (<=200^2 coarse / <=400^2 fine), called exactly as

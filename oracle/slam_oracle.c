@@ -10,6 +10,7 @@
 #include "slam_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -540,4 +541,17 @@ int orc_grow_map(const float *best_hits, int best_hits_size, const float *tx, co
         }
     }
     return newPointSize;
+}
+
+/* Subsystem_1/main.c:22-30 (readDatasetLineByLine): the dataset is read with fscanf(filename, "%f,", &value),
+ * `column` values per scan.  Same call, until end of file. */
+long orc_read_csv(const char *path, float *out, long max_values)
+{
+    FILE *fp = fopen(path, "r");
+    if (!fp) return -1;
+    long n = 0;
+    float value;
+    while (n < max_values && fscanf(fp, "%f,", &value) == 1) out[n++] = value;     /* main.c:27 */
+    fclose(fp);
+    return n;
 }

@@ -56,6 +56,10 @@ int orc_occupational_grid(const float *x, const float *y, int n, float pixel_siz
 void orc_lidar_angles(float angle_min, float angle_increment, int n, float *angles);
 /* readAScan, main.c:71-95: drops r < range_min | r > max_range (int), x = r * cosf(a),
  * y = r * sinf(a), compacted in beam order.  Returns scan.size. */
+/* readDatasetLineByLine (Subsystem_1/main.c:22-30) applied to a whole file: fscanf(fp, "%f,", &value) until it
+ * stops converting; returns the number of values (at most max_values). */
+long orc_read_csv(const char *path, float *out, long max_values);
+
 int orc_read_scan(const float *ranges, const float *angles, int n, float range_min, int max_range,
                   float *x, float *y);
 /* Transform, main.c:97-118. */

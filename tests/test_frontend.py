@@ -133,3 +133,59 @@ def test_device_chain_scan_to_pose_and_growth(ctx, oracle, synth, fg):
     finally:
         for m in gm:
             m.close()
+
+
+@pytest.mark.gpu
+def test_fastmatch_pair_equals_two_fastmatch_calls(b200slam, oracle, synth):
+    """b200slam_fastmatch_pair_async: FastMatch then FastMatch2 from its result (main.c:902-918) as two kernels
+    with no host step between them -- the second picks its lattice by the first one's winner on the device --
+    and the scan's size kept on the device (b200slam_scan_read_async).  Poses, bestHits_size and the bestHits[]
+    twin must equal two synchronous b200slam_fastmatch calls and the oracle, also where the 27 candidates'
+    hit counts differ (poses at the grid's edge) and with beams that readAScan drops."""
+    w = synth.make_workload("tiny")
+    field = oracle.edt(w["occ"])
+    coarse_occ = w["occ"].reshape(w["occ"].shape[0] // 2, 2, w["occ"].shape[1] // 2, 2).max(axis=(1, 3)).astype(np.int32)
+    cfield = oracle.edt(coarse_occ)
+    pixel_c, tl_c = synth.centred_geometry(coarse_occ.shape[0], coarse_occ.shape[1], 0.2)
+    angles = oracle.lidar_angles()
+    rng = np.random.default_rng(11)
+    ranges = rng.uniform(0.5, 9.0, len(angles)).astype(np.float32)
+    ranges[rng.choice(len(angles), 90, replace=False)] = 30.0           # dropped by readAScan (main.c:78)
+    ranges[5] = 0.01
+    sx, sy = oracle.read_scan(ranges, angles)
+    om_f = oracle.make_map(field, w["pixel"], w["top_left"])
+    om_c = oracle.make_map(cfield, pixel_c, tl_c)
+    res_a = np.array([0.05, 0.05, 0.008727], np.float32)
+    res_b = np.array([0.025, 0.025, 0.004363], np.float32)
+    poses = [np.array([w["pose0"][0] + 1.7 * k, w["pose0"][1] + 1.1 * k, w["pose0"][2] + 0.3 * k], np.float32) for k in range(9)]
+    with b200slam.Context(0) as ca, b200slam.Context(0) as cb:
+        maps = {}
+        for c in (ca, cb):
+            mf = c.new_map(*field.shape); mf.set_geometry(w["pixel"], w["top_left"]).upload_field(field)
+            mc = c.new_map(*cfield.shape); mc.set_geometry(pixel_c, tl_c).upload_field(cfield)
+            maps[c] = (mc, mf)
+            c.lidar_set(angles, 0.023)
+        obuf = np.zeros(2500, np.float32)
+        sbuf = np.zeros(2500, np.float32)
+        for k, p in enumerate(poses):
+            first_c = k % 2 == 0                                       # coarse grid after a rebuild, else the fine one
+            # oracle
+            o1, _, _ = oracle.fastmatch(om_c if first_c else om_f, sx, sy, p, res_a, hits_buf=obuf)
+            o2, _, on = oracle.fastmatch(om_f, sx, sy, o1, res_b, hits_buf=obuf)
+            # two synchronous calls, host-known scan size
+            n = ca.scan_read(ranges)
+            assert n == len(sx)
+            s1, _, _ = ca.fastmatch(maps[ca][0] if first_c else maps[ca][1], p, res_a, hits_buf=sbuf)
+            s2, _, sn = ca.fastmatch(maps[ca][1], s1, res_b, hits_buf=sbuf)
+            # the pair, scan size on the device
+            cb.scan_read_async(ranges)
+            cb.fastmatch_pair_async(maps[cb][0] if first_c else maps[cb][1], maps[cb][1], p, res_a, res_b)
+            pa, pb, pn, pbh = cb.fastmatch_pair_fetch()
+            assert pn == n
+            assert np.array_equal(bits(pa), bits(o1)) and np.array_equal(bits(pb), bits(o2)) and pbh == on, k
+            assert np.array_equal(bits(s1), bits(o1)) and np.array_equal(bits(s2), bits(o2)) and sn == on, k
+            assert np.array_equal(bits(cb.match_fetch_hits(2500)), bits(obuf)), k
+            assert np.array_equal(bits(sbuf), bits(obuf)), k
+        for c in (ca, cb):
+            for m in maps[c]:
+                m.close()

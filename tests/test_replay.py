@@ -76,16 +76,22 @@ def test_dropin_replay_is_byte_identical(reference_run, dataset, b200slam):
 
 
 @pytest.mark.gpu
-def test_device_resident_replay_is_byte_identical(reference_run, dataset, b200slam):
+@pytest.mark.parametrize("host_parse", [False, True])
+def test_device_resident_replay_is_byte_identical(reference_run, dataset, b200slam, host_parse):
     """b200slam_replay (host/slam_replay.c): the control flow of the reference's main() in C over the ABI,
     with readAScan / Transform / ExtractLocalMap / OccupationalGrid / both EDTs / FastMatch / FastMatch2 / map
-    growth all on the device.  Same pose trace, same map dump, byte for byte --
-    which also pins the inline map-growth code of main() (main.c:942-948) end to end."""
+    growth all on the device, the dataset parsed on the GPU (rank 4; host_parse: by the
+    host's fscanf instead), one synchronisation per scan (FastMatch and FastMatch2 queued as a pair, sizes kept
+    on the device).  Same pose trace, same map dump, byte for byte -- which also pins the inline map-growth code
+    of main() (main.c:942-948) end to end."""
     d, csv = dataset
     exe = os.path.join(os.path.dirname(b200slam.LIB_PATH), "b200slam_replay")
     assert os.path.exists(exe), "b200slam_replay missing: run __graft_entry__.build()"
     mapout = str(d / "map_dev.csv")
-    p = subprocess.run([exe, csv, mapout, str(NSCANS)], capture_output=True, text=True, timeout=900)
+    env = dict(os.environ)
+    if host_parse:
+        env["B200SLAM_REPLAY_HOST_PARSE"] = "1"
+    p = subprocess.run([exe, csv, mapout, str(NSCANS)], capture_output=True, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     gpu_lines = [ln for ln in p.stdout.splitlines() if not ln.startswith("time taken")]
     ref_lines, ref_map = reference_run
