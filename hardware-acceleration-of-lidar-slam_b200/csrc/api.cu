@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <new>
 
@@ -101,7 +102,7 @@ void b200slam_destroy(b200slam_ctx *ctx)
     cudaFree(ctx->d_scan_x); cudaFreeHost(ctx->h_scan); cudaFreeHost(ctx->h_hit_values);
     if (ctx->scan_event) cudaEventDestroy(ctx->scan_event);
     cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
-    cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match);
+    cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match); cudaFreeHost(ctx->h_result);
     cudaFree(ctx->d_keys); cudaFreeHost(ctx->h_keys); cudaFree(ctx->d_hit_values);
     cudaFree(ctx->d_scores);
     particles_unshare_blocks(ctx);
@@ -796,6 +797,12 @@ int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200sl
     L.d_scores = nullptr;
     L.exchange = L.collect_prev = L.post_deferred = false;
     L.seeded = true;
+    if (!ctx->h_result) {
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_result, sizeof(MatchHost), cudaHostAllocMapped));
+        memset(ctx->h_result, 0, sizeof(MatchHost));
+    }
+    L.host_result = true;
+    ctx->result_seq++;
     rc = lattice_launch(ctx, L);
     if (rc) return rc;
     ctx->last.valid = true; ctx->last.is_poses = false; ctx->last.gathered = false; ctx->last.exchanged = false;
@@ -812,16 +819,31 @@ int b200slam_fastmatch_pair_fetch(b200slam_ctx *ctx, float pose_a[3], float pose
 {
     if (!ctx) return B200SLAM_ERR_ARG;
     if (!ctx->pair.valid) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no b200slam_fastmatch_pair_async queued");
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_match, ctx->d_match, sizeof(MatchDev), cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->d_front)
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_front, ctx->d_front, sizeof(*ctx->d_front), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    const MatchDev &m = *ctx->h_match;
-    if (m.error) return device_error_check(ctx, m.error);
-    if (ctx->d_front) {
-        if (ctx->scan_n_dev) ctx->nbeams = ctx->h_front->scan_n;
-        if (ctx->mp_n_dev) ctx->mp_size = ctx->h_front->mp_n;
+    // The second kernel's tail writes the result block into mapped host memory, seq last: watch it arrive (no
+    // copy queued, no driver call).  Bounded: after two seconds fall back to a stream synchronisation, which
+    // also surfaces a launch failure.
+    volatile MatchHost *h = ctx->h_result;
+    {
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        unsigned spins = 0;
+        while (h->seq != ctx->result_seq) {
+            if ((++spins & 0xfffu) == 0) {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > 2.0) {
+                    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                    if (h->seq != ctx->result_seq)
+                        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "pair match finished without publishing its result");
+                }
+            }
+        }
+        __sync_synchronize();
     }
+    MatchHost m;
+    m.key = h->key; m.seed_key = h->seed_key; m.best_hits = h->best_hits; m.error = h->error;
+    if (m.error) return device_error_check(ctx, m.error);
+    if (ctx->scan_n_dev) ctx->nbeams = h->scan_n;
+    if (ctx->mp_n_dev) ctx->mp_size = h->mp_n;
     if (m.key == ~0ull || m.seed_key == ~0ull) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "pair match scored nothing");
     const int l1 = (int)(m.seed_key & 0xffffffffull), l2 = (int)(m.key & 0xffffffffull);
     float pa[3];

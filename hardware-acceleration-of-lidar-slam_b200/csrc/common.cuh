@@ -65,6 +65,15 @@ struct MatchDev {
     unsigned long long seed_key;    // b200slam_fastmatch_pair_async: the FIRST match's key, saved by the second (seeded) one
 };
 static_assert(sizeof(MatchDev::outbox) / sizeof(MatchDev::Outbox) == 64, "outbox ring == XCHG_EPOCHS");
+// Result block in MAPPED pinned host memory: the tail of the second kernel of a b200slam_fastmatch_pair_async
+// writes it straight over PCIe (seq last, behind a system-scope fence), so the host neither queues a copy nor
+// calls into the driver to learn the result -- it watches seq.
+struct MatchHost {
+    unsigned long long key, seed_key;
+    int best_hits, last_hits, written_hits, scan_n, mp_n;
+    unsigned int error;
+    unsigned long long seq;
+};
 constexpr int MATCH_SMALL = 64;
 // Every device-side wait is bounded (%globaltimer against b200slam_ctx::spin_timeout_ns, or an iteration
 // cap for the TMA barrier): a dead or mis-ordered peer costs a timeout and an error code, never a hung GPU.
@@ -216,6 +225,8 @@ struct b200slam_ctx {
     int64_t csv_count = 0;
     // b200slam_fastmatch_pair_async bookkeeping (host side)
     struct { bool valid = false; float guess[3], step_a[3], step_b[3]; } pair;
+    MatchHost *h_result = nullptr;        // mapped pinned (host pointer == device pointer under UVA)
+    unsigned long long result_seq = 0;
 
     // generic EDT scratch (u16 column distances)
     uint16_t *d_edt_scratch = nullptr;
@@ -281,6 +292,7 @@ struct LatticeLaunch {
     bool exchange;     // post the result to the other ranks through peer memory from the kernel's tail
     bool collect_prev; // ... and merge the previous, deferred exchange in the same tail
     bool post_deferred; // record the result in the outbox only; the next collect kernel posts it
+    bool host_result = false;   // the kernel's tail also writes the result into ctx->h_result (mapped host memory)
     bool seeded = false;   // 3 x 3 x 3 lattice centred on the winner of the match in front: h_tables holds all three
                            // candidate table sets (36 floats), the kernel picks by the previous key
 };

@@ -289,6 +289,9 @@ struct LatticeArgs {
     const float *scan_x, *scan_y;
     int nbeams;
     const int *nbeams_dev;    // not null: the scan's size as the device knows it (asynchronous scan loop; nbeams is an upper bound)
+    MatchHost *host_result;   // not null: the tail also writes the result block into mapped host memory, seq last
+    unsigned long long host_seq;
+    const int *mp_n_dev;      // the map points' size on the device (rides along in the host result block)
     int seeded;               // 3 x 3 x 3 lattice centred on the winner of the match in front (b200slam_fastmatch_pair_async):
                               // the parameter block holds ct[3][3] | st[3][3] | sxt[3][3] | syt[3][3], one row per possible seed
     float ipixel;
@@ -682,6 +685,17 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
         A.match->work_key = ~0ull;
         A.match->tickets = 0u;
         if (A.xchg.peers) A.match->epoch = epoch_s;
+        if (A.host_result) {
+            volatile MatchHost *h = A.host_result;
+            h->key = out_key;
+            h->seed_key = *reinterpret_cast<volatile unsigned long long *>(&A.match->seed_key);
+            h->best_hits = best_hits; h->last_hits = last_hits; h->written_hits = written;
+            h->scan_n = nbeams;
+            h->mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
+            h->error = *reinterpret_cast<volatile unsigned int *>(&A.match->error);
+            __threadfence_system();
+            h->seq = A.host_seq;
+        }
     }
 }
 
@@ -887,6 +901,9 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     A.scan_x = ctx->d_scan_x; A.scan_y = ctx->d_scan_y; A.nbeams = ctx->nbeams;
     A.nbeams_dev = ctx->scan_n_dev ? &ctx->d_front->scan_n : nullptr;
     A.seeded = L.seeded ? 1 : 0;
+    A.host_result = L.host_result ? ctx->h_result : nullptr;
+    A.host_seq = ctx->result_seq;
+    A.mp_n_dev = (ctx->mp_n_dev && ctx->d_front) ? &ctx->d_front->mp_n : nullptr;
     A.ipixel = 1 / m->pixel_size;                                        // main.c:383
     A.nth = L.nth; A.ntx = L.ntx; A.nty = L.nty;
     A.row_begin = L.row_begin; A.row_end = L.row_end;

@@ -143,9 +143,11 @@ int main(int argc, char **argv)
     for (int i = 0; i < 3; i++) { map_pose[i] = pose[i]; path[0][i] = pose[i]; }
 
     int miniUpdated = 1, path_iter = 1, rebuilds = 0;
+    double t_read = 0, t_rebuild = 0, t_queue = 0, t_fetch = 0, t_grow = 0;      /* where the host's time goes */
     const double t_loop = now_s();
     for (int scan_iter = 1; scan_iter < row; scan_iter++) {
         printf("scan %d\n", scan_iter + 1);
+        double t0 = now_s();
         if (host_parse) {
             const double tp = now_s();
             const int got = read_row(fp, ranges);
@@ -162,6 +164,7 @@ int main(int argc, char **argv)
             }
             must(b200slam_scan_read_resident_async(ctx, (int64_t)scan_iter * COLUMN, 24), "scan_read");
         }
+        t_read += now_s() - t0; t0 = now_s();
         int scan_transform_flag = 0;
         if (miniUpdated) {                                                /* main.c:865-872 */
             must(b200slam_scan_transform(ctx, pose), "scan_transform");
@@ -170,6 +173,7 @@ int main(int argc, char **argv)
             build_grids(coarse, fine, pixelSize, pixelSize2);
             rebuilds++;
         }
+        t_rebuild += now_s() - t0; t0 = now_s();
         /* constant-velocity motion model, main.c:875-898 */
         float pose_guess[3];
         if (scan_iter > 1) {
@@ -184,7 +188,9 @@ int main(int argc, char **argv)
          * result -- two kernels back to back, one synchronisation */
         must(b200slam_fastmatch_pair_async(ctx, miniUpdated ? coarse : fine, fine, pose_guess, fastResolution,
                                            fastResolution2), "fastmatch pair");
+        t_queue += now_s() - t0; t0 = now_s();
         must(b200slam_fastmatch_pair_fetch(ctx, NULL, pose, &size, NULL), "fastmatch pair fetch");
+        t_fetch += now_s() - t0; t0 = now_s();
         /* mini update, main.c:928-961 */
         float dp[3];
         for (int i = 0; i < 3; i++) dp[i] = fabsf(pose[i] - map_pose[i]);
@@ -196,6 +202,7 @@ int main(int argc, char **argv)
         } else {
             miniUpdated = 0;
         }
+        t_grow += now_s() - t0;
         printf("pose = %f  %f  %f\n", pose[0], pose[1], pose[2]);
         for (int i = 0; i < 3; i++) path[path_iter][i] = pose[i];
         path_iter++;
@@ -218,6 +225,9 @@ int main(int argc, char **argv)
                     "loop %.3f s wall -> %.1f us per scan on the device path\n", row, n, rebuilds,
             (unsigned long long)b200slam_launch_count(ctx), host_parse ? "parsed by fscanf" : "read + parsed on the GPU",
             t_parse, loop_s, row > 1 ? 1e6 * dev_s / (row - 1) : 0.0);
+    fprintf(stderr, "b200slam_replay: host time per scan: queue readAScan %.1f us, map rebuilds %.1f us (%d of them), queue the match pair "
+                    "%.1f us, wait for its result %.1f us, mini update / growth %.1f us\n", 1e6 * t_read / (row - 1),
+            1e6 * t_rebuild / (row - 1), rebuilds, 1e6 * t_queue / (row - 1), 1e6 * t_fetch / (row - 1), 1e6 * t_grow / (row - 1));
     free(mx); free(my); free(path);
     b200slam_map_destroy(ctx, coarse);
     b200slam_map_destroy(ctx, fine);

@@ -22,6 +22,6 @@ t0 = time.perf_counter()
 p = subprocess.run([exe, csv, os.path.join(d, "dev.map"), "3480"], capture_output=True, text=True)
 dt = time.perf_counter() - t0
 tt = [ln for ln in p.stdout.splitlines() if ln.startswith("time taken")]
-print(f"{'b200slam_replay (device resident)':28s} rc={p.returncode} wall={dt:7.3f} s  {tt[-1] if tt else ''}  last: {p.stdout.splitlines()[-2] if p.stdout else ''}  {p.stderr.strip()[-200:]}")
+print(f"{'b200slam_replay (device resident)':28s} rc={p.returncode} wall={dt:7.3f} s  {tt[-1] if tt else ''}  last: {p.stdout.splitlines()[-2] if p.stdout else ''}  {p.stderr.strip()[-700:]}")
 same = open(os.path.join(d, "dev.map"), "rb").read() == open(os.path.join(d, "ref_replay_accel.map"), "rb").read()
 print("device-resident map dump identical to the reference's:", same)
