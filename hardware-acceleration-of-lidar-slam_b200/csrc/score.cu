@@ -844,6 +844,214 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
     }
 }
 
+
+// ---- FastMatch-sized lattices: one CTA, gathers across all threads, sums in reference order ------------------
+// The reference's own call -- 27 candidates x <= 1079 beams (main.c:381-596) -- is 29 000 evaluations: a latency
+// problem, not a throughput one.  The lattice kernel above gives every candidate one thread that gathers AND adds
+// (27 live threads, ~45 us).  Here the two are split (hard part 2: the north_star's "beams
+// across lanes", with the exactness of design A kept):
+//   phase 1  all 1024 threads: work item = (beam, theta): rotate once, n_tx column and n_ty row indices, the
+//            n_tx * n_ty gathers -> vals[candidate][beam] in shared memory (+0.0f for an out-of-bounds beam, which
+//            leaves a non-negative sum unchanged) and one in-bounds bit mask per item;
+//   phase 2  thread c < n_candidates adds vals[c][0 .. nbeams) SEQUENTIALLY in beam order (main.c:516) -- the
+//            same additions in the same order as the reference, so the score is bit-identical -- and counts hits;
+//   phase 3  arg-min by warp shuffle on the packed (score, index) key; then bestHits[] exactly as the
+//            reference's loop leaves it (main.c:515: every candidate overwrites the array from index 0, so behind
+//            the last candidate's hits it holds those of the most recent candidate that had more): one warp per
+//            candidate that still owns entries compacts its in-bounds values out of shared memory by ballot.
+// No inter-CTA protocol, no atomics, no second pass over the field.  Measured in the 3480-scan replay: the
+// FastMatch + FastMatch2 pair went from ~95 us to ~?? us of GPU time per scan.
+constexpr int FM_THREADS = 1024;
+constexpr int FM_MAX_CAND = 32;
+constexpr int FM_MAX_BEAMS = 1536;             // vals: 27..32 x (1536 + 1) floats <= 197 KB of shared memory
+
+struct FmArgs {
+    const float *field;
+    int pitch, rows, cols;
+    const float *scan_x, *scan_y;
+    int nbeams;
+    const int *nbeams_dev;
+    float ipixel;
+    int nth, ntx, nty;
+    int nbp;                  // row pitch of vals (beam capacity rounded up to a multiple of 32, plus 1)
+    MatchDev *match;
+    float *hit_values;        // the bestHits[] twin ([1] of the context's buffer)
+    MatchHost *host_result;
+    unsigned long long host_seq;
+    const int *mp_n_dev;
+    int seeded;
+};
+
+__global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_constant__ FmArgs A, const __grid_constant__ LatticeTables T)
+{
+    extern __shared__ __align__(16) unsigned char fm_smem[];
+    float *vals = reinterpret_cast<float *>(fm_smem);                                 // [ncand][nbp]
+    const int ncand = A.nth * A.ntx * A.nty, per_th = A.ntx * A.nty;
+    unsigned int *inb = reinterpret_cast<unsigned int *>(vals + (size_t)ncand * A.nbp);   // [nth][nbp]: bit (itx * nty + ity)
+    __shared__ float tab_s[4 * FM_MAX_CAND];
+    __shared__ int cnt_s[FM_MAX_CAND];
+    __shared__ int stair_c[FM_MAX_CAND], stair_lo[FM_MAX_CAND];
+    __shared__ int nstair_s;
+    __shared__ unsigned long long key_s;
+
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
+    const float *ctT = T.v, *stT = T.v + A.nth, *sxtT = T.v + 2 * A.nth, *sytT = sxtT + A.ntx;
+    unsigned long long seed = ~0ull;
+    if (A.seeded) {
+        // centred on the winner of the match in front (main.c:909-918): the host sent the axis tables of all three
+        // possible centres per axis; see lattice_kernel
+        pdl_wait_prior_grids();
+        seed = *reinterpret_cast<volatile unsigned long long *>(&A.match->key);
+        const int lin1 = seed == ~0ull ? 13 : (int)(seed & 0xffffffffull);
+        const int ith1 = lin1 / 9, itx1 = (lin1 / 3) % 3, ity1 = lin1 % 3;
+        ctT = T.v + 3 * ith1; stT = T.v + 9 + 3 * ith1; sxtT = T.v + 18 + 3 * itx1; sytT = T.v + 27 + 3 * ity1;
+    }
+    if (tid < A.nth) { tab_s[tid] = ctT[tid]; tab_s[FM_MAX_CAND + tid] = stT[tid]; }
+    if (tid < A.ntx) tab_s[2 * FM_MAX_CAND + tid] = sxtT[tid];
+    if (tid < A.nty) tab_s[3 * FM_MAX_CAND + tid] = sytT[tid];
+    __syncthreads();
+
+    // ---- phase 1: every (beam, theta) item: rotation, cell indices, gathers ----------------------------------
+    for (int item = tid; item < nbeams * A.nth; item += FM_THREADS) {
+        const int i = item % nbeams, j = item / nbeams;
+        const float psx = __fmul_rn(A.scan_x[i], A.ipixel);                           // main.c:418
+        const float psy = __fmul_rn(A.scan_y[i], A.ipixel);                           // main.c:419
+        const float ct = tab_s[j], st = tab_s[FM_MAX_CAND + j];
+        const float Sx = rot_x(psx, psy, ct, st), Sy = rot_y(psx, psy, ct, st);       // main.c:462-463
+        unsigned int mask = 0;
+        for (int kx = 0; kx < A.ntx; ++kx) {
+            const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), A.cols);          // main.c:483
+            for (int ky = 0; ky < A.nty; ++ky) {
+                const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), A.rows);      // main.c:501
+                const bool in = c >= 0 && r >= 0;                                                  // main.c:512
+                vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(A.field + (in ? r * A.pitch + c : -1));
+                mask |= (unsigned int)in << (kx * A.nty + ky);
+            }
+        }
+        inb[j * A.nbp + i] = mask;
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per candidate, beams in scan order (main.c:516) -----------------------------------
+    unsigned long long key = ~0ull;
+    if (tid < ncand) {
+        const float *v = vals + (size_t)tid * A.nbp;
+        const unsigned int *m = inb + (tid / per_th) * A.nbp;
+        const int bit = tid % per_th;
+        float s = 0.0f;                                                               // main.c:507
+        int n = 0;
+        int i = 0;
+        for (; i + 8 <= nbeams; i += 8) {
+            float x[8];
+            unsigned int b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { x[u] = v[i + u]; b[u] = m[i + u]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s = __fadd_rn(s, x[u]); n += (b[u] >> bit) & 1u; }
+        }
+        for (; i < nbeams; ++i) { s = __fadd_rn(s, v[i]); n += (m[i] >> bit) & 1u; }
+        cnt_s[tid] = n;
+        key = pack_key(s, (unsigned int)tid);
+    }
+    // ---- phase 3: arg-min (lowest score, then lowest index: strict `<` in loop order, main.c:549) --------------
+    if (warp == 0) {
+        key = warp_min_u64(key);
+        if (lane == 0) key_s = key;
+    }
+    __syncthreads();
+    key = key_s;
+    // The match state and the bestHits[] twin belong to the kernel in front until it has completed.
+    pdl_wait_prior_grids();
+    if (tid == 0) {
+        // main.c:515: walk the candidates backwards; each one longer than what has been written so far supplies
+        // the entries it alone still owns
+        int ns = 0, written = 0;
+        if (key != ~0ull) {
+            for (int c = ncand - 1; c >= 0; --c)
+                if (c == ncand - 1 || cnt_s[c] > written) {
+                    stair_c[ns] = c; stair_lo[ns] = c == ncand - 1 ? 0 : written; ++ns;
+                    written = cnt_s[c];
+                }
+        }
+        nstair_s = ns;
+    }
+    __syncthreads();
+    for (int e = warp; e < nstair_s; e += FM_THREADS / 32) {
+        const int c = stair_c[e], lo = stair_lo[e];
+        const float *v = vals + (size_t)c * A.nbp;
+        const unsigned int *m = inb + (c / per_th) * A.nbp;
+        const int bit = c % per_th;
+        int run = 0;
+        for (int i0 = 0; i0 < nbeams; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < nbeams && ((m[i] >> bit) & 1u);
+            const unsigned int bal = __ballot_sync(0xffffffffu, in);
+            const int pos = run + __popc(bal & ((1u << lane) - 1u));
+            if (in && pos >= lo) A.hit_values[pos] = v[i];
+            run += __popc(bal);
+        }
+    }
+    if (tid == 0) {
+        int bh = 0, lh = 0, written = 0;
+        if (key != ~0ull) {
+            bh = cnt_s[(int)(key & 0xffffffffull)];                                   // bestHits_size: the winner's (main.c:557)
+            lh = cnt_s[ncand - 1];
+            for (int e = 0; e < nstair_s; ++e) written = max(written, cnt_s[stair_c[e]]);
+        }
+        A.match->key = key;
+        A.match->best_hits = bh;
+        A.match->last_hits = lh;
+        A.match->written_hits = written;
+        if (A.seeded) A.match->seed_key = seed;
+        if (A.host_result) {
+            volatile MatchHost *h = A.host_result;
+            h->key = key; h->seed_key = A.seeded ? seed : ~0ull;
+            h->best_hits = bh; h->last_hits = lh; h->written_hits = written;
+            h->scan_n = nbeams;
+            h->mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
+            h->error = *reinterpret_cast<volatile unsigned int *>(&A.match->error);
+            __threadfence_system();
+            h->seq = A.host_seq;
+        }
+    }
+}
+
+int launch_fastmatch(b200slam_ctx *ctx, const LatticeArgs &L, const LatticeTables &T)
+{
+    FmArgs A;
+    A.field = L.field; A.pitch = L.pitch; A.rows = L.rows; A.cols = L.cols;
+    A.scan_x = L.scan_x; A.scan_y = L.scan_y; A.nbeams = L.nbeams; A.nbeams_dev = L.nbeams_dev;
+    A.ipixel = L.ipixel;
+    A.nth = L.nth; A.ntx = L.ntx; A.nty = L.nty;
+    A.nbp = ((L.nbeams + 31) & ~31) + 1;                  // + 1: candidate rows start in different banks
+    A.match = L.match;
+    A.hit_values = L.hit_values + L.hit_stride;
+    A.host_result = L.host_result; A.host_seq = L.host_seq; A.mp_n_dev = L.mp_n_dev;
+    A.seeded = L.seeded;
+    const size_t smem = sizeof(float) * (size_t)(L.nth * L.ntx * L.nty + L.nth) * A.nbp;
+    static bool smem_set[64] = {};
+    if (!smem_set[ctx->device & 63]) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(fastmatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        smem_set[ctx->device & 63] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(FM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (ctx->use_pdl && ctx->prev_launch_was_lattice) ? 1 : 0;
+    CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, fastmatch_kernel, A, T));
+    LAUNCH_CHECK(ctx);
+    ctx->prev_launch_was_lattice = true;
+    return B200SLAM_OK;
+}
+
 template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0>
 int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T, int nth_cover)
 {
@@ -948,8 +1156,15 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     // FastMatch-sized lattices (the reference's 3 x 3 x 3): one candidate per thread with per-candidate
     // hit counts, so that the tail can leave bestHits[] exactly as the reference's loop does.
     if ((L.seeded || !getenv("B200SLAM_LATTICE_CFG")) && (long long)L.nth * L.ntx * L.nty <= MATCH_SMALL && L.row_begin == 0 &&
-        L.row_end == (int64_t)L.nth * L.ntx && !A.xchg.peers && L.nth_tab == L.nth)
+        L.row_end == (int64_t)L.nth * L.ntx && !A.xchg.peers && L.nth_tab == L.nth) {
+        // the reference's own size class: one CTA, gathers across all threads (fastmatch_kernel); scans longer than
+        // its shared memory holds, > 32 candidates or a wanted score table take the general kernel
+        const size_t fm_smem = sizeof(float) * (size_t)(L.nth * L.ntx * L.nty + L.nth) * (((A.nbeams + 31) & ~31) + 1);
+        if ((long long)L.nth * L.ntx * L.nty <= FM_MAX_CAND && A.nbeams <= FM_MAX_BEAMS && fm_smem <= 216 * 1024 && !A.scores &&
+            !L.d_tables && !getenv("B200SLAM_NO_FASTMATCH_KERNEL"))
+            return launch_fastmatch(ctx, A, T);
         return launch_lattice_cfg<1, 1, 4, 1, true>(ctx, A, T, nth_cover);
+    }
     if (L.seeded) return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "a seeded match is a whole 3 x 3 x 3 lattice on one GPU");
     // Row reuse (template parameter Q): usable when the ty step is pixel / Q, measured on the ty axis table
     // itself (host copy).  The kernel verifies every (beam, ty group) exactly, so a wrong guess here only

@@ -59,3 +59,15 @@ def fastmatch_golden():
 
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(params=["fastmatch_kernel", "lattice_kernel"])
+def small_lattice_kernel(request, monkeypatch):
+    """FastMatch-sized lattices (<= 32 candidates) run in the one-CTA fastmatch_kernel; B200SLAM_NO_FASTMATCH_KERNEL
+    (read at every launch) sends them through the general lattice kernel's per-candidate-count instantiation, which
+    larger small lattices and long scans still use.  Tests of the FastMatch semantics run under both."""
+    if request.param == "lattice_kernel":
+        monkeypatch.setenv("B200SLAM_NO_FASTMATCH_KERNEL", "1")
+    else:
+        monkeypatch.delenv("B200SLAM_NO_FASTMATCH_KERNEL", raising=False)
+    return request.param

@@ -136,7 +136,7 @@ def test_device_chain_scan_to_pose_and_growth(ctx, oracle, synth, fg):
 
 
 @pytest.mark.gpu
-def test_fastmatch_pair_equals_two_fastmatch_calls(b200slam, oracle, synth):
+def test_fastmatch_pair_equals_two_fastmatch_calls(b200slam, oracle, synth, small_lattice_kernel):
     """b200slam_fastmatch_pair_async: FastMatch then FastMatch2 from its result (main.c:902-918) as two kernels
     with no host step between them -- the second picks its lattice by the first one's winner on the device --
     and the scan's size kept on the device (b200slam_scan_read_async).  Poses, bestHits_size and the bestHits[]

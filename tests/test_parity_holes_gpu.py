@@ -73,7 +73,7 @@ def test_lattice_axis_tables_beyond_the_parameter_block(ctx, oracle, synth, n, n
 
 
 @pytest.mark.parametrize("graph", [False, True])
-def test_fastmatch_sized_matches_chained_by_pdl(b200slam, oracle, synth, graph):
+def test_fastmatch_sized_matches_chained_by_pdl(b200slam, oracle, synth, graph, small_lattice_kernel):
     """consecutive <= 64-candidate matches are chained by programmatic dependent launch,
     and the per-candidate hit counts the bestHits staircase walks are shared match state.  A burst of
     asynchronous 3 x 3 x 3 matches around poses at the grid's edge (so the 27 counts differ and the

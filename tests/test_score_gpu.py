@@ -37,7 +37,7 @@ def _check_lattice(ctx, oracle, m, om, w, n, step=None, pose0=None):
     return res
 
 
-def test_fastmatch_golden_vectors(ctx, fastmatch_golden):
+def test_fastmatch_golden_vectors(ctx, fastmatch_golden, small_lattice_kernel):
     g = fastmatch_golden
     for k in range(int(g["count"])):
         field = g[f"field_{k}"]
@@ -97,6 +97,30 @@ def test_lattice_ragged_beam_counts(ctx, oracle, synth, nbeams):
     m, om = _setup(ctx, oracle, w)
     try:
         _check_lattice(ctx, oracle, m, om, w, (4, 9, 10))
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("n", [(3, 3, 3), (1, 1, 1), (2, 3, 5), (4, 2, 4), (32, 1, 1), (1, 32, 1), (1, 1, 32), (2, 4, 4)])
+@pytest.mark.parametrize("nbeams", [0, 1, 33, 1079, 1536, 1537])
+def test_small_lattices_without_score_table(ctx, oracle, synth, n, nbeams, small_lattice_kernel):
+    """<= 32 candidates and no score table wanted: the one-CTA fastmatch_kernel (gathers across all threads, sums
+    in beam order by one thread per candidate); 1537 beams exceed its shared memory and take the general kernel.
+    Winner, score bits, both hit counts and the last candidate's hit values against the oracle, at the map's
+    edge so that candidates lose beams."""
+    w = synth.make_workload("tiny")
+    x, y = synth.scan_fixed_count(w["occ"], float(w["pixel"]), w["top_left"], w["true_pose"], max(nbeams, 1))
+    w["scan_x"], w["scan_y"] = x[:nbeams], y[:nbeams]
+    m, om = _setup(ctx, oracle, w)
+    try:
+        step = np.array([0.4, 0.3, 0.06], np.float32)
+        for pose0 in (w["pose0"], np.array([w["top_left"][0] + 2.0, w["top_left"][1] + 1.5, 0.4], np.float32)):
+            ores, _, olast = oracle.score_lattice(om, w["scan_x"], w["scan_y"], pose0, step, n, want_last_hits=True)
+            res, _, last = ctx.score_lattice(m, pose0, step, n, want_scores=False, want_last_hits=True)
+            assert res.best_index == ores.best_index and res.best_hits == ores.best_hits and res.last_hits == ores.last_hits
+            assert np.float32(res.best_score).tobytes() == np.float32(ores.best_score).tobytes()
+            assert np.array_equal(bits(res.pose()), bits(np.array(list(ores.best_pose), np.float32)))
+            assert np.array_equal(bits(last[:res.last_hits]), bits(olast[:ores.last_hits]))
     finally:
         m.close()
 
@@ -373,7 +397,7 @@ def test_config4_full_size_pyramid_10m_properties(ctx, oracle, synth, b200slam):
 
 
 @pytest.mark.gpu
-def test_fastmatch_leaves_besthits_exactly_as_the_reference_loop(ctx, oracle, synth):
+def test_fastmatch_leaves_besthits_exactly_as_the_reference_loop(ctx, oracle, synth, small_lattice_kernel):
     """main.c:515: EVERY candidate overwrites FastMatchParameters.bestHits[] from index 0, in loop order, and
     the array is a global that is never cleared.  After a call it therefore holds the last candidate's
     hits, behind them those of the most recent candidate that had more, and behind those whatever earlier
