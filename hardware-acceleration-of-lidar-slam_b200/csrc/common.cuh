@@ -317,7 +317,7 @@ int particles_share_blocks(b200slam_ctx *ctx);
 void particles_unshare_blocks(b200slam_ctx *ctx);
 // d_wsum layout
 enum PfScalar { PF_WLOCAL = 0, PF_WGLOBAL = 1, PF_RANK_OFFSET = 2, PF_KBEGIN = 3, PF_KCOUNT = 4, PF_NGLOBAL = 5,
-                PF_SLOT_BASE = 8 /* [nranks + 1]: first resampling slot held by each rank */, PF_SCALARS = 8 + XCHG_MAX_RANKS + 1 };
+                PF_TICKET = 6 /* finished CTAs of the push kernel (reset by its last CTA) */, PF_SLOT_BASE = 8 /* [nranks + 1]: first resampling slot held by each rank */, PF_SCALARS = 8 + XCHG_MAX_RANKS + 1 };
 int particles_weights_resample(b200slam_ctx *ctx, int64_t N, float beta, uint32_t u0_q32,
                                float *weights, uint64_t *wsum, int32_t *ancestors,
                                int64_t *k_begin, int64_t *k_count);

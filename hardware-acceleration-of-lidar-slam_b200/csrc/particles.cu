@@ -291,18 +291,21 @@ resample_gather_kernel(const unsigned long long *__restrict__ C, long long N,
 // are stored straight into rank d's other pose buffer / ancestor array over NVLink (every rank's pose block
 // is mapped through CUDA IPC).  Consecutive slots have consecutive destinations and (mostly) equal or
 // adjacent ancestors, so both sides coalesce.  A peer barrier behind this kernel completes the step.
+// The step's closing barrier is this kernel's tail: every CTA fences its peer stores (system scope) and takes a
+// ticket; the last one posts this rank's barrier flag to every peer and waits for theirs (bounded), so when the
+// kernel completes every rank's offspring has landed everywhere -- no separate barrier launch.
 __global__ void __launch_bounds__(256)
-resample_push_kernel(const unsigned long long *__restrict__ C, long long N_local, const unsigned long long *__restrict__ S,
+resample_push_kernel(const unsigned long long *__restrict__ C, long long N_local, unsigned long long *__restrict__ S,
                      unsigned int u0_q32, long long index_base, const float *__restrict__ src, size_t cap,
-                     float *const *__restrict__ peer_blocks, int dst_parity, int nranks)
+                     float *const *__restrict__ peer_blocks, int dst_parity, int nranks, const XchgArgs X, MatchDev *match)
 {
     __shared__ unsigned long long sbase[XCHG_MAX_RANKS + 1];
+    __shared__ int last_s;
     for (int r = threadIdx.x; r <= nranks; r += blockDim.x) sbase[r] = S[PF_SLOT_BASE + r];
     __syncthreads();
     const unsigned long long Wg = S[PF_WGLOBAL], Ng = S[PF_NGLOBAL], roff = S[PF_RANK_OFFSET];
-    const long long kb = (long long)S[PF_KBEGIN], kc = (long long)S[PF_KCOUNT];
-    if (Ng == 0) return;
-    const unsigned long long Wd = Wg / Ng, Wm = Wg % Ng, U = u_offset(Wd, u0_q32);
+    const long long kb = (long long)S[PF_KBEGIN], kc = Ng ? (long long)S[PF_KCOUNT] : 0;
+    const unsigned long long Wd = Ng ? Wg / Ng : 0, Wm = Ng ? Wg % Ng : 0, U = u_offset(Wd, u0_q32);
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < kc; s += (long long)gridDim.x * blockDim.x) {
         const unsigned long long k = (unsigned long long)(kb + s);
         const unsigned long long t = U + k * Wd + (k * Wm) / Ng - roff;     // T_k >= rank offset for owned slots
@@ -319,6 +322,38 @@ resample_push_kernel(const unsigned long long *__restrict__ C, long long N_local
 #pragma unroll
         for (int f = 0; f < 5; ++f) dst[f * cap + j] = src[f * cap + lo];
         reinterpret_cast<int *>(blk + 10 * cap)[j] = (int)(lo + index_base);
+    }
+    // ---- closing barrier ----------------------------------------------------------------------------------
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(&S[PF_TICKET], 1ull);
+        last_s = t == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence_system();
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(&match->bar_epoch) + 1;
+    if ((int)threadIdx.x < X.nranks) {
+        const int r = threadIdx.x;
+        *reinterpret_cast<volatile unsigned long long *>(&X.peers[r]->bar[X.rank]) = epoch;
+        const volatile unsigned long long *mine = &X.peers[X.rank]->bar[r];
+        const unsigned long long budget = *reinterpret_cast<volatile unsigned int *>(&match->error) ? 0ull : X.timeout_ns;
+        if (*mine < epoch) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
+            while (*mine < epoch)
+                if ((++spins & 255u) == 0 && global_timer_ns() - t0 > budget) {
+                    atomicOr(&match->error, DEV_ERR_BARRIER);
+                    break;
+                }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        match->bar_epoch = epoch;
+        S[PF_TICKET] = 0;
     }
 }
 
@@ -340,11 +375,8 @@ int particles_resample_resident(b200slam_ctx *ctx, int64_t N, float beta, uint32
     if (ctx->pf_sharded) {
         resample_push_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
             ctx->d_q, N, ctx->d_wsum, u0_q32, ctx->last_index_base, ctx->d_pose_soa, ctx->pose_cap, ctx->d_pf_peers,
-            ctx->pose_parity ^ 1, ctx->nranks);
+            ctx->pose_parity ^ 1, ctx->nranks, X, ctx->d_match);       // its tail is the step's closing barrier
         LAUNCH_CHECK(ctx);
-        // every rank's offspring has landed everywhere before anybody scores the new set
-        int rc = comm_peer_barrier(ctx);
-        if (rc) return rc;
     } else {
         resample_gather_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(
             ctx->d_q, N, ctx->d_wsum, u0_q32, ctx->d_anc_resident, ctx->d_pose_soa, ctx->d_pose_alt, ctx->pose_cap);
