@@ -125,6 +125,7 @@ struct b200slam_ctx {
     bool use_pdl = true;         // programmatic dependent launch between consecutive scan-matching kernels
     bool prev_launch_was_lattice = false;   // the last kernel queued on the stream was a scan-matching kernel
     bool prev_launch_was_edt = false;       // ... was a distance transform (the next transform may start under its tail)
+    const float *prev_lattice_field = nullptr;   // field the last scan-matching kernel reads (valid while prev_launch_was_lattice)
     int match_mode = B200SLAM_MATCH_LATENCY; // tile-shape policy of the lattice kernel (b200slam_set_match_mode)
 
     // scan (sensor frame), device resident

@@ -452,9 +452,13 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    // only directly behind another transform, and never for the multi-GPU variant (its peer stores are bracketed
-    // by barrier kernels)
-    cfg.numAttrs = (ctx->use_pdl && ctx->prev_launch_was_edt && !MULTI) ? 1 : 0;
+    // Only directly behind another transform, or behind a scan-matching kernel that reads a DIFFERENT field (the
+    // serial step EDT(i) -> match(i) -> EDT(i+1): the transform of the next map starts under the match's
+    // reduction tail; both kinds of kernel release their dependents at their first instruction and this one
+    // waits for the grid in front before it exits).  Never for the multi-GPU variant (its peer stores are
+    // bracketed by barrier kernels).
+    const bool behind_other_match = ctx->prev_launch_was_lattice && ctx->prev_lattice_field != d_field;
+    cfg.numAttrs = (ctx->use_pdl && (ctx->prev_launch_was_edt || behind_other_match) && !MULTI) ? 1 : 0;
     CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, tmap, d_field, (uint32_t)field_pitch * 4u, row_begin, row_end, cols, best_cb, t2,
                                      max_dist, peers, &ctx->d_match->error));
     LAUNCH_CHECK(ctx);

@@ -322,7 +322,10 @@ struct LatticeArgs {
 // inside a warp-uniform switch on p.  Everything is decided from the exact per-candidate row indices: a
 // (beam, ty group) whose rows do not follow the pattern (float fuzz at a rounding boundary, rows at the edge
 // of the grid) is flagged and takes the per-candidate path for that beam, so results stay bit-identical.
-template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0>
+// PITCH (row reuse only): the field's row pitch in floats when it is known at compile time (the power-of-two map
+// sizes of the BASELINE configurations), 0 = read it from the arguments.  The K row reads of a beam are then ONE
+// address computation and K loads at immediate offsets k * PITCH * 4 instead of a chain of K IMAD.WIDEs.
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0, int PITCH = 0>
 __global__ void __launch_bounds__(32 * WX * WY, TYPT >= 16 ? (Q > 0 ? 4 : 3) : 1)
 lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ LatticeTables T)
 {
@@ -480,7 +483,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
                     ph[u] = rv & 7;
                     const float *p0 = A.field + idx;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) dst[u][k] = ldg_ordered(p0 + (long)k * A.pitch);
+                    for (int k = 0; k < K; ++k) dst[u][k] = ldg_ordered(PITCH > 0 ? p0 + k * PITCH : p0 + (long)k * A.pitch);
                 }
 #pragma unroll
                 for (int j = 0; j < TYPT; ++j) asm volatile("" : "+f"(acc[j]));
@@ -873,7 +876,7 @@ struct FmArgs {
     const int *nbeams_dev;
     float ipixel;
     int nth, ntx, nty;
-    int nbp;                  // row pitch of vals (beam capacity rounded up to a multiple of 32, plus 1)
+    int nbp;                  // row pitch of vals (beam capacity rounded up to a multiple of 32, plus 4)
     MatchDev *match;
     float *hit_values;        // the bestHits[] twin ([1] of the context's buffer)
     MatchHost *host_result;
@@ -914,46 +917,53 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
     __syncthreads();
 
     // ---- phase 1: every (beam, theta) item: rotation, cell indices, gathers ----------------------------------
-    for (int item = tid; item < nbeams * A.nth; item += FM_THREADS) {
-        const int i = item % nbeams, j = item / nbeams;
-        const float psx = __fmul_rn(A.scan_x[i], A.ipixel);                           // main.c:418
-        const float psy = __fmul_rn(A.scan_y[i], A.ipixel);                           // main.c:419
+    for (int j = 0; j < A.nth; ++j) {
         const float ct = tab_s[j], st = tab_s[FM_MAX_CAND + j];
-        const float Sx = rot_x(psx, psy, ct, st), Sy = rot_y(psx, psy, ct, st);       // main.c:462-463
-        unsigned int mask = 0;
-        for (int kx = 0; kx < A.ntx; ++kx) {
-            const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), A.cols);          // main.c:483
-            for (int ky = 0; ky < A.nty; ++ky) {
-                const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), A.rows);      // main.c:501
-                const bool in = c >= 0 && r >= 0;                                                  // main.c:512
-                vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(A.field + (in ? r * A.pitch + c : -1));
-                mask |= (unsigned int)in << (kx * A.nty + ky);
+        for (int i = tid; i < nbeams; i += FM_THREADS) {
+            const float psx = __fmul_rn(A.scan_x[i], A.ipixel);                       // main.c:418
+            const float psy = __fmul_rn(A.scan_y[i], A.ipixel);                       // main.c:419
+            const float Sx = rot_x(psx, psy, ct, st), Sy = rot_y(psx, psy, ct, st);   // main.c:462-463
+            unsigned int mask = 0;
+            for (int kx = 0; kx < A.ntx; ++kx) {
+                const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), A.cols);          // main.c:483
+                for (int ky = 0; ky < A.nty; ++ky) {
+                    const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), A.rows);      // main.c:501
+                    const bool in = c >= 0 && r >= 0;                                                  // main.c:512
+                    vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(A.field + (in ? r * A.pitch + c : -1));
+                    mask |= (unsigned int)in << (kx * A.nty + ky);
+                }
             }
+            inb[j * A.nbp + i] = mask;
         }
-        inb[j * A.nbp + i] = mask;
     }
     __syncthreads();
 
-    // ---- phase 2: one thread per candidate, beams in scan order (main.c:516) -----------------------------------
+    // ---- phase 2: warp 0 -- one thread per candidate, beams in scan order (main.c:516), 4 per LDS.128; meanwhile
+    // warp c + 1 counts candidate c's in-bounds beams (bestHits_size, main.c:515-516) ----------------------------
     unsigned long long key = ~0ull;
-    if (tid < ncand) {
-        const float *v = vals + (size_t)tid * A.nbp;
-        const unsigned int *m = inb + (tid / per_th) * A.nbp;
-        const int bit = tid % per_th;
-        float s = 0.0f;                                                               // main.c:507
-        int n = 0;
-        int i = 0;
-        for (; i + 8 <= nbeams; i += 8) {
-            float x[8];
-            unsigned int b[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { x[u] = v[i + u]; b[u] = m[i + u]; }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { s = __fadd_rn(s, x[u]); n += (b[u] >> bit) & 1u; }
+    if (warp == 0) {
+        if (tid < ncand) {
+            const float *v = vals + (size_t)tid * A.nbp;                                  // 16-byte aligned: nbp % 4 == 0
+            float s = 0.0f;                                                               // main.c:507
+            int i = 0;
+            for (; i + 8 <= nbeams; i += 8) {
+                const float4 a = *reinterpret_cast<const float4 *>(v + i), b = *reinterpret_cast<const float4 *>(v + i + 4);
+                s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
+                s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
+            }
+            for (; i < nbeams; ++i) s = __fadd_rn(s, v[i]);
+            key = pack_key(s, (unsigned int)tid);
         }
-        for (; i < nbeams; ++i) { s = __fadd_rn(s, v[i]); n += (m[i] >> bit) & 1u; }
-        cnt_s[tid] = n;
-        key = pack_key(s, (unsigned int)tid);
+    } else {
+        for (int c = warp - 1; c < ncand; c += FM_THREADS / 32 - 1) {
+            const unsigned int *m = inb + (c / per_th) * A.nbp;
+            const int bit = c % per_th;
+            int n = 0;
+            for (int i = lane; i < nbeams; i += 32) n += (m[i] >> bit) & 1u;
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) n += __shfl_xor_sync(0xffffffffu, n, sft);
+            if (lane == 0) cnt_s[c] = n;
+        }
     }
     // ---- phase 3: arg-min (lowest score, then lowest index: strict `<` in loop order, main.c:549) --------------
     if (warp == 0) {
@@ -1025,7 +1035,7 @@ int launch_fastmatch(b200slam_ctx *ctx, const LatticeArgs &L, const LatticeTable
     A.scan_x = L.scan_x; A.scan_y = L.scan_y; A.nbeams = L.nbeams; A.nbeams_dev = L.nbeams_dev;
     A.ipixel = L.ipixel;
     A.nth = L.nth; A.ntx = L.ntx; A.nty = L.nty;
-    A.nbp = ((L.nbeams + 31) & ~31) + 1;                  // + 1: candidate rows start in different banks
+    A.nbp = ((L.nbeams + 31) & ~31) + 4;                  // + 4: rows stay 16-byte aligned and start 4 banks apart
     A.match = L.match;
     A.hit_values = L.hit_values + L.hit_stride;
     A.host_result = L.host_result; A.host_seq = L.host_seq; A.mp_n_dev = L.mp_n_dev;
@@ -1049,14 +1059,15 @@ int launch_fastmatch(b200slam_ctx *ctx, const LatticeArgs &L, const LatticeTable
     CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, fastmatch_kernel, A, T));
     LAUNCH_CHECK(ctx);
     ctx->prev_launch_was_lattice = true;
+    ctx->prev_lattice_field = A.field;
     return B200SLAM_OK;
 }
 
-template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0>
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0, int PITCH = 0>
 int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T, int nth_cover)
 {
     constexpr int TXT = 32 * WX, TYT = TYPT * WY;
-    auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT, Q>;
+    auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT, Q, PITCH>;
     // Beams per chunk: the whole scan when its tables fit the budget, else even chunks.
     constexpr int GUARD = LatticePipe<TYPT, UM, Q>::GUARD;
     const int per_beam = (TXT + (Q > 0 ? WY : TYT) + 2) * 4;
@@ -1095,6 +1106,7 @@ int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T
     CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, A, T));
     LAUNCH_CHECK(ctx);
     ctx->prev_launch_was_lattice = true;
+    ctx->prev_lattice_field = A.field;
     return B200SLAM_OK;
 }
 
@@ -1159,7 +1171,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
         L.row_end == (int64_t)L.nth * L.ntx && !A.xchg.peers && L.nth_tab == L.nth) {
         // the reference's own size class: one CTA, gathers across all threads (fastmatch_kernel); scans longer than
         // its shared memory holds, > 32 candidates or a wanted score table take the general kernel
-        const size_t fm_smem = sizeof(float) * (size_t)(L.nth * L.ntx * L.nty + L.nth) * (((A.nbeams + 31) & ~31) + 1);
+        const size_t fm_smem = sizeof(float) * (size_t)(L.nth * L.ntx * L.nty + L.nth) * (((A.nbeams + 31) & ~31) + 4);
         if ((long long)L.nth * L.ntx * L.nty <= FM_MAX_CAND && A.nbeams <= FM_MAX_BEAMS && fm_smem <= 216 * 1024 && !A.scores &&
             !L.d_tables && !getenv("B200SLAM_NO_FASTMATCH_KERNEL"))
             return launch_fastmatch(ctx, A, T);
@@ -1210,6 +1222,12 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
 #define B200SLAM_CFG(T_, X_, Y_, M_, Q_) \
     if (pick_t == T_ && pick_x == X_ && pick_y == Y_ && pick_m == M_ && pick_q == Q_) \
         return launch_lattice_cfg<T_, X_, Y_, M_, false, Q_>(ctx, A, T, nth_cover);
+    if (pick_t == 16 && pick_x == 2 && pick_y == 4 && pick_m == 1 && pick_q == 2 && !getenv("B200SLAM_LATTICE_NO_PITCH")) {
+        // row reuse on a map whose pitch is a compile-time constant of the kernel (see PITCH)
+        if (A.pitch == 8192) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 8192>(ctx, A, T, nth_cover);
+        if (A.pitch == 4096) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 4096>(ctx, A, T, nth_cover);
+        if (A.pitch == 2048) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 2048>(ctx, A, T, nth_cover);
+    }
     B200SLAM_CFG(16, 2, 4, 1, 0)        // 64 x 64 tile, 256 threads
     B200SLAM_CFG(8, 1, 8, 1, 0)         // 32 x 64
     B200SLAM_CFG(4, 1, 8, 1, 0)         // 32 x 32
