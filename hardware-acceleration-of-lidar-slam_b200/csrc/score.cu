@@ -270,14 +270,14 @@ struct LatticeTables {
 // Gather pipeline shape: U beams per group, NBUF register buffers (NBUF - 1 groups in flight);
 // GUARD = table rows appended for padding (a multiple of NBUF*U) and for the prefetches that
 // run past the end.
-template <int TYPT, int UM = 1, int Q = 0>
+template <int TYPT, int UM = 1, int Q = 0, int NB = 0>
 struct LatticePipe {
     static constexpr int U = UM * (TYPT >= 16 ? 1 : 16 / TYPT);      // UM: deeper groups for low-occupancy shapes
     // 16 candidates per thread: two buffers.  With row reuse that is 16 sums + 2 x 9 gathered values in 64
     // registers = 4 CTAs (32 warps) per SM; the kernel is latency bound, and measured on config 3 occupancy beats
     // a third buffer: 648 us against 684 us with three buffers at 3 CTAs per SM (80 registers), 1386 us with three
     // buffers squeezed into 64 registers (spills), 1011 us at 2 CTAs per SM.
-    static constexpr int NBUF = TYPT >= 16 ? 2 : 3;
+    static constexpr int NBUF = NB > 0 ? NB : (TYPT >= 16 ? 2 : 3);
     static constexpr int PAD = NBUF * U;
     static constexpr int GUARD = PAD - 1 + (NBUF - 1) * U;
 };
@@ -325,7 +325,7 @@ struct LatticeArgs {
 // PITCH (row reuse only): the field's row pitch in floats when it is known at compile time (the power-of-two map
 // sizes of the BASELINE configurations), 0 = read it from the arguments.  The K row reads of a beam are then ONE
 // address computation and K loads at immediate offsets k * PITCH * 4 instead of a chain of K IMAD.WIDEs.
-template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0, int PITCH = 0>
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0, int PITCH = 0, int NB = 0>
 __global__ void __launch_bounds__(32 * WX * WY, TYPT >= 16 ? (Q > 0 ? 4 : 3) : 1)
 lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ LatticeTables T)
 {
@@ -336,7 +336,7 @@ lattice_kernel(const __grid_constant__ LatticeArgs A, const __grid_constant__ La
     constexpr int TXT = 32 * WX;
     constexpr int TYT = TYPT * WY;
     constexpr int NT = 32 * WX * WY;
-    using P = LatticePipe<TYPT, UM, Q>;
+    using P = LatticePipe<TYPT, UM, Q, NB>;
     constexpr int U = P::U, NBUF = P::NBUF, GUARD = P::GUARD;
     static_assert(NT % TXT == 0 && NT % TYT == 0, "tile shape");
     extern __shared__ __align__(16) int lat_smem[];
@@ -1063,13 +1063,13 @@ int launch_fastmatch(b200slam_ctx *ctx, const LatticeArgs &L, const LatticeTable
     return B200SLAM_OK;
 }
 
-template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0, int PITCH = 0>
+template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0, int PITCH = 0, int NB = 0>
 int launch_lattice_cfg(b200slam_ctx *ctx, LatticeArgs &A, const LatticeTables &T, int nth_cover)
 {
     constexpr int TXT = 32 * WX, TYT = TYPT * WY;
-    auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT, Q, PITCH>;
+    auto kern = lattice_kernel<TYPT, WX, WY, UM, COUNT, Q, PITCH, NB>;
     // Beams per chunk: the whole scan when its tables fit the budget, else even chunks.
-    constexpr int GUARD = LatticePipe<TYPT, UM, Q>::GUARD;
+    constexpr int GUARD = LatticePipe<TYPT, UM, Q, NB>::GUARD;
     const int per_beam = (TXT + (Q > 0 ? WY : TYT) + 2) * 4;
     // 16 candidates per thread: chunks that leave room for 4 (row reuse) / 3 resident CTAs per SM
     const int budget = (TYPT >= 16 ? (Q > 0 ? 50 : 56) * 1024 : 100 * 1024) - (Q > 0 ? TYT * 4 : 0);
@@ -1196,7 +1196,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
         // step = pixel / 2): 64 x 64 tiles 648 us against 1059 us without reuse, 32 x 64 tiles 1033 us; with 4
         // candidates per thread the per-beam bookkeeping outweighs the saved gathers (1503 us), so those
         // shapes are compiled (and tested) but never chosen.  The Q = 4 factors are estimates.
-        {16, 2, 4, 1, 2, 0.61}, {8, 1, 8, 1, 2, 0.98},
+        {16, 2, 4, 1, 2, 0.50}, {8, 1, 8, 1, 2, 0.98},
         {16, 2, 4, 1, 4, 0.55}, {8, 1, 8, 1, 4, 0.85},
     };
     int pick_t = 0, pick_x = 0, pick_y = 0, pick_m = 1, pick_q = 0;
@@ -1224,9 +1224,12 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
         return launch_lattice_cfg<T_, X_, Y_, M_, false, Q_>(ctx, A, T, nth_cover);
     if (pick_t == 16 && pick_x == 2 && pick_y == 4 && pick_m == 1 && pick_q == 2 && !getenv("B200SLAM_LATTICE_NO_PITCH")) {
         // row reuse on a map whose pitch is a compile-time constant of the kernel (see PITCH)
+        // (a third buffer spills at 64 registers: 232 bytes in the loop)
+        if (A.pitch == 16384) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 16384>(ctx, A, T, nth_cover);
         if (A.pitch == 8192) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 8192>(ctx, A, T, nth_cover);
         if (A.pitch == 4096) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 4096>(ctx, A, T, nth_cover);
         if (A.pitch == 2048) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 2048>(ctx, A, T, nth_cover);
+        if (A.pitch == 1024) return launch_lattice_cfg<16, 2, 4, 1, false, 2, 1024>(ctx, A, T, nth_cover);
     }
     B200SLAM_CFG(16, 2, 4, 1, 0)        // 64 x 64 tile, 256 threads
     B200SLAM_CFG(8, 1, 8, 1, 0)         // 32 x 64

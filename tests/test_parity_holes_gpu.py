@@ -184,3 +184,37 @@ def test_generic_edt_more_rows_than_a_grid_dimension(ctx, oracle, synth):
     occ = synth.grid_bernoulli(70001, 40, 0.01, seed=5)
     for md in (1.0, 17.0):
         assert np.array_equal(bits(ctx.edt(occ, md)), bits(oracle.edt(occ, md)))
+
+
+@pytest.mark.parametrize("cols", [1024, 2048, 4096, 8192, 16384, 1000])
+def test_row_reuse_kernel_specialised_on_the_pitch(ctx, oracle, synth, monkeypatch, cols):
+    """The row-reuse matcher has one instantiation per power-of-two map pitch (the K row reads of a beam become one
+    address computation and K loads at immediate offsets) and a generic one (cols = 1000 -> pitch 1024 is still a
+    specialised pitch; B200SLAM_LATTICE_NO_PITCH forces the generic kernel on the same map).  Every score against
+    the oracle, on lattices with partial tiles, at the map's edge."""
+    rows = 300
+    occ = synth.grid_rooms(rows, cols, synth.SEED_GRID + cols)
+    pixel, tl = synth.centred_geometry(rows, cols, 0.1)
+    true_pose = (0.37, -0.21, 0.1)
+    x, y = synth.scan_fixed_count(occ, float(pixel), tl, true_pose, 200)
+    field = oracle.edt(occ)
+    m = ctx.new_map(rows, cols)
+    try:
+        m.set_geometry(pixel, tl).upload_field(field)
+        ctx.scan_upload(x, y)
+        om = oracle.make_map(field, pixel, tl)
+        step = np.array([0.05, 0.05, 0.008727], np.float32)
+        monkeypatch.setenv("B200SLAM_LATTICE_CFG", "16,2,4,1,2")
+        for generic in (False, True):
+            if generic:
+                monkeypatch.setenv("B200SLAM_LATTICE_NO_PITCH", "1")
+            for pose0, n in ((np.array([0.4, -0.2, 0.11], np.float32), (2, 70, 67)),
+                             (np.array([tl[0] + 1.0, tl[1] + 14.0, 0.3], np.float32), (1, 64, 130))):
+                ores, oscores, _ = oracle.score_lattice(om, x, y, pose0, step, n)
+                res, scores, _ = ctx.score_lattice(m, pose0, step, n, want_scores=True)
+                assert np.array_equal(bits(scores), bits(oscores)), (cols, generic, n)
+                assert res.best_index == ores.best_index and res.best_hits == ores.best_hits
+    finally:
+        monkeypatch.delenv("B200SLAM_LATTICE_CFG", raising=False)
+        monkeypatch.delenv("B200SLAM_LATTICE_NO_PITCH", raising=False)
+        m.close()
