@@ -112,6 +112,8 @@ def load_library() -> C.CDLL:
         "b200slam_fastmatch_pair_async": (i, [vp, vp, vp, c_float_p, c_float_p, c_float_p]),
         "b200slam_fastmatch_pair_fetch": (i, [vp, c_float_p, c_float_p, c_int_p, c_int_p]),
         "b200slam_mappoints_grow_async": (i, [vp, f]),
+        "b200slam_scan_step_async": (i, [vp, c_float_p, i, vp, vp, c_float_p, c_float_p, c_float_p]),
+        "b200slam_scan_step_resident_async": (i, [vp, C.c_int64, i, vp, vp, c_float_p, c_float_p, c_float_p]),
         "b200slam_csv_ingest": (i, [vp, vp, C.c_size_t, vp, C.c_int64, c_i64_p]),
         "b200slam_csv_values": (i, [vp, C.POINTER(vp), c_i64_p]),
         "b200slam_scan_transform": (i, [vp, c_float_p]),
@@ -409,6 +411,19 @@ class Context:
         self._check(self.L.b200slam_fastmatch_pair_fetch(self.h, pa, pb, C.byref(n), C.byref(bh)))
         self._nbeams = n.value
         return np.array(list(pa), np.float32), np.array(list(pb), np.float32), n.value, bh.value
+
+    def scan_step_async(self, ranges, map_a: Map, map_b: Map, pose, res_a, res_b, max_range: int = 24):
+        """readAScan + FastMatch + FastMatch2 as one kernel; fetch with fastmatch_pair_fetch."""
+        r = np.ascontiguousarray(ranges, np.float32)
+        assert len(r) == self._lidar_n
+        self._check(self.L.b200slam_scan_step_async(self.h, _fptr(r), int(max_range), map_a.h, map_b.h, _f3(pose), _f3(res_a),
+                                                    _f3(res_b)))
+        self._nbeams = self._lidar_n
+
+    def scan_step_resident_async(self, first_value: int, map_a: Map, map_b: Map, pose, res_a, res_b, max_range: int = 24):
+        self._check(self.L.b200slam_scan_step_resident_async(self.h, int(first_value), int(max_range), map_a.h, map_b.h,
+                                                             _f3(pose), _f3(res_a), _f3(res_b)))
+        self._nbeams = self._lidar_n
 
     def mappoints_grow_async(self, threshold: float = 1.5):
         self._check(self.L.b200slam_mappoints_grow_async(self.h, threshold))

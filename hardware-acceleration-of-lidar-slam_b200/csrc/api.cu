@@ -756,21 +756,12 @@ int b200slam_fastmatch(b200slam_ctx *ctx, b200slam_map *map, const float pose[3]
 
 /* ---- FastMatch + FastMatch2 without a host round trip in between ------------------------ */
 
-int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200slam_map *map_b, const float pose[3],
-                                  const float res_a[3], const float res_b[3])
+// FastMatch2 starts from FastMatch's result (main.c:918), which is one of 3 x 3 x 3 lattice points: the axis
+// tables of every possible centre, computed exactly as stage_lattice would from the fetched pose (main.c:424-437:
+// the centre is itself a lattice value of the first match).  t: ct[3][3] | st[3][3] | sxt[3][3] | syt[3][3].
+static void seeded_tables(const b200slam_map *map_b, const float pose[3], const float step_a[3], const float step_b[3],
+                          float t[36])
 {
-    if (!ctx || !map_a || !map_b || !pose || !res_a || !res_b) return B200SLAM_ERR_ARG;
-    const float step_a[3] = {res_a[0], res_a[0], res_a[2]};               // main.c:386-387
-    const float step_b[3] = {res_b[0], res_b[0], res_b[2]};
-    const int n[3] = {3, 3, 3};
-    int rc = queue_lattice(ctx, map_a, pose, step_a, n, 0, 9, false, 0);  // FastMatch (main.c:902 / :909)
-    if (rc) return rc;
-    rc = check_lattice_args(ctx, map_b, pose, step_b, n);
-    if (rc) return rc;
-    // FastMatch2 starts from FastMatch's result (main.c:918), which is one of 3 x 3 x 3 lattice points: the axis
-    // tables of every possible centre, computed here exactly as stage_lattice would from the fetched pose
-    // (main.c:424-437: the centre is itself a lattice value of the first match)
-    float *t = ctx->h_param_tab;
     const float ipixel = 1 / map_b->pixel_size;                          // main.c:383
     for (int s1 = 0; s1 < 3; ++s1) {
         const float th1 = b200slam_lattice_value(pose[2], step_a[2], s1, 3);
@@ -788,6 +779,42 @@ int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200sl
             t[27 + 3 * s1 + k] = dy * ipixel;                                     // main.c:437
         }
     }
+}
+
+static int pair_bookkeeping(b200slam_ctx *ctx, const float pose[3], const float step_a[3], const float step_b[3])
+{
+    ctx->last.valid = true; ctx->last.is_poses = false; ctx->last.gathered = false; ctx->last.exchanged = false;
+    for (int i = 0; i < 3; ++i) {
+        ctx->last.n[i] = 3;
+        ctx->last.step[i] = step_b[i];
+        ctx->pair.guess[i] = pose[i]; ctx->pair.step_a[i] = step_a[i]; ctx->pair.step_b[i] = step_b[i];
+    }
+    ctx->pair.valid = true;
+    return B200SLAM_OK;
+}
+
+static int ensure_host_result(b200slam_ctx *ctx)
+{
+    if (!ctx->h_result) {
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_result, sizeof(MatchHost), cudaHostAllocMapped));
+        memset(ctx->h_result, 0, sizeof(MatchHost));
+    }
+    return B200SLAM_OK;
+}
+
+int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200slam_map *map_b, const float pose[3],
+                                  const float res_a[3], const float res_b[3])
+{
+    if (!ctx || !map_a || !map_b || !pose || !res_a || !res_b) return B200SLAM_ERR_ARG;
+    const float step_a[3] = {res_a[0], res_a[0], res_a[2]};               // main.c:386-387
+    const float step_b[3] = {res_b[0], res_b[0], res_b[2]};
+    const int n[3] = {3, 3, 3};
+    int rc = queue_lattice(ctx, map_a, pose, step_a, n, 0, 9, false, 0);  // FastMatch (main.c:902 / :909)
+    if (rc) return rc;
+    rc = check_lattice_args(ctx, map_b, pose, step_b, n);
+    if (rc) return rc;
+    float *t = ctx->h_param_tab;
+    seeded_tables(map_b, pose, step_a, step_b, t);
     LatticeLaunch L;
     L.map = map_b;
     L.nth = L.ntx = L.nty = 3;
@@ -797,22 +824,68 @@ int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200sl
     L.d_scores = nullptr;
     L.exchange = L.collect_prev = L.post_deferred = false;
     L.seeded = true;
-    if (!ctx->h_result) {
-        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_result, sizeof(MatchHost), cudaHostAllocMapped));
-        memset(ctx->h_result, 0, sizeof(MatchHost));
-    }
+    rc = ensure_host_result(ctx);
+    if (rc) return rc;
     L.host_result = true;
     ctx->result_seq++;
     rc = lattice_launch(ctx, L);
     if (rc) return rc;
-    ctx->last.valid = true; ctx->last.is_poses = false; ctx->last.gathered = false; ctx->last.exchanged = false;
-    for (int i = 0; i < 3; ++i) {
-        ctx->last.n[i] = 3;
-        ctx->last.step[i] = step_b[i];
-        ctx->pair.guess[i] = pose[i]; ctx->pair.step_a[i] = step_a[i]; ctx->pair.step_b[i] = step_b[i];
-    }
-    ctx->pair.valid = true;
-    return B200SLAM_OK;
+    return pair_bookkeeping(ctx, pose, step_a, step_b);
+}
+
+// readAScan + FastMatch + FastMatch2 as ONE kernel.  d_src: the scan's ranges on the device.
+static int scan_step_queue(b200slam_ctx *ctx, const float *d_src, int max_range, b200slam_map *map_a, b200slam_map *map_b,
+                           const float pose[3], const float res_a[3], const float res_b[3])
+{
+    const float step_a[3] = {res_a[0], res_a[0], res_a[2]};               // main.c:386-387
+    const float step_b[3] = {res_b[0], res_b[0], res_b[2]};
+    const int n[3] = {3, 3, 3};
+    if (!map_a->has_geometry || !map_b->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
+    LatticeLaunch L;
+    int rc = stage_lattice(ctx, map_a, pose, step_a, n, 0, 9, &L);        // 12 floats in ctx->h_param_tab
+    if (rc) return rc;
+    float t12[12], t36[36];
+    memcpy(t12, L.h_tables, sizeof t12);
+    seeded_tables(map_b, pose, step_a, step_b, t36);
+    rc = ensure_host_result(ctx);
+    if (rc) return rc;
+    ctx->result_seq++;
+    rc = scan_step_launch(ctx, map_a, map_b, t12, t36, d_src, max_range);
+    if (rc) return rc;
+    ctx->nbeams = ctx->lidar_n;            // upper bound until the fetch
+    ctx->scan_n_dev = true;
+    ctx->scan_t_valid = false;
+    return pair_bookkeeping(ctx, pose, step_a, step_b);
+}
+
+int b200slam_scan_step_async(b200slam_ctx *ctx, const float *ranges, int max_range, b200slam_map *map_a, b200slam_map *map_b,
+                             const float pose[3], const float res_a[3], const float res_b[3])
+{
+    if (!ctx || !ranges || !map_a || !map_b || !pose || !res_a || !res_b) return B200SLAM_ERR_ARG;
+    if (ctx->lidar_n <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_lidar_set first");
+    int rc = ensure_scan_capacity(ctx, ctx->lidar_n);
+    if (!rc) rc = ensure_front(ctx);
+    if (rc) return rc;
+    const int nl = ctx->lidar_n;
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->scan_event));                  // pinned staging free again
+    memcpy(ctx->h_ranges, ranges, sizeof(float) * nl);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ranges, ctx->h_ranges, sizeof(float) * nl, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->scan_event, ctx->stream));
+    return scan_step_queue(ctx, ctx->d_ranges, max_range, map_a, map_b, pose, res_a, res_b);
+}
+
+int b200slam_scan_step_resident_async(b200slam_ctx *ctx, int64_t first_value, int max_range, b200slam_map *map_a,
+                                      b200slam_map *map_b, const float pose[3], const float res_a[3], const float res_b[3])
+{
+    if (!ctx || first_value < 0 || !map_a || !map_b || !pose || !res_a || !res_b) return B200SLAM_ERR_ARG;
+    if (ctx->lidar_n <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_lidar_set first");
+    if (!ctx->d_csv_values || first_value + ctx->lidar_n > ctx->csv_count)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "values [%lld, %lld) are not in the ingested CSV (%lld values)",
+                                  (long long)first_value, (long long)(first_value + ctx->lidar_n), (long long)ctx->csv_count);
+    int rc = ensure_scan_capacity(ctx, ctx->lidar_n);
+    if (!rc) rc = ensure_front(ctx);
+    if (rc) return rc;
+    return scan_step_queue(ctx, ctx->d_csv_values + first_value, max_range, map_a, map_b, pose, res_a, res_b);
 }
 
 int b200slam_fastmatch_pair_fetch(b200slam_ctx *ctx, float pose_a[3], float pose_b[3], int *scan_size, int *best_hits_size)

@@ -300,6 +300,8 @@ struct LatticeLaunch {
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
 int exchange_collect_launch(b200slam_ctx *ctx);
+int scan_step_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_map *mb, const float *tables12,
+                     const float *tables36, const float *d_ranges, int max_range);
 // B200SLAM_ERR_STATE (with a message) when a bounded device-side wait has given up since the last comm_init.
 int device_error_check(b200slam_ctx *ctx, unsigned int error_bits);
 inline XchgArgs xchg_args(const b200slam_ctx *ctx)

@@ -866,15 +866,26 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
 // FastMatch + FastMatch2 pair went from ~95 us to ~?? us of GPU time per scan.
 constexpr int FM_THREADS = 1024;
 constexpr int FM_MAX_CAND = 32;
-constexpr int FM_MAX_BEAMS = 1536;             // vals: 27..32 x (1536 + 1) floats <= 197 KB of shared memory
+constexpr int FM_MAX_BEAMS = 1536;             // vals: 27..32 x (1536 + 4) floats <= 197 KB of shared memory
+constexpr int FM_TAB_B = 128;                  // offset of the second pass's tables in the parameter block
 
-struct FmArgs {
-    const float *field;
+struct FmMap {
+    const float *field;       // [0][0]; field[-1] == 0
     int pitch, rows, cols;
-    const float *scan_x, *scan_y;
-    int nbeams;
-    const int *nbeams_dev;
     float ipixel;
+};
+
+// One launch = optional readAScan + one or two matches ("passes").  Pass 0 reads its axis tables ct | st | sxt | syt
+// packed at the front of the parameter block -- or, seeded0, all three candidate table sets per axis (36 floats),
+// picked by the winner the kernel IN FRONT left in match->key.  Pass 1 (b200slam_scan_step_async: FastMatch2 from
+// FastMatch's result, main.c:909-918) is always seeded, by pass 0's own winner, from the 36 floats at FM_TAB_B.
+struct FmArgs {
+    FmMap map[2];
+    int npass;
+    int seeded0;
+    const float *scan_x, *scan_y;
+    int nbeams;               // upper bound when nbeams_dev / read_scan is set
+    const int *nbeams_dev;
     int nth, ntx, nty;
     int nbp;                  // row pitch of vals (beam capacity rounded up to a multiple of 32, plus 4)
     MatchDev *match;
@@ -882,7 +893,12 @@ struct FmArgs {
     MatchHost *host_result;
     unsigned long long host_seq;
     const int *mp_n_dev;
-    int seeded;
+    // readAScan in front (main.c:71-95), nullptr: the scan is already there
+    const float *ranges, *cos_a, *sin_a;
+    int lidar_n, max_range;
+    float range_min;
+    float *scan_x_out, *scan_y_out;
+    b200slam_ctx::FrontOut *front;
 };
 
 __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_constant__ FmArgs A, const __grid_constant__ LatticeTables T)
@@ -894,130 +910,185 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
     __shared__ float tab_s[4 * FM_MAX_CAND];
     __shared__ int cnt_s[FM_MAX_CAND];
     __shared__ int stair_c[FM_MAX_CAND], stair_lo[FM_MAX_CAND];
-    __shared__ int nstair_s;
+    __shared__ int nstair_s, nscan_s;
+    __shared__ int wcount_s[FM_THREADS / 32];
     __shared__ unsigned long long key_s;
 
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
-    const float *ctT = T.v, *stT = T.v + A.nth, *sxtT = T.v + 2 * A.nth, *sytT = sxtT + A.ntx;
-    unsigned long long seed = ~0ull;
-    if (A.seeded) {
-        // centred on the winner of the match in front (main.c:909-918): the host sent the axis tables of all three
-        // possible centres per axis; see lattice_kernel
-        pdl_wait_prior_grids();
-        seed = *reinterpret_cast<volatile unsigned long long *>(&A.match->key);
-        const int lin1 = seed == ~0ull ? 13 : (int)(seed & 0xffffffffull);
-        const int ith1 = lin1 / 9, itx1 = (lin1 / 3) % 3, ity1 = lin1 % 3;
-        ctT = T.v + 3 * ith1; stT = T.v + 9 + 3 * ith1; sxtT = T.v + 18 + 3 * itx1; sytT = T.v + 27 + 3 * ity1;
+    int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
+    if (A.ranges) {
+        // ---- readAScan (main.c:71-95): drop r < range_min | r > max_range, x = r cos, y = r sin, compacted in
+        // beam order (the same arithmetic as scan_read_kernel, frontend.cu) -----------------------------------
+        pdl_wait_prior_grids();                       // the scan buffers belong to the kernels in front
+        const float maxr = (float)A.max_range;
+        int base = 0;
+        for (int i0 = 0; i0 < A.lidar_n; i0 += FM_THREADS) {
+            const int i = i0 + tid;
+            float r = 0.0f;
+            bool keep = false;
+            if (i < A.lidar_n) {
+                r = A.ranges[i];
+                keep = !((r < A.range_min) | (r > maxr));                             // main.c:78
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, keep);
+            __syncthreads();
+            if (lane == 0) wcount_s[warp] = __popc(m);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll 8
+            for (int w = 0; w < FM_THREADS / 32; ++w) {
+                const int c = wcount_s[w];
+                before += w < warp ? c : 0;
+                total += c;
+            }
+            if (keep) {
+                const int slot = base + before + __popc(m & ((1u << lane) - 1u));
+                A.scan_x_out[slot] = __fmul_rn(r, A.cos_a[i]);                        // main.c:90
+                A.scan_y_out[slot] = __fmul_rn(r, A.sin_a[i]);                        // main.c:91
+            }
+            base += total;
+        }
+        if (tid == 0) { A.front->count = base; A.front->scan_n = base; nscan_s = base; }
+        __threadfence_block();
+        __syncthreads();                              // the scan just written is read below through global memory
+        nbeams = nscan_s;
     }
-    if (tid < A.nth) { tab_s[tid] = ctT[tid]; tab_s[FM_MAX_CAND + tid] = stT[tid]; }
-    if (tid < A.ntx) tab_s[2 * FM_MAX_CAND + tid] = sxtT[tid];
-    if (tid < A.nty) tab_s[3 * FM_MAX_CAND + tid] = sytT[tid];
-    __syncthreads();
 
-    // ---- phase 1: every (beam, theta) item: rotation, cell indices, gathers ----------------------------------
-    for (int j = 0; j < A.nth; ++j) {
-        const float ct = tab_s[j], st = tab_s[FM_MAX_CAND + j];
-        for (int i = tid; i < nbeams; i += FM_THREADS) {
-            const float psx = __fmul_rn(A.scan_x[i], A.ipixel);                       // main.c:418
-            const float psy = __fmul_rn(A.scan_y[i], A.ipixel);                       // main.c:419
-            const float Sx = rot_x(psx, psy, ct, st), Sy = rot_y(psx, psy, ct, st);   // main.c:462-463
-            unsigned int mask = 0;
-            for (int kx = 0; kx < A.ntx; ++kx) {
-                const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), A.cols);          // main.c:483
-                for (int ky = 0; ky < A.nty; ++ky) {
-                    const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), A.rows);      // main.c:501
-                    const bool in = c >= 0 && r >= 0;                                                  // main.c:512
-                    vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(A.field + (in ? r * A.pitch + c : -1));
-                    mask |= (unsigned int)in << (kx * A.nty + ky);
+    unsigned long long seed = ~0ull, key = ~0ull;
+    int bh = 0, lh = 0, written = 0;
+    for (int pass = 0; pass < A.npass; ++pass) {
+        const FmMap M = A.map[pass];
+        // ---- axis tables of this pass ------------------------------------------------------------------------
+        {
+            const float *ctT = T.v, *stT = T.v + A.nth, *sxtT = T.v + 2 * A.nth, *sytT = sxtT + A.ntx;
+            if (pass == 1 || A.seeded0) {
+                // centred on the winner of the match in front (main.c:909-918): the host sent the axis tables of all
+                // three possible centres per axis; see lattice_kernel
+                const float *tb = T.v + (pass == 1 ? FM_TAB_B : 0);
+                if (pass == 0) {
+                    pdl_wait_prior_grids();
+                    seed = *reinterpret_cast<volatile unsigned long long *>(&A.match->key);
+                } else {
+                    seed = key;
                 }
+                const int lin1 = seed == ~0ull ? 13 : (int)(seed & 0xffffffffull);
+                const int ith1 = lin1 / 9, itx1 = (lin1 / 3) % 3, ity1 = lin1 % 3;
+                ctT = tb + 3 * ith1; stT = tb + 9 + 3 * ith1; sxtT = tb + 18 + 3 * itx1; sytT = tb + 27 + 3 * ity1;
             }
-            inb[j * A.nbp + i] = mask;
+            __syncthreads();                          // tab_s / cnt_s / vals of the previous pass are done with
+            if (tid < A.nth) { tab_s[tid] = ctT[tid]; tab_s[FM_MAX_CAND + tid] = stT[tid]; }
+            if (tid < A.ntx) tab_s[2 * FM_MAX_CAND + tid] = sxtT[tid];
+            if (tid < A.nty) tab_s[3 * FM_MAX_CAND + tid] = sytT[tid];
+            __syncthreads();
         }
-    }
-    __syncthreads();
+        // ---- phase 1: every (beam, theta) item: rotation, cell indices, gathers ------------------------------
+        const float *sx_src = A.ranges ? A.scan_x_out : A.scan_x, *sy_src = A.ranges ? A.scan_y_out : A.scan_y;
+        for (int j = 0; j < A.nth; ++j) {
+            const float ct = tab_s[j], st = tab_s[FM_MAX_CAND + j];
+            for (int i = tid; i < nbeams; i += FM_THREADS) {
+                const float psx = __fmul_rn(sx_src[i], M.ipixel);                     // main.c:418
+                const float psy = __fmul_rn(sy_src[i], M.ipixel);                     // main.c:419
+                const float Sx = rot_x(psx, psy, ct, st), Sy = rot_y(psx, psy, ct, st);   // main.c:462-463
+                unsigned int mask = 0;
+                for (int kx = 0; kx < A.ntx; ++kx) {
+                    const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), M.cols);          // main.c:483
+                    for (int ky = 0; ky < A.nty; ++ky) {
+                        const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), M.rows);      // main.c:501
+                        const bool in = c >= 0 && r >= 0;                                                  // main.c:512
+                        vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(M.field + (in ? r * M.pitch + c : -1));
+                        mask |= (unsigned int)in << (kx * A.nty + ky);
+                    }
+                }
+                inb[j * A.nbp + i] = mask;
+            }
+        }
+        __syncthreads();
 
-    // ---- phase 2: warp 0 -- one thread per candidate, beams in scan order (main.c:516), 4 per LDS.128; meanwhile
-    // warp c + 1 counts candidate c's in-bounds beams (bestHits_size, main.c:515-516) ----------------------------
-    unsigned long long key = ~0ull;
-    if (warp == 0) {
-        if (tid < ncand) {
-            const float *v = vals + (size_t)tid * A.nbp;                                  // 16-byte aligned: nbp % 4 == 0
-            float s = 0.0f;                                                               // main.c:507
-            int i = 0;
-            for (; i + 8 <= nbeams; i += 8) {
-                const float4 a = *reinterpret_cast<const float4 *>(v + i), b = *reinterpret_cast<const float4 *>(v + i + 4);
-                s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
-                s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
+        // ---- phase 2: warp 0 -- one thread per candidate, beams in scan order (main.c:516), 8 per iteration with
+        // the next 8 already loaded; meanwhile warp c + 1 counts candidate c's in-bounds beams (main.c:515-516) ----
+        key = ~0ull;
+        if (warp == 0) {
+            if (tid < ncand) {
+                const float *v = vals + (size_t)tid * A.nbp;                          // 16-byte aligned: nbp % 4 == 0
+                float s = 0.0f;                                                       // main.c:507
+                int i = 0;
+                if (nbeams >= 8) {
+                    float4 a = *reinterpret_cast<const float4 *>(v), b = *reinterpret_cast<const float4 *>(v + 4);
+                    for (; i + 16 <= nbeams; i += 8) {
+                        const float4 na = *reinterpret_cast<const float4 *>(v + i + 8), nb = *reinterpret_cast<const float4 *>(v + i + 12);
+                        s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
+                        s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
+                        a = na; b = nb;
+                    }
+                    s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
+                    s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
+                    i += 8;
+                }
+                for (; i < nbeams; ++i) s = __fadd_rn(s, v[i]);
+                key = pack_key(s, (unsigned int)tid);
             }
-            for (; i < nbeams; ++i) s = __fadd_rn(s, v[i]);
-            key = pack_key(s, (unsigned int)tid);
+        } else {
+            for (int c = warp - 1; c < ncand; c += FM_THREADS / 32 - 1) {
+                const unsigned int *m = inb + (c / per_th) * A.nbp;
+                const int bit = c % per_th;
+                int n = 0;
+                for (int i = lane; i < nbeams; i += 32) n += (m[i] >> bit) & 1u;
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) n += __shfl_xor_sync(0xffffffffu, n, sft);
+                if (lane == 0) cnt_s[c] = n;
+            }
         }
-    } else {
-        for (int c = warp - 1; c < ncand; c += FM_THREADS / 32 - 1) {
+        // ---- phase 3: arg-min (lowest score, then lowest index: strict `<` in loop order, main.c:549) -----------
+        if (warp == 0) {
+            key = warp_min_u64(key);
+            if (lane == 0) key_s = key;
+        }
+        __syncthreads();
+        key = key_s;
+        // The match state and the bestHits[] twin belong to the kernel in front until it has completed.
+        pdl_wait_prior_grids();
+        if (tid == 0) {
+            // main.c:515: walk the candidates backwards; each one longer than what has been written so far supplies
+            // the entries it alone still owns
+            int ns = 0, w = 0;
+            for (int c = ncand - 1; c >= 0; --c)
+                if (c == ncand - 1 || cnt_s[c] > w) {
+                    stair_c[ns] = c; stair_lo[ns] = c == ncand - 1 ? 0 : w; ++ns;
+                    w = cnt_s[c];
+                }
+            nstair_s = ns;
+        }
+        __syncthreads();
+        for (int e = warp; e < nstair_s; e += FM_THREADS / 32) {
+            const int c = stair_c[e], lo = stair_lo[e];
+            const float *v = vals + (size_t)c * A.nbp;
             const unsigned int *m = inb + (c / per_th) * A.nbp;
             const int bit = c % per_th;
-            int n = 0;
-            for (int i = lane; i < nbeams; i += 32) n += (m[i] >> bit) & 1u;
-#pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) n += __shfl_xor_sync(0xffffffffu, n, sft);
-            if (lane == 0) cnt_s[c] = n;
+            int run = 0;
+            for (int i0 = 0; i0 < nbeams; i0 += 32) {
+                const int i = i0 + lane;
+                const bool in = i < nbeams && ((m[i] >> bit) & 1u);
+                const unsigned int bal = __ballot_sync(0xffffffffu, in);
+                const int pos = run + __popc(bal & ((1u << lane) - 1u));
+                if (in && pos >= lo) A.hit_values[pos] = v[i];
+                run += __popc(bal);
+            }
         }
-    }
-    // ---- phase 3: arg-min (lowest score, then lowest index: strict `<` in loop order, main.c:549) --------------
-    if (warp == 0) {
-        key = warp_min_u64(key);
-        if (lane == 0) key_s = key;
-    }
-    __syncthreads();
-    key = key_s;
-    // The match state and the bestHits[] twin belong to the kernel in front until it has completed.
-    pdl_wait_prior_grids();
-    if (tid == 0) {
-        // main.c:515: walk the candidates backwards; each one longer than what has been written so far supplies
-        // the entries it alone still owns
-        int ns = 0, written = 0;
-        if (key != ~0ull) {
-            for (int c = ncand - 1; c >= 0; --c)
-                if (c == ncand - 1 || cnt_s[c] > written) {
-                    stair_c[ns] = c; stair_lo[ns] = c == ncand - 1 ? 0 : written; ++ns;
-                    written = cnt_s[c];
-                }
-        }
-        nstair_s = ns;
-    }
-    __syncthreads();
-    for (int e = warp; e < nstair_s; e += FM_THREADS / 32) {
-        const int c = stair_c[e], lo = stair_lo[e];
-        const float *v = vals + (size_t)c * A.nbp;
-        const unsigned int *m = inb + (c / per_th) * A.nbp;
-        const int bit = c % per_th;
-        int run = 0;
-        for (int i0 = 0; i0 < nbeams; i0 += 32) {
-            const int i = i0 + lane;
-            const bool in = i < nbeams && ((m[i] >> bit) & 1u);
-            const unsigned int bal = __ballot_sync(0xffffffffu, in);
-            const int pos = run + __popc(bal & ((1u << lane) - 1u));
-            if (in && pos >= lo) A.hit_values[pos] = v[i];
-            run += __popc(bal);
-        }
+        bh = cnt_s[(int)(key & 0xffffffffull)];                                       // bestHits_size: the winner's (main.c:557)
+        lh = cnt_s[ncand - 1];
+        written = 0;
+        for (int e = 0; e < nstair_s; ++e) written = max(written, cnt_s[stair_c[e]]);
     }
     if (tid == 0) {
-        int bh = 0, lh = 0, written = 0;
-        if (key != ~0ull) {
-            bh = cnt_s[(int)(key & 0xffffffffull)];                                   // bestHits_size: the winner's (main.c:557)
-            lh = cnt_s[ncand - 1];
-            for (int e = 0; e < nstair_s; ++e) written = max(written, cnt_s[stair_c[e]]);
-        }
         A.match->key = key;
         A.match->best_hits = bh;
         A.match->last_hits = lh;
         A.match->written_hits = written;
-        if (A.seeded) A.match->seed_key = seed;
+        if (A.npass > 1 || A.seeded0) A.match->seed_key = seed;
         if (A.host_result) {
             volatile MatchHost *h = A.host_result;
-            h->key = key; h->seed_key = A.seeded ? seed : ~0ull;
+            h->key = key; h->seed_key = (A.npass > 1 || A.seeded0) ? seed : ~0ull;
             h->best_hits = bh; h->last_hits = lh; h->written_hits = written;
             h->scan_n = nbeams;
             h->mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
@@ -1028,19 +1099,15 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
     }
 }
 
-int launch_fastmatch(b200slam_ctx *ctx, const LatticeArgs &L, const LatticeTables &T)
+size_t fastmatch_smem_bytes(int ncand, int nth, int nbeams)
 {
-    FmArgs A;
-    A.field = L.field; A.pitch = L.pitch; A.rows = L.rows; A.cols = L.cols;
-    A.scan_x = L.scan_x; A.scan_y = L.scan_y; A.nbeams = L.nbeams; A.nbeams_dev = L.nbeams_dev;
-    A.ipixel = L.ipixel;
-    A.nth = L.nth; A.ntx = L.ntx; A.nty = L.nty;
-    A.nbp = ((L.nbeams + 31) & ~31) + 4;                  // + 4: rows stay 16-byte aligned and start 4 banks apart
-    A.match = L.match;
-    A.hit_values = L.hit_values + L.hit_stride;
-    A.host_result = L.host_result; A.host_seq = L.host_seq; A.mp_n_dev = L.mp_n_dev;
-    A.seeded = L.seeded;
-    const size_t smem = sizeof(float) * (size_t)(L.nth * L.ntx * L.nty + L.nth) * A.nbp;
+    return sizeof(float) * (size_t)(ncand + nth) * (((nbeams + 31) & ~31) + 4);
+}
+
+int fastmatch_launch_args(b200slam_ctx *ctx, FmArgs &A, const LatticeTables &T)
+{
+    A.nbp = ((A.nbeams + 31) & ~31) + 4;                  // + 4: rows stay 16-byte aligned and start 4 banks apart
+    const size_t smem = fastmatch_smem_bytes(A.nth * A.ntx * A.nty, A.nth, A.nbeams);
     static bool smem_set[64] = {};
     if (!smem_set[ctx->device & 63]) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(fastmatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1059,8 +1126,24 @@ int launch_fastmatch(b200slam_ctx *ctx, const LatticeArgs &L, const LatticeTable
     CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, fastmatch_kernel, A, T));
     LAUNCH_CHECK(ctx);
     ctx->prev_launch_was_lattice = true;
-    ctx->prev_lattice_field = A.field;
+    ctx->prev_lattice_field = A.map[A.npass - 1].field;
     return B200SLAM_OK;
+}
+
+int launch_fastmatch(b200slam_ctx *ctx, const LatticeArgs &L, const LatticeTables &T)
+{
+    FmArgs A = {};
+    A.map[0].field = L.field; A.map[0].pitch = L.pitch; A.map[0].rows = L.rows; A.map[0].cols = L.cols; A.map[0].ipixel = L.ipixel;
+    A.map[1] = A.map[0];
+    A.npass = 1;
+    A.seeded0 = L.seeded;
+    A.scan_x = L.scan_x; A.scan_y = L.scan_y; A.nbeams = L.nbeams; A.nbeams_dev = L.nbeams_dev;
+    A.nth = L.nth; A.ntx = L.ntx; A.nty = L.nty;
+    A.match = L.match;
+    A.hit_values = L.hit_values + L.hit_stride;
+    A.host_result = L.host_result; A.host_seq = L.host_seq; A.mp_n_dev = L.mp_n_dev;
+    A.ranges = nullptr;
+    return fastmatch_launch_args(ctx, A, T);
 }
 
 template <int TYPT, int WX, int WY, int UM = 1, bool COUNT = false, int Q = 0, int PITCH = 0, int NB = 0>
@@ -1171,7 +1254,7 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
         L.row_end == (int64_t)L.nth * L.ntx && !A.xchg.peers && L.nth_tab == L.nth) {
         // the reference's own size class: one CTA, gathers across all threads (fastmatch_kernel); scans longer than
         // its shared memory holds, > 32 candidates or a wanted score table take the general kernel
-        const size_t fm_smem = sizeof(float) * (size_t)(L.nth * L.ntx * L.nty + L.nth) * (((A.nbeams + 31) & ~31) + 4);
+        const size_t fm_smem = fastmatch_smem_bytes(L.nth * L.ntx * L.nty, L.nth, A.nbeams);
         if ((long long)L.nth * L.ntx * L.nty <= FM_MAX_CAND && A.nbeams <= FM_MAX_BEAMS && fm_smem <= 216 * 1024 && !A.scores &&
             !L.d_tables && !getenv("B200SLAM_NO_FASTMATCH_KERNEL"))
             return launch_fastmatch(ctx, A, T);
@@ -1242,6 +1325,38 @@ int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L)
     B200SLAM_CFG(16, 2, 4, 1, 4) B200SLAM_CFG(8, 1, 8, 1, 4) B200SLAM_CFG(4, 1, 8, 1, 4)      // row reuse, step = pixel / 4
 #undef B200SLAM_CFG
     return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "B200SLAM_LATTICE_CFG names no compiled tile shape");
+}
+
+// readAScan + FastMatch + FastMatch2 as ONE kernel (b200slam_scan_step_async).  tables: 12 floats of the first
+// lattice at [0], the 36 floats of the seeded second lattice at [FM_TAB_B].
+int scan_step_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_map *mb, const float *tables12,
+                     const float *tables36, const float *d_ranges, int max_range)
+{
+    FmArgs A = {};
+    const b200slam_map *mm[2] = {ma, mb};
+    for (int p = 0; p < 2; ++p) {
+        A.map[p].field = mm[p]->d_field; A.map[p].pitch = mm[p]->field_pitch; A.map[p].rows = mm[p]->rows;
+        A.map[p].cols = mm[p]->cols; A.map[p].ipixel = 1 / mm[p]->pixel_size;                 // main.c:383
+    }
+    A.npass = 2;
+    A.seeded0 = 0;
+    A.scan_x = ctx->d_scan_x; A.scan_y = ctx->d_scan_y;
+    A.nbeams = ctx->lidar_n; A.nbeams_dev = nullptr;
+    A.nth = A.ntx = A.nty = 3;
+    A.match = ctx->d_match;
+    A.hit_values = ctx->d_hit_values + ctx->scan_cap;
+    A.host_result = ctx->h_result; A.host_seq = ctx->result_seq;
+    A.mp_n_dev = (ctx->mp_n_dev && ctx->d_front) ? &ctx->d_front->mp_n : nullptr;
+    A.ranges = d_ranges; A.cos_a = ctx->d_lidar; A.sin_a = ctx->d_lidar + ctx->lidar_n;
+    A.lidar_n = ctx->lidar_n; A.max_range = max_range; A.range_min = ctx->lidar_range_min;
+    A.scan_x_out = ctx->d_scan_x; A.scan_y_out = ctx->d_scan_y;
+    A.front = ctx->d_front;
+    if (A.nbeams > FM_MAX_BEAMS || fastmatch_smem_bytes(27, 3, A.nbeams) > 216 * 1024)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "scan of %d beams exceeds the fused scan step (%d)", A.nbeams, FM_MAX_BEAMS);
+    LatticeTables T;
+    memcpy(T.v, tables12, sizeof(float) * 12);
+    memcpy(T.v + FM_TAB_B, tables36, sizeof(float) * 36);
+    return fastmatch_launch_args(ctx, A, T);
 }
 
 int exchange_collect_launch(b200slam_ctx *ctx)

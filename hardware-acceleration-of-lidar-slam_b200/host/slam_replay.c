@@ -12,9 +12,9 @@
  *   - the dataset is read once, uploaded as raw text and parsed ON THE GPU (b200slam_csv_ingest: the
  *     reference's fscanf("%f,") loop, main.c:22-30, bit for bit); readAScan then reads its ranges from
  *     the resident values;
- *   - per scan the host queues readAScan and the FastMatch / FastMatch2 pair (three kernels, no host step
+ *   - per scan the host queues ONE kernel -- readAScan, FastMatch and FastMatch2 in one CTA (no host step
  *     between them: scan.size stays on the device, and the second match picks its lattice by the first
- *     one's winner) and synchronises ONCE to fetch the two poses it needs for the motion model, the
+ *     one's winner) -- and synchronises ONCE to fetch the two poses it needs for the motion model, the
  *     mini-update test (main.c:875-898, 928-940) and the next lattice's cosf / sinf;
  *   - map growth (main.c:942-948) is queued without reading its count back; only a map rebuild (2 % of
  *     the scans) reads sizes, because the grid geometry is computed with the reference's host float
@@ -156,13 +156,15 @@ int main(int argc, char **argv)
                 fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
                 return 1;
             }
-            must(b200slam_scan_read_async(ctx, ranges, 24), "scan_read");
-        } else {
-            if ((int64_t)(scan_iter + 1) * COLUMN > nvalues) {
-                fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
-                return 1;
-            }
-            must(b200slam_scan_read_resident_async(ctx, (int64_t)scan_iter * COLUMN, 24), "scan_read");
+        } else if ((int64_t)(scan_iter + 1) * COLUMN > nvalues) {
+            fprintf(stderr, "b200slam_replay: dataset ends at scan %d (asked for %d)\n", scan_iter, row);
+            return 1;
+        }
+        /* After a mini update the scan is needed by Transform / ExtractLocalMap before the matches: readAScan is
+         * its own kernel.  Otherwise (98 % of the scans) readAScan + FastMatch2 + FastMatch2 are ONE kernel below. */
+        if (miniUpdated) {
+            if (host_parse) must(b200slam_scan_read_async(ctx, ranges, 24), "scan_read");
+            else must(b200slam_scan_read_resident_async(ctx, (int64_t)scan_iter * COLUMN, 24), "scan_read");
         }
         t_read += now_s() - t0; t0 = now_s();
         int scan_transform_flag = 0;
@@ -186,8 +188,13 @@ int main(int argc, char **argv)
         }
         /* main.c:901-922: FastMatch (coarse grid after a rebuild, else the fine one) then FastMatch2 from its
          * result -- two kernels back to back, one synchronisation */
-        must(b200slam_fastmatch_pair_async(ctx, miniUpdated ? coarse : fine, fine, pose_guess, fastResolution,
-                                           fastResolution2), "fastmatch pair");
+        if (miniUpdated)
+            must(b200slam_fastmatch_pair_async(ctx, coarse, fine, pose_guess, fastResolution, fastResolution2), "fastmatch pair");
+        else if (host_parse)
+            must(b200slam_scan_step_async(ctx, ranges, 24, fine, fine, pose_guess, fastResolution, fastResolution2), "scan step");
+        else
+            must(b200slam_scan_step_resident_async(ctx, (int64_t)scan_iter * COLUMN, 24, fine, fine, pose_guess, fastResolution,
+                                                   fastResolution2), "scan step");
         t_queue += now_s() - t0; t0 = now_s();
         must(b200slam_fastmatch_pair_fetch(ctx, NULL, pose, &size, NULL), "fastmatch pair fetch");
         t_fetch += now_s() - t0; t0 = now_s();

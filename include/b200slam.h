@@ -272,6 +272,16 @@ int b200slam_fastmatch_pair_async(b200slam_ctx *ctx, b200slam_map *map_a, b200sl
                                   const float res_a[3], const float res_b[3]);
 int b200slam_fastmatch_pair_fetch(b200slam_ctx *ctx, float pose_a[3], float pose_b[3], int *scan_size, int *best_hits_size);
 int b200slam_mappoints_grow_async(b200slam_ctx *ctx, float threshold);
+/* The whole steady-state scan of the reference's loop as ONE kernel launch: readAScan (main.c:71-95) on `ranges`
+ * (host, lidar_n floats; _resident: values [first_value, first_value + lidar_n) of b200slam_csv_ingest), then
+ * FastMatch on map_a around `pose` and FastMatch2 on map_b around its result (main.c:902-918), one CTA, the scan
+ * and both matches' working set in shared memory.  Equivalent to b200slam_scan_read_async +
+ * b200slam_fastmatch_pair_async (same results, same side effects: scan, scan size, bestHits[] twin);
+ * b200slam_fastmatch_pair_fetch returns the result.  Scans of up to 1536 beams. */
+int b200slam_scan_step_async(b200slam_ctx *ctx, const float *ranges, int max_range, b200slam_map *map_a, b200slam_map *map_b,
+                             const float pose[3], const float res_a[3], const float res_b[3]);
+int b200slam_scan_step_resident_async(b200slam_ctx *ctx, int64_t first_value, int max_range, b200slam_map *map_a,
+                                      b200slam_map *map_b, const float pose[3], const float res_a[3], const float res_b[3]);
 
 /* ---- scan ingest -----------------------------------------------------------
  * Replaces readDatasetLineByLine (Subsystem_1/main.c:22-30): `column` x fscanf(fp, "%f,", &value).  The whole

@@ -158,9 +158,9 @@ def test_fastmatch_pair_equals_two_fastmatch_calls(b200slam, oracle, synth, smal
     res_a = np.array([0.05, 0.05, 0.008727], np.float32)
     res_b = np.array([0.025, 0.025, 0.004363], np.float32)
     poses = [np.array([w["pose0"][0] + 1.7 * k, w["pose0"][1] + 1.1 * k, w["pose0"][2] + 0.3 * k], np.float32) for k in range(9)]
-    with b200slam.Context(0) as ca, b200slam.Context(0) as cb:
+    with b200slam.Context(0) as ca, b200slam.Context(0) as cb, b200slam.Context(0) as cc:
         maps = {}
-        for c in (ca, cb):
+        for c in (ca, cb, cc):
             mf = c.new_map(*field.shape); mf.set_geometry(w["pixel"], w["top_left"]).upload_field(field)
             mc = c.new_map(*cfield.shape); mc.set_geometry(pixel_c, tl_c).upload_field(cfield)
             maps[c] = (mc, mf)
@@ -186,6 +186,15 @@ def test_fastmatch_pair_equals_two_fastmatch_calls(b200slam, oracle, synth, smal
             assert np.array_equal(bits(s1), bits(o1)) and np.array_equal(bits(s2), bits(o2)) and sn == on, k
             assert np.array_equal(bits(cb.match_fetch_hits(2500)), bits(obuf)), k
             assert np.array_equal(bits(sbuf), bits(obuf)), k
-        for c in (ca, cb):
+            # readAScan + both matches as ONE kernel (b200slam_scan_step_async): same poses, counts, bestHits[] twin,
+            # and the scan it leaves on the device is readAScan's
+            cc.scan_step_async(ranges, maps[cc][0] if first_c else maps[cc][1], maps[cc][1], p, res_a, res_b)
+            qa, qb, qn, qbh = cc.fastmatch_pair_fetch()
+            assert qn == n and qbh == on
+            assert np.array_equal(bits(qa), bits(o1)) and np.array_equal(bits(qb), bits(o2)), k
+            assert np.array_equal(bits(cc.match_fetch_hits(2500)), bits(obuf)), k
+            gx, gy = cc.scan_download(transformed=False)
+            assert np.array_equal(bits(gx), bits(sx)) and np.array_equal(bits(gy), bits(sy))
+        for c in (ca, cb, cc):
             for m in maps[c]:
                 m.close()
