@@ -907,6 +907,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
     float *vals = reinterpret_cast<float *>(fm_smem);                                 // [ncand][nbp]
     const int ncand = A.nth * A.ntx * A.nty, per_th = A.ntx * A.nty;
     unsigned int *inb = reinterpret_cast<unsigned int *>(vals + (size_t)ncand * A.nbp);   // [nth][nbp]: bit (itx * nty + ity)
+    float2 *ps_s = reinterpret_cast<float2 *>(inb + (size_t)A.nth * A.nbp);              // [nbp]: the scan in pixels
     __shared__ float tab_s[4 * FM_MAX_CAND];
     __shared__ int cnt_s[FM_MAX_CAND];
     __shared__ int stair_c[FM_MAX_CAND], stair_lo[FM_MAX_CAND];
@@ -982,26 +983,32 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             if (tid < A.nty) tab_s[3 * FM_MAX_CAND + tid] = sytT[tid];
             __syncthreads();
         }
-        // ---- phase 1: every (beam, theta) item: rotation, cell indices, gathers ------------------------------
+        // ---- phase 1: every (beam, theta) item: rotation, cell indices, gathers.  The scaled scan goes through
+        // shared memory once per pass, the items are dealt out flat (3 x 1079 items = 3.2 per thread, not 6 for
+        // the threads that own a second beam), and the loop is unrolled so that the gathers of a thread's items
+        // are all in flight together: the phase costs about one L2 round trip.
         const float *sx_src = A.ranges ? A.scan_x_out : A.scan_x, *sy_src = A.ranges ? A.scan_y_out : A.scan_y;
-        for (int j = 0; j < A.nth; ++j) {
+        for (int i = tid; i < nbeams; i += FM_THREADS)
+            ps_s[i] = make_float2(__fmul_rn(sx_src[i], M.ipixel), __fmul_rn(sy_src[i], M.ipixel));      // main.c:418-419
+        __syncthreads();
+        const int nitems = nbeams * A.nth;
+#pragma unroll 4
+        for (int item = tid; item < nitems; item += FM_THREADS) {
+            const int j = item / nbeams, i = item - j * nbeams;
             const float ct = tab_s[j], st = tab_s[FM_MAX_CAND + j];
-            for (int i = tid; i < nbeams; i += FM_THREADS) {
-                const float psx = __fmul_rn(sx_src[i], M.ipixel);                     // main.c:418
-                const float psy = __fmul_rn(sy_src[i], M.ipixel);                     // main.c:419
-                const float Sx = rot_x(psx, psy, ct, st), Sy = rot_y(psx, psy, ct, st);   // main.c:462-463
-                unsigned int mask = 0;
-                for (int kx = 0; kx < A.ntx; ++kx) {
-                    const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), M.cols);          // main.c:483
-                    for (int ky = 0; ky < A.nty; ++ky) {
-                        const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), M.rows);      // main.c:501
-                        const bool in = c >= 0 && r >= 0;                                                  // main.c:512
-                        vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(M.field + (in ? r * M.pitch + c : -1));
-                        mask |= (unsigned int)in << (kx * A.nty + ky);
-                    }
+            const float2 ps = ps_s[i];
+            const float Sx = rot_x(ps.x, ps.y, ct, st), Sy = rot_y(ps.x, ps.y, ct, st);                 // main.c:462-463
+            unsigned int mask = 0;
+            for (int kx = 0; kx < A.ntx; ++kx) {
+                const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), M.cols);          // main.c:483
+                for (int ky = 0; ky < A.nty; ++ky) {
+                    const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), M.rows);      // main.c:501
+                    const bool in = c >= 0 && r >= 0;                                                  // main.c:512
+                    vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(M.field + (in ? r * M.pitch + c : -1));
+                    mask |= (unsigned int)in << (kx * A.nty + ky);
                 }
-                inb[j * A.nbp + i] = mask;
             }
+            inb[j * A.nbp + i] = mask;
         }
         __syncthreads();
 
@@ -1101,7 +1108,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
 
 size_t fastmatch_smem_bytes(int ncand, int nth, int nbeams)
 {
-    return sizeof(float) * (size_t)(ncand + nth) * (((nbeams + 31) & ~31) + 4);
+    return sizeof(float) * (size_t)(ncand + nth + 2) * (((nbeams + 31) & ~31) + 4);
 }
 
 int fastmatch_launch_args(b200slam_ctx *ctx, FmArgs &A, const LatticeTables &T)
