@@ -914,6 +914,14 @@ int b200slam_fastmatch_pair_fetch(b200slam_ctx *ctx, float pose_a[3], float pose
     }
     MatchHost m;
     m.key = h->key; m.seed_key = h->seed_key; m.best_hits = h->best_hits; m.error = h->error;
+    if (getenv("B200SLAM_FM_TRACE")) {              // diagnostics: SM cycles between the fused kernel's phase boundaries
+        static int printed = 0;
+        if (printed++ % 500 == 100) {
+            fprintf(stderr, "[b200slam] fastmatch kernel phases (cycles):");
+            for (int i = 1; i < 16 && h->trace[i]; ++i) fprintf(stderr, " %lld", h->trace[i] - h->trace[i - 1]);
+            fprintf(stderr, "\n");
+        }
+    }
     if (m.error) return device_error_check(ctx, m.error);
     if (ctx->scan_n_dev) ctx->nbeams = h->scan_n;
     if (ctx->mp_n_dev) ctx->mp_size = h->mp_n;

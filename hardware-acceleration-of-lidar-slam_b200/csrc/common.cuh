@@ -73,6 +73,7 @@ struct MatchHost {
     int best_hits, last_hits, written_hits, scan_n, mp_n;
     unsigned int error;
     unsigned long long seq;
+    long long trace[16];        // SM cycle counter at the fused kernel's phase boundaries (B200SLAM_FM_TRACE diagnostics)
 };
 constexpr int MATCH_SMALL = 64;
 // Every device-side wait is bounded (%globaltimer against b200slam_ctx::spin_timeout_ns, or an iteration

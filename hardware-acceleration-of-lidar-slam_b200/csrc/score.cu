@@ -899,6 +899,7 @@ struct FmArgs {
     float range_min;
     float *scan_x_out, *scan_y_out;
     b200slam_ctx::FrontOut *front;
+    int trace;                // diagnostics (B200SLAM_FM_TRACE): SM cycle counter at the phase boundaries -> host_result->trace
 };
 
 __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_constant__ FmArgs A, const __grid_constant__ LatticeTables T)
@@ -917,6 +918,9 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
 
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int ntrace = 0;
+#define FM_TRACE() do { if (A.trace && A.host_result && tid == 0 && ntrace < 16) A.host_result->trace[ntrace++] = clock64(); } while (0)
+    FM_TRACE();
     int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
     if (A.ranges) {
         // ---- readAScan (main.c:71-95): drop r < range_min | r > max_range, x = r cos, y = r sin, compacted in
@@ -955,6 +959,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
         __syncthreads();                              // the scan just written is read below through global memory
         nbeams = nscan_s;
     }
+    FM_TRACE();
 
     unsigned long long seed = ~0ull, key = ~0ull;
     int bh = 0, lh = 0, written = 0;
@@ -1011,6 +1016,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             inb[j * A.nbp + i] = mask;
         }
         __syncthreads();
+        FM_TRACE();
 
         // ---- phase 2: warp 0 -- one thread per candidate, beams in scan order (main.c:516), 8 per iteration with
         // the next 8 already loaded; meanwhile warp c + 1 counts candidate c's in-bounds beams (main.c:515-516) ----
@@ -1035,6 +1041,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
                 for (; i < nbeams; ++i) s = __fadd_rn(s, v[i]);
                 key = pack_key(s, (unsigned int)tid);
             }
+            FM_TRACE();
         } else {
             for (int c = warp - 1; c < ncand; c += FM_THREADS / 32 - 1) {
                 const unsigned int *m = inb + (c / per_th) * A.nbp;
@@ -1052,6 +1059,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             if (lane == 0) key_s = key;
         }
         __syncthreads();
+        FM_TRACE();
         key = key_s;
         // The match state and the bestHits[] twin belong to the kernel in front until it has completed.
         pdl_wait_prior_grids();
@@ -1086,6 +1094,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
         lh = cnt_s[ncand - 1];
         written = 0;
         for (int e = 0; e < nstair_s; ++e) written = max(written, cnt_s[stair_c[e]]);
+        FM_TRACE();
     }
     if (tid == 0) {
         A.match->key = key;
@@ -1100,10 +1109,12 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             h->scan_n = nbeams;
             h->mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
             h->error = *reinterpret_cast<volatile unsigned int *>(&A.match->error);
+            FM_TRACE();
             __threadfence_system();
             h->seq = A.host_seq;
         }
     }
+#undef FM_TRACE
 }
 
 size_t fastmatch_smem_bytes(int ncand, int nth, int nbeams)
@@ -1114,6 +1125,7 @@ size_t fastmatch_smem_bytes(int ncand, int nth, int nbeams)
 int fastmatch_launch_args(b200slam_ctx *ctx, FmArgs &A, const LatticeTables &T)
 {
     A.nbp = ((A.nbeams + 31) & ~31) + 4;                  // + 4: rows stay 16-byte aligned and start 4 banks apart
+    A.trace = getenv("B200SLAM_FM_TRACE") ? 1 : 0;
     const size_t smem = fastmatch_smem_bytes(A.nth * A.ntx * A.nty, A.nth, A.nbeams);
     static bool smem_set[64] = {};
     if (!smem_set[ctx->device & 63]) {
