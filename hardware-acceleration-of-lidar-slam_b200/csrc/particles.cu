@@ -122,6 +122,31 @@ __host__ __device__ inline unsigned long long u_offset(unsigned long long Wd, un
     return (Wd >> 32) * u0_q32 + (((Wd & 0xffffffffull) * u0_q32) >> 32);
 }
 
+// slots_below for a whole CTA: every thread tests one k per round (the predicate T_k < c is monotone in k), so the
+// range shrinks by blockDim.x per round -- two rounds for a million slots, one 64-bit division per thread and round,
+// where one thread's binary search is ~40 dependent 64-bit divisions (10 us).  All threads call it and get the
+// same answer.
+__device__ long long slots_below_cta(unsigned long long c, unsigned long long U, unsigned long long Wd,
+                                     unsigned long long Wm, long long N)
+{
+    long long lo = 0, hi = N;                       // the answer lies in [lo, hi]
+    while (hi > lo) {
+        const long long step = (hi - lo + blockDim.x - 1) / blockDim.x;
+        const long long k = lo + (long long)threadIdx.x * step;
+        bool p = false;
+        if (k < hi) p = U + (unsigned long long)k * Wd + ((unsigned long long)k * Wm) / (unsigned long long)N < c;
+        const int cnt = __syncthreads_count(p);     // the true samples are a prefix
+        if (cnt == 0) {
+            hi = lo;
+        } else {
+            const long long last_true = lo + (long long)(cnt - 1) * step;
+            lo = last_true + 1;
+            hi = last_true + step < hi ? last_true + step : hi;
+        }
+    }
+    return lo;
+}
+
 // Exclusive scan of the per-CTA sums (one CTA); total -> out[PF_WLOCAL].
 // Sharded resident set (X.peers != nullptr): second exchange of the filter step.  This rank's integer
 // weight sum goes to every rank as exchange number match->epoch + 1; when every rank's sum (and the
@@ -176,6 +201,7 @@ block_sums_scan_kernel(unsigned long long *__restrict__ block_sums, int nb,
         Nr[threadIdx.x] = ok ? n : 0u;
     }
     __syncthreads();
+    __shared__ unsigned long long sWg, sOff, sNg;
     if (threadIdx.x == 0) {
         unsigned long long Wg = 0, off = 0, Ng = 0;
         for (int r = 0; r < X.nranks; ++r) {
@@ -185,12 +211,17 @@ block_sums_scan_kernel(unsigned long long *__restrict__ block_sums, int nb,
             Ng += Nr[r];
         }
         out[PF_SLOT_BASE + X.nranks] = Ng;
-        long long kb = 0, ke = 0;
-        if (Wg > 0 && Ng > 0) {
-            const unsigned long long Wd = Wg / Ng, Wm = Wg % Ng, U = u_offset(Wd, u0_q32);
-            kb = slots_below(off, U, Wd, Wm, (long long)Ng);
-            ke = slots_below(off + Wl, U, Wd, Wm, (long long)Ng);
-        }
+        sWg = Wg; sOff = off; sNg = Ng;
+    }
+    __syncthreads();
+    const unsigned long long Wg = sWg, off = sOff, Ng = sNg;
+    long long kb = 0, ke = 0;
+    if (Wg > 0 && Ng > 0) {                          // uniform across the CTA
+        const unsigned long long Wd = Wg / Ng, Wm = Wg % Ng, U = u_offset(Wd, u0_q32);
+        kb = slots_below_cta(off, U, Wd, Wm, (long long)Ng);
+        ke = slots_below_cta(off + Wl, U, Wd, Wm, (long long)Ng);
+    }
+    if (threadIdx.x == 0) {
         out[PF_WGLOBAL] = Wg; out[PF_RANK_OFFSET] = off; out[PF_NGLOBAL] = Ng;
         out[PF_KBEGIN] = (unsigned long long)kb; out[PF_KCOUNT] = (unsigned long long)(ke - kb);
         match->epoch = e2; match->posted = e2; match->collected = e2;

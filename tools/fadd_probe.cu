@@ -2,6 +2,35 @@
 // (development probe for fastmatch_kernel's phase 2)   nvcc -arch=sm_100a -O3 -o tools/build/fadd_probe tools/fadd_probe.cu
 #include <cstdio>
 #include <cuda_runtime.h>
+struct Big { float v[960]; };
+// probe2: the same loop in fastmatch_kernel's clothes -- __launch_bounds__(1024, 1), a 4 KB parameter block, the
+// programmatic-dependent-launch instructions, register pressure
+__global__ void __launch_bounds__(1024, 1) probe2(float *out, long long *cyc, int n, int nbp, const __grid_constant__ Big T)
+{
+    extern __shared__ __align__(16) float vals[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int i = threadIdx.x; i < 32 * nbp; i += blockDim.x) vals[i] = 1.0f + (i % 7) * 0.125f + T.v[i % 960];
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x < 27) {
+        const float *v = vals + threadIdx.x * nbp;
+        long long t0 = clock64();
+        float s = 0.f;
+        int i = 0;
+        float4 a = *reinterpret_cast<const float4 *>(v), b = *reinterpret_cast<const float4 *>(v + 4);
+        for (; i + 16 <= n; i += 8) {
+            const float4 na = *reinterpret_cast<const float4 *>(v + i + 8), nb = *reinterpret_cast<const float4 *>(v + i + 12);
+            s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
+            s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
+            a = na; b = nb;
+        }
+        long long t1 = clock64();
+        out[threadIdx.x] = s;
+        if (threadIdx.x == 0) cyc[0] = t1 - t0;
+    }
+    __syncthreads();
+}
+
 __global__ void probe(float *out, long long *cyc, int n, int nbp, int mode, int nthreads_active)
 {
     extern __shared__ __align__(16) float vals[];
@@ -48,6 +77,22 @@ int main()
                 for (int rep = 0; rep < 2; ++rep) { probe<<<1, threads, 32 * nbp * 4>>>(out, cyc, n, nbp, mode, active); cudaDeviceSynchronize(); }
                 printf("block %4d threads, %2d summing, mode %d: %lld cycles = %.1f per add\n", threads, active, mode, cyc[0], (double)cyc[0] / n);
             }
+    {
+        Big T = {};
+        cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int pdl = 0; pdl < 2; ++pdl)
+            for (int rep = 0; rep < 3; ++rep) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 32 * nbp * 4;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = pdl;
+                cudaLaunchKernelEx(&cfg, probe2, out, cyc, n, nbp, T);
+                cudaDeviceSynchronize();
+                printf("probe2 (1024 threads, launch bounds, 4 KB params, griddepcontrol, pdl attr %d): %lld cycles = %.1f per add\n", pdl, cyc[0], (double)cyc[0] / n);
+            }
+    }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
