@@ -31,6 +31,39 @@ __global__ void __launch_bounds__(1024, 1) probe2(float *out, long long *cyc, in
     __syncthreads();
 }
 
+// probe3: probe2 with ~60 live registers per thread (the register file of the SM completely allocated, as in
+// fastmatch_kernel) and phase-1-like traffic before the loop
+__global__ void __launch_bounds__(1024, 1) probe3(float *out, long long *cyc, int n, int nbp, const float *g, int stride)
+{
+    extern __shared__ __align__(16) float vals[];
+    float keep[40];
+#pragma unroll
+    for (int q = 0; q < 40; ++q) keep[q] = g[(threadIdx.x * 40 + q) * stride];
+    for (int i = threadIdx.x; i < 32 * nbp; i += blockDim.x) vals[i] = 1.0f + (i % 7) * 0.125f + __ldg(g + (i * 37) % 4096);
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        const float *v = vals + threadIdx.x * nbp;
+        long long t0 = clock64();
+        float s = 0.f;
+        int i = 0;
+        float4 a = *reinterpret_cast<const float4 *>(v), b = *reinterpret_cast<const float4 *>(v + 4);
+        for (; i + 16 <= n; i += 8) {
+            const float4 na = *reinterpret_cast<const float4 *>(v + i + 8), nb = *reinterpret_cast<const float4 *>(v + i + 12);
+            s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
+            s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
+            a = na; b = nb;
+        }
+        long long t1 = clock64();
+        out[threadIdx.x] = s;
+        if (threadIdx.x == 0) cyc[0] = t1 - t0;
+    }
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 40; ++q) acc += keep[q];
+    out[1024 + threadIdx.x] = acc;
+}
+
 __global__ void probe(float *out, long long *cyc, int n, int nbp, int mode, int nthreads_active)
 {
     extern __shared__ __align__(16) float vals[];
@@ -92,6 +125,16 @@ int main()
                 cudaDeviceSynchronize();
                 printf("probe2 (1024 threads, launch bounds, 4 KB params, griddepcontrol, pdl attr %d): %lld cycles = %.1f per add\n", pdl, cyc[0], (double)cyc[0] / n);
             }
+    }
+    {
+        float *g; cudaMalloc(&g, 1 << 22); cudaMemset(g, 0, 1 << 22);
+        float *out3; cudaMalloc(&out3, 16384);
+        cudaFuncSetAttribute(probe3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int rep = 0; rep < 3; ++rep) {
+            probe3<<<1, 1024, 32 * nbp * 4>>>(out3, cyc, n, nbp, g, 1);
+            cudaDeviceSynchronize();
+            printf("probe3 (64 registers per thread, register file full): %lld cycles = %.1f per add\n", cyc[0], (double)cyc[0] / n);
+        }
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
