@@ -848,25 +848,40 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
 }
 
 
-// ---- FastMatch-sized lattices: one CTA, gathers across all threads, sums in reference order ------------------
+// ---- FastMatch-sized lattices: one thread-block cluster, one CTA per theta, sums in reference order -----------
 // The reference's own call -- 27 candidates x <= 1079 beams (main.c:381-596) -- is 29 000 evaluations: a latency
 // problem, not a throughput one.  The lattice kernel above gives every candidate one thread that gathers AND adds
-// (27 live threads, ~45 us).  Here the two are split (hard part 2: the north_star's "beams
-// across lanes", with the exactness of design A kept):
-//   phase 1  all 1024 threads: work item = (beam, theta): rotate once, n_tx column and n_ty row indices, the
-//            n_tx * n_ty gathers -> vals[candidate][beam] in shared memory (+0.0f for an out-of-bounds beam, which
-//            leaves a non-negative sum unchanged) and one in-bounds bit mask per item;
-//   phase 2  thread c < n_candidates adds vals[c][0 .. nbeams) SEQUENTIALLY in beam order (main.c:516) -- the
-//            same additions in the same order as the reference, so the score is bit-identical -- and counts hits;
-//   phase 3  arg-min by warp shuffle on the packed (score, index) key; then bestHits[] exactly as the
-//            reference's loop leaves it (main.c:515: every candidate overwrites the array from index 0, so behind
-//            the last candidate's hits it holds those of the most recent candidate that had more): one warp per
-//            candidate that still owns entries compacts its in-bounds values out of shared memory by ballot.
-// No inter-CTA protocol, no atomics, no second pass over the field.  Measured in the 3480-scan replay: the
-// FastMatch + FastMatch2 pair went from ~95 us to ~?? us of GPU time per scan.
+// (27 live threads, ~45 us).  Here the work is split three ways (hard part 2: the north_star's
+// "beams across lanes", with the exactness of design A kept):
+//   CTAs     a cluster of min(n_theta, 8) CTAs; CTA r owns the candidates of theta r, r + C, ...  A divergent gather
+//            costs the SM's L1 about two cycles per 128-byte line touched, ~8 lines per warp-load for neighbouring
+//            beams: 27 candidates on one SM are bound by that (measured ~10 000 cycles), three SMs take a third each;
+//   gather   the warps not on warp 0's scheduler; work item = (32-beam chunk, theta), chunks in scan order: rotate
+//            once, n_tx column and n_ty row indices, the n_tx * n_ty loads -> vals[candidate][beam] in shared
+//            memory (+0.0f for an out-of-bounds or padding beam, which leaves a non-negative sum unchanged), one
+//            ballot per candidate -> in-bounds bit mask of the chunk, then the chunk's progress counter.
+//            For the reference's 3 x 3 translations the loops are compile-time and the 9 loads in flight together;
+//   sums     warp 0, one thread per candidate of the CTA, follows the gather chunk by chunk (a progress counter per chunk) and
+//            adds vals[c][0 .. nbeams) SEQUENTIALLY in beam order (main.c:516) -- the same additions in the same
+//            order as the reference, so the score is bit-identical.  One dependent FADD per beam (4 cycles) is the
+//            floor of the kernel; warp 0 has its scheduler to itself so that nothing else delays the chain;
+//   hits     the gather warps, after their last chunk: hits in front of every chunk (warp scan of the mask
+//            popcounts) and per candidate;
+//   exchange every CTA stores its candidates' hit counts and its best (score, index) key into the shared memory of
+//            all CTAs (DSMEM), one cluster barrier; then each CTA knows the winner (arg-min: lowest score, then
+//            lowest index) and all counts, and writes its share of bestHits[] exactly as the reference's loop leaves
+//            it (main.c:515: every candidate overwrites the array from index 0, so behind the last candidate's hits
+//            it holds those of the most recent candidate that had more -- a "staircase" of suffix maxima over the
+//            counts): every (stair, chunk) pair is an independent compaction out of shared memory.
+// No atomics, no second pass over the field, no global-memory protocol between the CTAs.
 constexpr int FM_THREADS = 1024;
+constexpr int FM_WARPS = FM_THREADS / 32;
+constexpr int FM_GATHER_WARPS = FM_WARPS - FM_WARPS / 4;   // warps 4, 8, ... share warp 0's scheduler and stay idle
 constexpr int FM_MAX_CAND = 32;
-constexpr int FM_MAX_BEAMS = 1536;             // vals: 27..32 x (1536 + 4) floats <= 197 KB of shared memory
+constexpr int FM_MAX_CLUSTER = 8;              // portable cluster size
+constexpr int FM_MAX_BEAMS = 1536;
+constexpr int FM_MAX_CHUNKS = FM_MAX_BEAMS / 32;
+constexpr int FM_GROUP = 4;                    // chunks the summing warp takes at a time; scans are padded to whole groups
 constexpr int FM_TAB_B = 128;                  // offset of the second pass's tables in the parameter block
 
 struct FmMap {
@@ -902,30 +917,175 @@ struct FmArgs {
     int trace;                // diagnostics (B200SLAM_FM_TRACE): SM cycle counter at the phase boundaries -> host_result->trace
 };
 
+inline int fastmatch_cluster_size(int nth) { return nth < FM_MAX_CLUSTER ? nth : FM_MAX_CLUSTER; }
+
+// Progress counters in shared memory, one per group of FM_GROUP chunks: gather warps add one per (chunk, theta) item
+// behind their stores, the summing warp polls before it starts on a group.
+__device__ __forceinline__ void fm_group_done(unsigned int *counter)
+{
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" :: "r"((unsigned int)__cvta_generic_to_shared(counter)) : "memory");
+}
+__device__ __forceinline__ unsigned int fm_group_progress(const unsigned int *counter)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"((unsigned int)__cvta_generic_to_shared(counter)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fm_gather_barrier()               // the gather warps of one CTA among themselves
+{
+    asm volatile("bar.sync 1, %0;" :: "n"(FM_GATHER_WARPS * 32) : "memory");
+}
+__device__ __forceinline__ unsigned int fm_cluster_rank()
+{
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned int fm_cluster_size()
+{
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// address of this CTA's shared-memory object `p` in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned int fm_peer_smem(const void *p, unsigned int rank)
+{
+    unsigned int a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"((unsigned int)__cvta_generic_to_shared(p)), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void fm_cluster_sync()                 // releases the DSMEM stores in front of it
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// cell of (int)roundf(v) when the 1-based index passes `1 < S < n` (main.c:512), else a value so negative that
+// its sum with any valid offset stays negative
+__device__ __forceinline__ int cell_or_invalid(float v, int n_minus_2)
+{
+    const int r = round_cell(v);
+    return ((unsigned)(r - 1) < (unsigned)n_minus_2) ? r : INVALID_OFF;
+}
+
+// What a CTA of the cluster owns: thetas rank, rank + C, ...; its l-th theta's candidates are local l * per_th + q.
+struct FmShare {
+    int rank, C, nth_loc, nloc, per_th;
+    __device__ __forceinline__ int owner(int c) const { return (c / per_th) % C; }
+    __device__ __forceinline__ int local(int c) const { return (c / per_th) / C * per_th + c % per_th; }
+    __device__ __forceinline__ int global(int lc) const { return ((lc / per_th) * C + rank) * per_th + lc % per_th; }
+};
+
+// The gathers of one pass by gather warp g.  NX, NY > 0: translation counts known at compile time.
+template <int NX, int NY>
+__device__ __forceinline__ void fm_gather(const FmArgs &A, const FmMap &M, const FmShare &S, int nbeams, int nchunk, const float *tab_s,
+                                          const float2 *ps_s, float *vals, unsigned int *balm, unsigned int *group_done, int g, int lane)
+{
+    const int ntx = NX > 0 ? NX : A.ntx, nty = NY > 0 ? NY : A.nty;
+    const float *field = M.field;
+    const int pitch = M.pitch, cols2 = M.cols - 2, rows2 = M.rows - 2, nbp = A.nbp;
+    constexpr int NXA = NX > 0 ? NX : 1, NYA = NY > 0 ? NY : 1;
+    [[maybe_unused]] float sxt[NXA], syt[NYA];
+    if constexpr (NX > 0 && NY > 0) {
+#pragma unroll
+        for (int k = 0; k < NX; ++k) sxt[k] = tab_s[2 * FM_MAX_CAND + k];
+#pragma unroll
+        for (int k = 0; k < NY; ++k) syt[k] = tab_s[3 * FM_MAX_CAND + k];
+    }
+    // work items (chunk k, local theta l) in chunk order, FM_GATHER_WARPS apart
+    const int dk = FM_GATHER_WARPS / S.nth_loc, dl = FM_GATHER_WARPS - dk * S.nth_loc;
+    int k = g / S.nth_loc, l = g - k * S.nth_loc;
+    for (; k < nchunk; k += dk, l += dl) {
+        if (l >= S.nth_loc) { l -= S.nth_loc; if (++k >= nchunk) break; }
+        const int i = (k << 5) + lane, j = l * S.C + S.rank;
+        const float ct = tab_s[j], st = tab_s[FM_MAX_CAND + j];
+        const float2 ps = ps_s[i];
+        const float Sx = rot_x(ps.x, ps.y, ct, st), Sy = rot_y(ps.x, ps.y, ct, st);                     // main.c:462-463
+        float *dst = vals + (size_t)l * S.per_th * nbp + i;
+        unsigned int *bm = balm + k * S.nloc + l * S.per_th;
+        const bool beam = i < nbeams;                                                                   // else padding of the last group
+        if constexpr (NX > 0 && NY > 0) {
+            int c[NX], ro[NY];
+#pragma unroll
+            for (int kx = 0; kx < NX; ++kx) {
+                c[kx] = cell_or_invalid(__fadd_rn(Sx, sxt[kx]), cols2);                                 // main.c:483
+                if (!beam) c[kx] = INVALID_OFF;
+            }
+#pragma unroll
+            for (int ky = 0; ky < NY; ++ky) {
+                const int r = cell_or_invalid(__fadd_rn(Sy, syt[ky]), rows2);                           // main.c:501
+                ro[ky] = r < 0 ? INVALID_OFF : r * pitch;
+            }
+            float v[NX * NY];
+            unsigned int bal[NX * NY];
+#pragma unroll
+            for (int kx = 0; kx < NX; ++kx)
+#pragma unroll
+                for (int ky = 0; ky < NY; ++ky) {
+                    const int idx = max(ro[ky] + c[kx], -1);                                            // either invalid: field[-1] == +0.0f
+                    v[kx * NY + ky] = __ldg(field + idx);
+                    bal[kx * NY + ky] = __ballot_sync(0xffffffffu, idx >= 0);                           // main.c:512
+                }
+#pragma unroll
+            for (int q = 0; q < NX * NY; ++q) dst[q * nbp] = v[q];
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < NX * NY; ++q) bm[q] = bal[q];
+            }
+        } else {
+            for (int kx = 0; kx < ntx; ++kx) {
+                int c = cell_or_invalid(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), cols2);             // main.c:483
+                if (!beam) c = INVALID_OFF;
+                for (int ky = 0; ky < nty; ++ky) {
+                    const int r = cell_or_invalid(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), rows2);   // main.c:501
+                    const int idx = max((r < 0 ? INVALID_OFF : r * pitch) + c, -1);
+                    const int q = kx * nty + ky;
+                    dst[q * nbp] = __ldg(field + idx);
+                    const unsigned int bal = __ballot_sync(0xffffffffu, idx >= 0);                      // main.c:512
+                    if (lane == 0) bm[q] = bal;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) fm_group_done(group_done + k / FM_GROUP);
+    }
+}
+
 __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_constant__ FmArgs A, const __grid_constant__ LatticeTables T)
 {
     extern __shared__ __align__(16) unsigned char fm_smem[];
-    float *vals = reinterpret_cast<float *>(fm_smem);                                 // [ncand][nbp]
-    const int ncand = A.nth * A.ntx * A.nty, per_th = A.ntx * A.nty;
-    unsigned int *inb = reinterpret_cast<unsigned int *>(vals + (size_t)ncand * A.nbp);   // [nth][nbp]: bit (itx * nty + ity)
-    float2 *ps_s = reinterpret_cast<float2 *>(inb + (size_t)A.nth * A.nbp);              // [nbp]: the scan in pixels
+    const int ncand = A.nth * A.ntx * A.nty;
+    FmShare S;
+    S.rank = (int)fm_cluster_rank(); S.C = (int)fm_cluster_size(); S.per_th = A.ntx * A.nty;
+    S.nth_loc = (A.nth - S.rank + S.C - 1) / S.C; S.nloc = S.nth_loc * S.per_th;
+    const int nloc_cap = (A.nth + S.C - 1) / S.C * S.per_th;                           // the same carve-up in every CTA
+    const int chunk_cap = A.nbp >> 5;                                                  // 32-beam chunks per scan, upper bound
+    float *vals = reinterpret_cast<float *>(fm_smem);                                 // [nloc][nbp]
+    float2 *raw_s = reinterpret_cast<float2 *>(vals + (size_t)nloc_cap * A.nbp);        // [nbp]: the scan
+    float2 *ps_s = raw_s + A.nbp;                                                      // [nbp]: the scan in pixels of this pass's map
+    unsigned int *balm = reinterpret_cast<unsigned int *>(ps_s + A.nbp);               // [chunk][nloc]: in-bounds beams of a chunk
+    int *pre = reinterpret_cast<int *>(balm + nloc_cap * chunk_cap);                   // [nloc][chunk_cap]: hits in front of a chunk
+    __shared__ unsigned int group_done[FM_MAX_CHUNKS / FM_GROUP];                      // (chunk, theta) items of a group gathered so far, over the passes
+    __shared__ __align__(8) unsigned long long xkey_s[2][FM_MAX_CLUSTER];              // per pass parity: best key of every CTA
+    __shared__ int xcnt_s[2][FM_MAX_CAND];                                             // per pass parity: hits of every candidate
     __shared__ float tab_s[4 * FM_MAX_CAND];
-    __shared__ int cnt_s[FM_MAX_CAND];
-    __shared__ int stair_c[FM_MAX_CAND], stair_lo[FM_MAX_CAND];
-    __shared__ int nstair_s, nscan_s;
-    __shared__ int wcount_s[FM_THREADS / 32];
-    __shared__ unsigned long long key_s;
+    __shared__ int nscan_s;
+    __shared__ int wcount_s[FM_WARPS];
+    __shared__ long long trace_s[16];             // kept on chip while the kernel runs: a store to host memory per phase would perturb it
 
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool lead = S.rank == 0;
     int ntrace = 0;
-#define FM_TRACE() do { if (A.trace && A.host_result && tid == 0 && ntrace < 16) A.host_result->trace[ntrace++] = clock64(); } while (0)
+#define FM_TRACE() do { if (A.trace && lead && tid == 0 && ntrace < 12) trace_s[ntrace++] = clock64(); } while (0)
     FM_TRACE();
+    if (tid < FM_MAX_CHUNKS / FM_GROUP) group_done[tid] = 0;
+    // Everything this kernel reads (scan, beam count, match state) and writes (bestHits[] twin, match state) may
+    // belong to the kernel in front until it has completed; being resident already saves the launch latency.
+    pdl_wait_prior_grids();
     int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
     if (A.ranges) {
         // ---- readAScan (main.c:71-95): drop r < range_min | r > max_range, x = r cos, y = r sin, compacted in
-        // beam order (the same arithmetic as scan_read_kernel, frontend.cu) -----------------------------------
-        pdl_wait_prior_grids();                       // the scan buffers belong to the kernels in front
+        // beam order (the same arithmetic as scan_read_kernel, frontend.cu); every CTA for itself, the first one
+        // for the kernels behind -------------------------------------------------------------------------------
         const float maxr = (float)A.max_range;
         int base = 0;
         for (int i0 = 0; i0 < A.lidar_n; i0 += FM_THREADS) {
@@ -942,161 +1102,152 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             __syncthreads();
             int before = 0, total = 0;
 #pragma unroll 8
-            for (int w = 0; w < FM_THREADS / 32; ++w) {
+            for (int w = 0; w < FM_WARPS; ++w) {
                 const int c = wcount_s[w];
                 before += w < warp ? c : 0;
                 total += c;
             }
             if (keep) {
                 const int slot = base + before + __popc(m & ((1u << lane) - 1u));
-                A.scan_x_out[slot] = __fmul_rn(r, A.cos_a[i]);                        // main.c:90
-                A.scan_y_out[slot] = __fmul_rn(r, A.sin_a[i]);                        // main.c:91
+                const float x = __fmul_rn(r, A.cos_a[i]), y = __fmul_rn(r, A.sin_a[i]);   // main.c:90-91
+                raw_s[slot] = make_float2(x, y);
+                if (lead) { A.scan_x_out[slot] = x; A.scan_y_out[slot] = y; }
             }
             base += total;
         }
-        if (tid == 0) { A.front->count = base; A.front->scan_n = base; nscan_s = base; }
-        __threadfence_block();
-        __syncthreads();                              // the scan just written is read below through global memory
+        if (tid == 0) {
+            nscan_s = base;
+            if (lead) { A.front->count = base; A.front->scan_n = base; }
+        }
+        __syncthreads();
         nbeams = nscan_s;
+    } else {
+        for (int i = tid; i < nbeams; i += FM_THREADS) raw_s[i] = make_float2(A.scan_x[i], A.scan_y[i]);
     }
+    const int nchunk = (nbeams + 31) >> 5;                                            // 32-beam chunks with beams in them
+    const int ngroup = (nchunk + FM_GROUP - 1) / FM_GROUP, nchunk_pad = ngroup * FM_GROUP;   // gathered and added: whole groups
     FM_TRACE();
 
     unsigned long long seed = ~0ull, key = ~0ull;
     int bh = 0, lh = 0, written = 0;
     for (int pass = 0; pass < A.npass; ++pass) {
         const FmMap M = A.map[pass];
-        // ---- axis tables of this pass ------------------------------------------------------------------------
+        const int par = pass & 1;
+        // ---- axis tables of this pass and the scan in pixels ---------------------------------------------------
         {
             const float *ctT = T.v, *stT = T.v + A.nth, *sxtT = T.v + 2 * A.nth, *sytT = sxtT + A.ntx;
             if (pass == 1 || A.seeded0) {
                 // centred on the winner of the match in front (main.c:909-918): the host sent the axis tables of all
                 // three possible centres per axis; see lattice_kernel
                 const float *tb = T.v + (pass == 1 ? FM_TAB_B : 0);
-                if (pass == 0) {
-                    pdl_wait_prior_grids();
-                    seed = *reinterpret_cast<volatile unsigned long long *>(&A.match->key);
-                } else {
-                    seed = key;
-                }
+                seed = pass == 0 ? *reinterpret_cast<volatile unsigned long long *>(&A.match->key) : key;
                 const int lin1 = seed == ~0ull ? 13 : (int)(seed & 0xffffffffull);
                 const int ith1 = lin1 / 9, itx1 = (lin1 / 3) % 3, ity1 = lin1 % 3;
                 ctT = tb + 3 * ith1; stT = tb + 9 + 3 * ith1; sxtT = tb + 18 + 3 * itx1; sytT = tb + 27 + 3 * ity1;
             }
-            __syncthreads();                          // tab_s / cnt_s / vals of the previous pass are done with
+            __syncthreads();                          // raw_s filled; vals / balm / pre / tab_s of the previous pass done with
             if (tid < A.nth) { tab_s[tid] = ctT[tid]; tab_s[FM_MAX_CAND + tid] = stT[tid]; }
             if (tid < A.ntx) tab_s[2 * FM_MAX_CAND + tid] = sxtT[tid];
             if (tid < A.nty) tab_s[3 * FM_MAX_CAND + tid] = sytT[tid];
+            for (int i = tid; i < (nchunk_pad << 5); i += FM_THREADS) {
+                const float2 p = i < nbeams ? raw_s[i] : make_float2(0.0f, 0.0f);                    // padding of the last group: any finite value
+                ps_s[i] = make_float2(__fmul_rn(p.x, M.ipixel), __fmul_rn(p.y, M.ipixel));           // main.c:418-419
+            }
             __syncthreads();
         }
-        // ---- phase 1: every (beam, theta) item: rotation, cell indices, gathers.  The scaled scan goes through
-        // shared memory once per pass, the items are dealt out flat (3 x 1079 items = 3.2 per thread, not 6 for
-        // the threads that own a second beam), and the loop is unrolled so that the gathers of a thread's items
-        // are all in flight together: the phase costs about one L2 round trip.
-        const float *sx_src = A.ranges ? A.scan_x_out : A.scan_x, *sy_src = A.ranges ? A.scan_y_out : A.scan_y;
-        for (int i = tid; i < nbeams; i += FM_THREADS)
-            ps_s[i] = make_float2(__fmul_rn(sx_src[i], M.ipixel), __fmul_rn(sy_src[i], M.ipixel));      // main.c:418-419
-        __syncthreads();
-        const int nitems = nbeams * A.nth;
-#pragma unroll 4
-        for (int item = tid; item < nitems; item += FM_THREADS) {
-            const int j = item / nbeams, i = item - j * nbeams;
-            const float ct = tab_s[j], st = tab_s[FM_MAX_CAND + j];
-            const float2 ps = ps_s[i];
-            const float Sx = rot_x(ps.x, ps.y, ct, st), Sy = rot_y(ps.x, ps.y, ct, st);                 // main.c:462-463
-            unsigned int mask = 0;
-            for (int kx = 0; kx < A.ntx; ++kx) {
-                const int c = cell_index(__fadd_rn(Sx, tab_s[2 * FM_MAX_CAND + kx]), M.cols);          // main.c:483
-                for (int ky = 0; ky < A.nty; ++ky) {
-                    const int r = cell_index(__fadd_rn(Sy, tab_s[3 * FM_MAX_CAND + ky]), M.rows);      // main.c:501
-                    const bool in = c >= 0 && r >= 0;                                                  // main.c:512
-                    vals[(size_t)(j * per_th + kx * A.nty + ky) * A.nbp + i] = __ldg(M.field + (in ? r * M.pitch + c : -1));
-                    mask |= (unsigned int)in << (kx * A.nty + ky);
-                }
-            }
-            inb[j * A.nbp + i] = mask;
-        }
-        __syncthreads();
         FM_TRACE();
 
-        // ---- phase 2: warp 0 -- one thread per candidate, beams in scan order (main.c:516), 8 per iteration with
-        // the next 8 already loaded; meanwhile warp c + 1 counts candidate c's in-bounds beams (main.c:515-516) ----
-        key = ~0ull;
         if (warp == 0) {
-            if (tid < ncand) {
-                const float *v = vals + (size_t)tid * A.nbp;                          // 16-byte aligned: nbp % 4 == 0
-                float s = 0.0f;                                                       // main.c:507
-                int i = 0;
-                if (nbeams >= 8) {
-                    float4 a = *reinterpret_cast<const float4 *>(v), b = *reinterpret_cast<const float4 *>(v + 4);
-                    for (; i + 16 <= nbeams; i += 8) {
-                        const float4 na = *reinterpret_cast<const float4 *>(v + i + 8), nb = *reinterpret_cast<const float4 *>(v + i + 12);
-                        s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
-                        s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
-                        a = na; b = nb;
-                    }
-                    s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
-                    s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
-                    i += 8;
-                }
-                for (; i < nbeams; ++i) s = __fadd_rn(s, v[i]);
-                key = pack_key(s, (unsigned int)tid);
-            }
-            FM_TRACE();
-        } else {
-            for (int c = warp - 1; c < ncand; c += FM_THREADS / 32 - 1) {
-                const unsigned int *m = inb + (c / per_th) * A.nbp;
-                const int bit = c % per_th;
-                int n = 0;
-                for (int i = lane; i < nbeams; i += 32) n += (m[i] >> bit) & 1u;
+            // ---- sums: one thread per candidate of this CTA, beams in scan order (main.c:516), chunk by chunk behind
+            // the gather; half a chunk ahead in registers ----------------------------------------------------------
+            const float4 *v = reinterpret_cast<const float4 *>(vals + (size_t)(lane < S.nloc ? lane : 0) * A.nbp);   // 16-byte aligned: nbp % 4 == 0
+            float s = 0.0f;                                                           // main.c:507
+            unsigned int spins = 0;
+            const unsigned int target = (unsigned int)(FM_GROUP * S.nth_loc * (pass + 1));   // the counters run on over the passes
+            for (int gq = 0; gq < ngroup; ++gq) {
+                // the only branch on the chain: once per FM_GROUP chunks; the adds of a group are straight-line code
+                // with its loads spread between them (a dependent FADD issues every 4 cycles, 3 slots are free)
+                while (fm_group_progress(group_done + gq) < target)
+                    if (++spins > (1u << 24)) { spins = ~0u - (1u << 25); break; }
+                const float4 *p = v + gq * (FM_GROUP * 8);
 #pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) n += __shfl_xor_sync(0xffffffffu, n, sft);
-                if (lane == 0) cnt_s[c] = n;
-            }
-        }
-        // ---- phase 3: arg-min (lowest score, then lowest index: strict `<` in loop order, main.c:549) -----------
-        if (warp == 0) {
-            key = warp_min_u64(key);
-            if (lane == 0) key_s = key;
-        }
-        __syncthreads();
-        FM_TRACE();
-        key = key_s;
-        // The match state and the bestHits[] twin belong to the kernel in front until it has completed.
-        pdl_wait_prior_grids();
-        if (tid == 0) {
-            // main.c:515: walk the candidates backwards; each one longer than what has been written so far supplies
-            // the entries it alone still owns
-            int ns = 0, w = 0;
-            for (int c = ncand - 1; c >= 0; --c)
-                if (c == ncand - 1 || cnt_s[c] > w) {
-                    stair_c[ns] = c; stair_lo[ns] = c == ncand - 1 ? 0 : w; ++ns;
-                    w = cnt_s[c];
+                for (int q = 0; q < FM_GROUP * 8; ++q) {
+                    const float4 x = p[q];
+                    s = __fadd_rn(s, x.x); s = __fadd_rn(s, x.y); s = __fadd_rn(s, x.z); s = __fadd_rn(s, x.w);
                 }
-            nstair_s = ns;
-        }
-        __syncthreads();
-        for (int e = warp; e < nstair_s; e += FM_THREADS / 32) {
-            const int c = stair_c[e], lo = stair_lo[e];
-            const float *v = vals + (size_t)c * A.nbp;
-            const unsigned int *m = inb + (c / per_th) * A.nbp;
-            const int bit = c % per_th;
-            int run = 0;
-            for (int i0 = 0; i0 < nbeams; i0 += 32) {
-                const int i = i0 + lane;
-                const bool in = i < nbeams && ((m[i] >> bit) & 1u);
-                const unsigned int bal = __ballot_sync(0xffffffffu, in);
-                const int pos = run + __popc(bal & ((1u << lane) - 1u));
-                if (in && pos >= lo) A.hit_values[pos] = v[i];
-                run += __popc(bal);
+            }
+            if (spins > (1u << 24) && lane == 0) atomicOr(&A.match->error, DEV_ERR_BARRIER);   // a gather warp never arrived
+            // ---- this CTA's best (lowest score, then lowest index: strict `<` in loop order, main.c:549) -> every CTA --
+            unsigned long long mine = lane < S.nloc ? pack_key(s, (unsigned int)S.global(lane)) : ~0ull;
+            mine = warp_min_u64(mine);
+            if (lane < S.C)
+                asm volatile("st.shared::cluster.u64 [%0], %1;" :: "r"(fm_peer_smem(&xkey_s[par][S.rank], lane)), "l"(mine) : "memory");
+        } else if ((warp & 3) != 0) {
+            const int g = warp - 1 - (warp >> 2);                                     // 0 .. FM_GATHER_WARPS - 1
+            // ---- gather ---------------------------------------------------------------------------------------------
+            if (A.ntx == 3 && A.nty == 3) fm_gather<3, 3>(A, M, S, nbeams, nchunk_pad, tab_s, ps_s, vals, balm, group_done, g, lane);
+            else fm_gather<0, 0>(A, M, S, nbeams, nchunk_pad, tab_s, ps_s, vals, balm, group_done, g, lane);
+            if (A.trace && lead && lane == 0 && g == 0) trace_s[12 + pass] = clock64();
+            fm_gather_barrier();
+            // ---- hits: per candidate, the in-bounds beams (main.c:512-516) in front of every chunk and in total,
+            // the total to every CTA ---------------------------------------------------------------------------------
+            for (int lc = g; lc < S.nloc; lc += FM_GATHER_WARPS) {
+                int total = 0;
+                for (int k0 = 0; k0 < nchunk; k0 += 32) {
+                    const int k = k0 + lane;
+                    const int x = k < nchunk ? __popc(balm[k * S.nloc + lc]) : 0;
+                    int incl = x;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    if (k < nchunk) pre[lc * chunk_cap + k] = total + incl - x;
+                    total += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane < S.C)
+                    asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(fm_peer_smem(&xcnt_s[par][S.global(lc)], lane)), "r"(total) : "memory");
             }
         }
-        bh = cnt_s[(int)(key & 0xffffffffull)];                                       // bestHits_size: the winner's (main.c:557)
-        lh = cnt_s[ncand - 1];
-        written = 0;
-        for (int e = 0; e < nstair_s; ++e) written = max(written, cnt_s[stair_c[e]]);
+        fm_cluster_sync();
         FM_TRACE();
+        // ---- the winner, and the hit counts of all candidates ------------------------------------------------------
+        key = ~0ull;
+        for (int r = 0; r < S.C; ++r) key = min(key, xkey_s[par][r]);
+        const int cnt = lane < ncand ? xcnt_s[par][lane] : -1;
+        bh = xcnt_s[par][(int)(key & 0xffffffffull)];                                 // bestHits_size: the winner's (main.c:557)
+        lh = xcnt_s[par][ncand - 1];
+        // main.c:515: every candidate overwrites bestHits[] from index 0, so the array ends up holding, behind the last
+        // candidate's hits, those of the most recent candidate that had more.  Candidate c still owns entries
+        // [suffix max of the counts behind it, its own count): lane c works that out by shuffles
+        int sfx = cnt;                                                                // max over lanes >= this one
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_down_sync(0xffffffffu, sfx, d);
+            if (lane + d < 32) sfx = max(sfx, o);
+        }
+        written = __shfl_sync(0xffffffffu, sfx, 0);                                   // the longest candidate
+        if (warp != 0 && (warp & 3) != 0) {
+            const int g = warp - 1 - (warp >> 2);
+            int behind = __shfl_down_sync(0xffffffffu, sfx, 1);                       // max over lanes > this one
+            if (lane == 31) behind = -1;
+            const bool stair = lane < ncand && (lane == ncand - 1 || cnt > behind) && S.owner(lane) == S.rank;
+            const int lo_l = lane == ncand - 1 ? 0 : behind;
+            unsigned int stairs = __ballot_sync(0xffffffffu, stair);                  // this CTA's share
+            while (stairs) {
+                const int c = __ffs(stairs) - 1;
+                stairs &= stairs - 1;
+                const int lo = __shfl_sync(0xffffffffu, lo_l, c), lc = S.local(c);
+                const float *v = vals + (size_t)lc * A.nbp;
+                for (int k = g; k < nchunk; k += FM_GATHER_WARPS) {
+                    const unsigned int bal = balm[k * S.nloc + lc];
+                    const int pos = pre[lc * chunk_cap + k] + __popc(bal & ((1u << lane) - 1u));
+                    if (((bal >> lane) & 1u) && pos >= lo) A.hit_values[pos] = v[(k << 5) + lane];
+                }
+            }
+        }
     }
-    if (tid == 0) {
+    if (lead && tid == 0) {
         A.match->key = key;
         A.match->best_hits = bh;
         A.match->last_hits = lh;
@@ -1110,6 +1261,8 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             h->mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
             h->error = *reinterpret_cast<volatile unsigned int *>(&A.match->error);
             FM_TRACE();
+            if (A.trace)                          // [0, 12): phase boundaries seen by thread 0; [12 + pass]: end of gather warp 0's last chunk
+                for (int i = 0; i < 16; ++i) h->trace[i] = (i < ntrace || (i >= 12 && i < 12 + A.npass)) ? trace_s[i] : 0;
             __threadfence_system();
             h->seq = A.host_seq;
         }
@@ -1117,14 +1270,21 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
 #undef FM_TRACE
 }
 
+// beams per row of vals: whole groups of chunks, + 4 so that rows stay 16-byte aligned and start 4 banks apart
+inline int fastmatch_row_pitch(int nbeams) { return ((nbeams + 32 * FM_GROUP - 1) / (32 * FM_GROUP)) * (32 * FM_GROUP) + 4; }
+
+// dynamic shared memory of one CTA of the cluster
 size_t fastmatch_smem_bytes(int ncand, int nth, int nbeams)
 {
-    return sizeof(float) * (size_t)(ncand + nth + 2) * (((nbeams + 31) & ~31) + 4);
+    const int C = fastmatch_cluster_size(nth), per_th = ncand / nth;
+    const size_t nloc = (size_t)((nth + C - 1) / C) * per_th;
+    const size_t nbp = fastmatch_row_pitch(nbeams);
+    return sizeof(float) * ((nloc + 4) * nbp + 2 * nloc * (nbp >> 5));
 }
 
 int fastmatch_launch_args(b200slam_ctx *ctx, FmArgs &A, const LatticeTables &T)
 {
-    A.nbp = ((A.nbeams + 31) & ~31) + 4;                  // + 4: rows stay 16-byte aligned and start 4 banks apart
+    A.nbp = fastmatch_row_pitch(A.nbeams);
     A.trace = getenv("B200SLAM_FM_TRACE") ? 1 : 0;
     const size_t smem = fastmatch_smem_bytes(A.nth * A.ntx * A.nty, A.nth, A.nbeams);
     static bool smem_set[64] = {};
@@ -1133,15 +1293,17 @@ int fastmatch_launch_args(b200slam_ctx *ctx, FmArgs &A, const LatticeTables &T)
         smem_set[ctx->device & 63] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(1);
+    cfg.gridDim = dim3(fastmatch_cluster_size(A.nth));  // one cluster, one CTA per theta (up to 8)
     cfg.blockDim = dim3(FM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cfg.gridDim.x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (ctx->use_pdl && ctx->prev_launch_was_lattice) ? 1 : 0;
+    cfg.numAttrs = (ctx->use_pdl && ctx->prev_launch_was_lattice) ? 2 : 1;
     CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, fastmatch_kernel, A, T));
     LAUNCH_CHECK(ctx);
     ctx->prev_launch_was_lattice = true;
