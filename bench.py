@@ -30,8 +30,11 @@ Own arm, per rank (one process per GPU; torch.distributed only for barrier / max
   * `roofline` / `rooflines`: per kernel, from back-to-back launches of that kernel alone inside a CUDA
                graph (its in-pipeline duration) -- HBM roofline for the transform, issue-slot roofline for
                the matcher (its gathers are served by L1/L2; the HBM-equivalent figure stays as a note)
-  * `e2e`    : the same step through the host-buffer C ABI calls: H2D of the int32 grid and the scan
-               from pinned memory and D2H of the match result inside the timed region
+  * `e2e`    : the same step through the host-buffer C ABI calls in the reference's own order (main.c:884-918:
+               OccupationalGrid -> euclidean_distance_transform -> FastMatch): H2D of the map's POINTS (what
+               OccupationalGrid takes; rasterised on the device) and the scan from pinned memory, D2H of the
+               match result, all inside the timed region.  `e2e_int32_grid`: the same with the already
+               rasterised int32 grid as the host buffer (4 B per cell: PCIe bound)
   * `cpu_baseline` (rank 0, N == 1): the reference's own EDT2 + FastMatch2 (oracle/_ref) or the oracle
                port on a bounded sample of the same workload
 N > 1: weak scaling -- every rank keeps the per-GPU workload (map replicated, its own block of theta rows
@@ -686,19 +689,87 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
     h2d = cells * 4 + 2 * nbeams * 4 + (2 * n_global[0] + ntx + nty) * 4
     d2h = 16
 
+    # ---- e2e, the reference's own sequence (main.c:884-918): OccupationalGrid from the map's POINTS ->
+    # euclidean_distance_transform -> FastMatch.  The host buffers are the map points (x, y: what the reference's
+    # OccupationalGrid takes) and the scan; 8 bytes per point cross PCIe instead of 4 bytes per cell, the grid is
+    # rasterised on the device.  Two cells at the 3-pixel margin pin the bounding box so that the rasterised
+    # grid is rows x cols again.
+    ptx, pty, occ_pts = [], [], []
+    for i in range(ring):
+        o = np.array(occs[i], copy=True)
+        o[3, 3] = 1
+        o[rows - 4, cols - 4] = 1
+        r_, c_ = np.nonzero(o)
+        px = ctx.pinned_empty((len(r_),), np.float32)
+        py = ctx.pinned_empty((len(r_),), np.float32)
+        px[...] = (float(w["top_left"][0]) + c_ * float(w["pixel"])).astype(np.float32)
+        py[...] = (float(w["top_left"][1]) + r_ * float(w["pixel"])).astype(np.float32)
+        ptx.append(px); pty.append(py)
+        occ_pts.append(o if i == 0 else None)
+    npts = max(len(a) for a in ptx)
+    barrier()
+    expected_pts = None
+    raster_ok = True
+    if rank == 0:
+        ctx.set_match_mode(mod.MATCH_LATENCY)
+        expected_pts = []
+        for i in range(ring):
+            got = maps[i].rasterise(np.array(ptx[i]), np.array(pty[i]), float(w["pixel"]))[:2]
+            raster_ok = raster_ok and got == (rows, cols)
+            if i == 0:
+                raster_ok = raster_ok and bool(np.array_equal(maps[i].download_occupancy(), occ_pts[0]))
+            maps[i].edt(10.0)
+            expected_pts.append(match_tuple(ctx.score_lattice_rows(maps[i], w["pose0"], w["step"], n_global, 0,
+                                                                   n_global[0] * ntx, False)))
+        ctx.set_match_mode(policy)
+    expected_pts = job.bcast(expected_pts)
+    barrier()
+
+    def issue_pts(i, c):
+        m = maps[i % ring]
+        m.rasterise_async(ptx[i % ring], pty[i % ring], float(w["pixel"]), ctx=c)      # H2D points (pinned) + rasterise
+        c._check(c.L.b200slam_map_edt(c.h, m.h, 10.0))
+        c.scan_upload(scan_x, scan_y)                                                  # H2D scan (pinned)
+        c.score_lattice_async(m, w["pose0"], w["step"], n_global, row_b, row_e, 1 if allreduce else 0)
+
+    def run_e2e_pts(n):
+        issue_pts(0, pair[0])
+        for i in range(1, n):
+            issue_pts(i, pair[i & 1])
+            pair[(i - 1) & 1].match_fetch()                    # D2H result of step i-1
+        return pair[(n - 1) & 1].match_fetch()
+
+    KP = max(3, min(K, 50))
+    run_e2e_pts(4)
+    barrier()
+    t0 = time.perf_counter()
+    res = run_e2e_pts(KP)
+    e2e_pts_s = time.perf_counter() - t0
+    checks["e2e_points"] = match_tuple(res)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(KP):
+        issue_pts(i, ctx)
+        res = ctx.match_fetch()
+    e2e_pts_serial_s = time.perf_counter() - t0
+    checks["e2e_points_one_context"] = match_tuple(res)
+    barrier()
+    h2d_pts = 8 * npts + 2 * nbeams * 4 + (2 * n_global[0] + ntx + nty) * 4
+
     # ---- verification: every launch sequence, on every rank, against rank 0's stand-alone winners ----------
     want = {"serial_graph": expected[last_map], "timed_region": expected[last_map],
-            "e2e_one_context": expected[(KE - 1) % ring], "e2e": expected[(KE - 1) % ring]}
+            "e2e_one_context": expected[(KE - 1) % ring], "e2e": expected[(KE - 1) % ring],
+            "e2e_points": expected_pts[(KP - 1) % ring], "e2e_points_one_context": expected_pts[(KP - 1) % ring]}
     mism = {k: (v, want[k]) for k, v in checks.items() if tuple(v) != tuple(want[k])}
     if args.no_allreduce and world > 1:
         mism = {}                                              # diagnostic mode: ranks hold shard-local winners
-    verified = job.all_true(not mism)
+    verified = job.all_true(not mism and raster_ok)
     if mism:
         print(f"[bench] rank {rank}: result mismatch {mism}", file=sys.stderr, flush=True)
 
     # ---- max over ranks ---------------------------------------------------------------
-    e2e_s, edt_ms_avg, lat_ms_avg, e2e_serial_s, lat_ms_latency_mode = job.max_over_ranks(
-        [e2e_s, edt_ms_avg, lat_ms_avg, e2e_serial_s, lat_ms_latency_mode])
+    e2e_s, edt_ms_avg, lat_ms_avg, e2e_serial_s, lat_ms_latency_mode, e2e_pts_s, e2e_pts_serial_s = job.max_over_ranks(
+        [e2e_s, edt_ms_avg, lat_ms_avg, e2e_serial_s, lat_ms_latency_mode, e2e_pts_s, e2e_pts_serial_s])
 
     if rank == 0:
         ms_per_step = med_ms / K
@@ -761,16 +832,29 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
             "edt_mcells_per_s": cells / (edt_ms * 1e-3) / 1e6,
             "match_evals_per_s_per_gpu": evals_per_rank / (lat_ms * 1e-3),
             "roofline": roofline, "rooflines": roofs,
-            "e2e": {"value": total_evals / (e2e_s / KE), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / KE * 1e3, "steps": KE,
+            "e2e": {"value": total_evals / (e2e_pts_s / KP), "unit": UNIT, "h2d_bytes_per_step": h2d_pts,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_pts_s / KP * 1e3, "steps": KP,
+                    "host_buffers": f"the map's {npts} points (x, y f32: what the reference's OccupationalGrid takes, "
+                                    "main.c:271) + the scan, page-locked; result read back every step",
+                    "calls": "b200slam_map_rasterise_async -> b200slam_map_edt -> b200slam_scan_upload -> "
+                             "b200slam_score_lattice_async -> b200slam_match_fetch  (the reference's OccupationalGrid -> "
+                             "euclidean_distance_transform -> FastMatch, main.c:884-918)",
                     "how": "two contexts alternate: the next step's H2D runs under this step's kernels and result D2H",
-                    "one_context_ms_per_step": e2e_serial_s / KE * 1e3},
+                    "one_context_ms_per_step": e2e_pts_serial_s / KP * 1e3},
+            "e2e_int32_grid": {"value": total_evals / (e2e_s / KE), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / KE * 1e3, "steps": KE,
+                               "host_buffers": "the rasterised int32 occupancy grid (4 B per cell: PCIe bound) + the scan",
+                               "how": "two contexts alternate: the next step's H2D runs under this step's kernels and result D2H",
+                               "one_context_ms_per_step": e2e_serial_s / KE * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "result": {"best_index": checks["timed_region"][0], "best_score_bits": checks["timed_region"][1],
                        "best_hits": checks["timed_region"][2], "e2e_best_index": checks["e2e"][0],
                        "verified": bool(verified),
-                       "verified_how": f"timed region == strictly sequential graph == e2e (both forms) == rank 0 scoring all "
+                       "e2e_points_rasterised_grid_identical": bool(raster_ok),
+                       "verified_how": f"timed region == strictly sequential graph == e2e from the int32 grid (both forms) == rank 0 "
+                                       f"scoring alone; e2e from points (both forms) == rank 0 alone on the grid rasterised from the same "
+                                       f"points (== the int32 grid + 2 margin cells, compared cell for cell); all: rank 0 scoring all "
                                        f"{n_global[0] * ntx * nty} candidates alone with synchronous calls, on every one of the "
                                        f"{world} rank(s): index, score bits, winner's and last candidate's hit counts"},
         }
@@ -1143,7 +1227,7 @@ def main():
     job = Job()
     K = args.steps
     keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "reps", "serial_ms_per_step", "config", "timing",
-            "edt_mcells_per_s", "match_evals_per_s_per_gpu", "roofline", "rooflines", "e2e", "gpu_launches", "result")
+            "edt_mcells_per_s", "match_evals_per_s_per_gpu", "roofline", "rooflines", "e2e", "e2e_int32_grid", "gpu_launches", "result")
     if args.workload == "config2":
         line = particles_block(args, synth, job, K)
     elif args.workload == "config4":

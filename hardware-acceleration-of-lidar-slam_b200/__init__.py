@@ -88,6 +88,7 @@ def load_library() -> C.CDLL:
         "b200slam_map_upload_occupancy": (i, [vp, vp, vp, i]),
         "b200slam_map_resize": (i, [vp, i, i]),
         "b200slam_map_rasterise": (i, [vp, vp, vp, vp, i, f, c_int_p, c_int_p, c_float_p]),
+        "b200slam_map_rasterise_async": (i, [vp, vp, vp, vp, i, f, c_int_p, c_int_p, c_float_p]),
         "b200slam_map_download_occupancy": (i, [vp, vp, vp, i]),
         "b200slam_map_edt": (i, [vp, vp, f]),
         "b200slam_map_download_field": (i, [vp, vp, vp, i]),
@@ -268,6 +269,19 @@ class Map:
         tl = (C.c_float * 2)()
         self.ctx._check(self.ctx.L.b200slam_map_rasterise(self.ctx.h, self.h, x.ctypes.data, y.ctypes.data, len(x),
                                                           pixel_size, C.byref(r), C.byref(c), tl))
+        self.rows, self.cols = r.value, c.value
+        return r.value, c.value, (np.float32(tl[0]), np.float32(tl[1]))
+
+    def rasterise_async(self, x, y, pixel_size: float, ctx=None):
+        """rasterise() with x, y in page-locked memory (Context.pinned_empty): queued straight from the
+        caller's arrays, which must stay unchanged until the next synchronising call.  ctx: queue on
+        another context of the same GPU (double buffering)."""
+        assert x.dtype == np.float32 and y.dtype == np.float32 and x.flags.c_contiguous and y.flags.c_contiguous
+        c_ = ctx or self.ctx
+        r, c = C.c_int32(0), C.c_int32(0)
+        tl = (C.c_float * 2)()
+        c_._check(c_.L.b200slam_map_rasterise_async(c_.h, self.h, x.ctypes.data, y.ctypes.data, len(x),
+                                                    pixel_size, C.byref(r), C.byref(c), tl))
         self.rows, self.cols = r.value, c.value
         return r.value, c.value, (np.float32(tl[0]), np.float32(tl[1]))
 

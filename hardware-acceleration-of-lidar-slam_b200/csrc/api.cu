@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <time.h>
+#include <xmmintrin.h>
 
 #include <new>
 
@@ -212,6 +213,7 @@ void b200slam_map_destroy(b200slam_ctx *ctx, b200slam_map *map)
     if (map->shared_nranks) comm_unshare_map(ctx, map);
     cudaFree(map->d_occ);
     cudaFree(map->d_field_alloc);
+    cudaFree(map->d_raster_cells);
     delete map;
 }
 
@@ -239,6 +241,7 @@ int b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const in
     CUDA_TRY(ctx, cudaMemcpy2DAsync(map->d_occ, sizeof(int32_t) * (size_t)map->occ_pitch, occ,
                                     sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)map->cols,
                                     map->rows, cudaMemcpyHostToDevice, ctx->stream));
+    map->raster_cells_n = -1;                 // contents no longer "zero except the rasterised cells"
     return B200SLAM_OK;
 }
 
@@ -261,6 +264,35 @@ int ensure_points_capacity(b200slam_ctx *ctx, size_t npoints)
     ctx->d_points = d; ctx->h_points = h;
     ctx->points_cap = cap;
     return B200SLAM_OK;
+}
+
+// main.c:272-289: bounding box of the points -- strict compares, seeded with point 0.  Minimum and maximum do not
+// depend on the order the points are visited in (a NaN never passes a strict compare, a NaN seed stays; which
+// zero survives among +0 / -0 changes nothing once the margin is subtracted), so the walk is 4 lanes wide:
+// _mm_min_ps(v, acc) is exactly `v < acc ? v : acc`.
+static void points_bbox(const float *x, const float *y, int n, float bbox[4])
+{
+    __m128 lox = _mm_set1_ps(x[0]), hix = lox, loy = _mm_set1_ps(y[0]), hiy = loy;
+    int a = 0;
+    for (; a + 4 <= n; a += 4) {
+        const __m128 vx = _mm_loadu_ps(x + a), vy = _mm_loadu_ps(y + a);
+        lox = _mm_min_ps(vx, lox); hix = _mm_max_ps(vx, hix);
+        loy = _mm_min_ps(vy, loy); hiy = _mm_max_ps(vy, hiy);
+    }
+    float l[4][4];
+    _mm_storeu_ps(l[0], lox); _mm_storeu_ps(l[1], loy); _mm_storeu_ps(l[2], hix); _mm_storeu_ps(l[3], hiy);
+    for (int k = 0; k < 4; ++k) bbox[k] = l[k][0];
+    for (int k = 0; k < 2; ++k)
+        for (int j = 1; j < 4; ++j) {
+            if (l[k][j] < bbox[k]) bbox[k] = l[k][j];
+            if (l[k + 2][j] > bbox[k + 2]) bbox[k + 2] = l[k + 2][j];
+        }
+    for (; a < n; ++a) {
+        if (x[a] < bbox[0]) bbox[0] = x[a];
+        if (x[a] > bbox[2]) bbox[2] = x[a];
+        if (y[a] < bbox[1]) bbox[1] = y[a];
+        if (y[a] > bbox[3]) bbox[3] = y[a];
+    }
 }
 
 int rasterise_from_bbox(b200slam_ctx *ctx, b200slam_map *map, int npoints, const float bbox[4], float pixel_size,
@@ -299,14 +331,8 @@ int b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x,
                            float pixel_size, int *rows_out, int *cols_out, float top_left_out[2])
 {
     if (!ctx || !map || !x || !y || npoints <= 0 || !(pixel_size > 0.0f)) return B200SLAM_ERR_ARG;
-    // main.c:272-289: bounding box, strict compares, seeded with point 0
-    float bbox[4] = {x[0], y[0], x[0], y[0]};
-    for (int a = 0; a < npoints; ++a) {
-        if (x[a] < bbox[0]) bbox[0] = x[a];
-        if (x[a] > bbox[2]) bbox[2] = x[a];
-        if (y[a] < bbox[1]) bbox[1] = y[a];
-        if (y[a] > bbox[3]) bbox[3] = y[a];
-    }
+    float bbox[4];
+    points_bbox(x, y, npoints, bbox);
     int rc = ensure_points_capacity(ctx, (size_t)npoints);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));          // pinned staging buffer free again
@@ -317,6 +343,31 @@ int b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x,
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points + ctx->points_cap, ctx->h_points + ctx->points_cap,
                                   sizeof(float) * npoints, cudaMemcpyHostToDevice, ctx->stream));
     ctx->local_n = npoints;                                     // these points ARE the resident local map now
+    for (int i = 0; i < 4; ++i) ctx->local_bbox[i] = bbox[i];
+    return rasterise_from_bbox(ctx, map, npoints, bbox, pixel_size, rows_out, cols_out, top_left_out);
+}
+
+int b200slam_map_rasterise_async(b200slam_ctx *ctx, b200slam_map *map, const float *x, const float *y, int npoints,
+                                 float pixel_size, int *rows_out, int *cols_out, float top_left_out[2])
+{
+    if (!ctx || !map || !x || !y || npoints <= 0 || !(pixel_size > 0.0f)) return B200SLAM_ERR_ARG;
+    cudaPointerAttributes ax, ay;
+    if (cudaPointerGetAttributes(&ax, x) != cudaSuccess || cudaPointerGetAttributes(&ay, y) != cudaSuccess ||
+        ax.type != cudaMemoryTypeHost || ay.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG,
+                                  "b200slam_map_rasterise_async: x and y must be page-locked host memory "
+                                  "(b200slam_host_alloc); use b200slam_map_rasterise for pageable arrays");
+    }
+    float bbox[4];
+    points_bbox(x, y, npoints, bbox);
+    int rc = ensure_points_capacity(ctx, (size_t)npoints);
+    if (rc) return rc;
+    // queued straight from the caller's page-locked arrays: no staging copy, no wait
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points, x, sizeof(float) * npoints, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_points + ctx->points_cap, y, sizeof(float) * npoints, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    ctx->local_n = npoints;
     for (int i = 0; i < 4; ++i) ctx->local_bbox[i] = bbox[i];
     return rasterise_from_bbox(ctx, map, npoints, bbox, pixel_size, rows_out, cols_out, top_left_out);
 }
@@ -362,7 +413,7 @@ int b200slam_map_device_ptrs(b200slam_map *map, int32_t **occ, int *occ_pitch, f
                              int *field_pitch)
 {
     if (!map) return B200SLAM_ERR_ARG;
-    if (occ) *occ = map->d_occ;
+    if (occ) { *occ = map->d_occ; map->occ_exposed = true; map->raster_cells_n = -1; }
     if (occ_pitch) *occ_pitch = map->occ_pitch;
     if (field) *field = map->d_field;
     if (field_pitch) *field_pitch = map->field_pitch;

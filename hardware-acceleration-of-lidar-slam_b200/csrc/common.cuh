@@ -27,6 +27,14 @@ struct b200slam_map {
     float *d_field = nullptr;         // [0][0]
     float pixel_size = 1.0f, top_left_x = 0.0f, top_left_y = 0.0f;
     bool has_geometry = false;
+    // Rasterisation keeps the occupancy "zero everywhere except the cells the last rasterisation set" and
+    // remembers those cells, so the next one erases O(points) cells instead of clearing O(cells) bytes:
+    // raster_cells_n < 0: the allocation's contents are unknown (fresh, uploaded by the host) -> clear it all once;
+    // occ_exposed: the raw pointer was handed out (b200slam_map_device_ptrs) -> always clear the region in use.
+    int32_t *d_raster_cells = nullptr;
+    size_t raster_cells_cap = 0;
+    int raster_cells_n = -1;
+    bool occ_exposed = false;
     // b200slam_map_share: every rank's field allocation mapped here through CUDA IPC
     // (peer_alloc[own rank] == d_field_alloc); nullptr until shared
     float *peer_alloc[64] = {};

@@ -17,8 +17,18 @@ raster_clear_kernel(int4 *__restrict__ occ, long n4)
 }
 
 __global__ void __launch_bounds__(256)
+raster_erase_kernel(const int32_t *__restrict__ cells, int n, int32_t *__restrict__ occ)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int off = cells[a];
+    if (off >= 0) occ[off] = 0;
+}
+
+__global__ void __launch_bounds__(256)
 raster_scatter_kernel(const float *__restrict__ px, const float *__restrict__ py, int n, float min_x,
-                      float min_y, float pixel, int sgrid_x, int rows, int32_t *__restrict__ occ, int pitch)
+                      float min_y, float pixel, int sgrid_x, int rows, int32_t *__restrict__ occ, int pitch,
+                      int32_t *__restrict__ cells)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
@@ -28,20 +38,50 @@ raster_scatter_kernel(const float *__restrict__ px, const float *__restrict__ py
     const int hy = (int)roundf(__fdiv_rn(dy, pixel)) + 1;                   // main.c:340
     const int idx = (((hy - 1) * sgrid_x) + hx) - 1;                        // main.c:345
     const int row = idx / sgrid_x, col = idx % sgrid_x;                     // main.c:348-349
-    if (row >= 0 && row < rows && col >= 0) occ[(long)row * pitch + col] = 1;   // main.c:355
+    const bool in = row >= 0 && row < rows && col >= 0;
+    const int off = in ? row * pitch + col : -1;                            // cells < 2^30 (b200slam_map_create)
+    if (in) occ[off] = 1;                                                   // main.c:355
+    if (cells) cells[a] = off;
 }
 
 }  // namespace
 
 int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float min_x, float min_y, float pixel_size)
 {
-    // main.c:319 clears the whole array; the rows x pitch region in use is what anyone reads
-    const long n4 = (long)map->rows * map->occ_pitch / 4;
-    raster_clear_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<int4 *>(map->d_occ), n4);
-    LAUNCH_CHECK(ctx);
+    // main.c:319 clears the whole array.  Here the occupancy is kept zero outside the cells the previous
+    // rasterisation set, which are remembered, so clearing is erasing those (O(points), not O(cells)).
+    int32_t *cells = nullptr;
+    if (!map->occ_exposed) {
+        if ((size_t)npoints > map->raster_cells_cap) {
+            const size_t cap = ((size_t)npoints + 4095) & ~(size_t)4095;
+            int32_t *d = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&d, sizeof(int32_t) * cap));
+            if (map->raster_cells_n > 0) {                 // the old list still has to erase its cells
+                CUDA_TRY(ctx, cudaMemcpyAsync(d, map->d_raster_cells, sizeof(int32_t) * map->raster_cells_n,
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
+                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            cudaFree(map->d_raster_cells);
+            map->d_raster_cells = d;
+            map->raster_cells_cap = cap;
+        }
+        cells = map->d_raster_cells;
+    }
+    if (cells && map->raster_cells_n >= 0) {
+        if (map->raster_cells_n > 0) {
+            raster_erase_kernel<<<(map->raster_cells_n + 255) / 256, 256, 0, ctx->stream>>>(cells, map->raster_cells_n,
+                                                                                          map->d_occ);
+            LAUNCH_CHECK(ctx);
+        }
+    } else {
+        const long n4 = (long)(cells ? map->cap_rows : map->rows) * map->occ_pitch / 4;
+        raster_clear_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<int4 *>(map->d_occ), n4);
+        LAUNCH_CHECK(ctx);
+    }
     raster_scatter_kernel<<<(npoints + 255) / 256, 256, 0, ctx->stream>>>(
         ctx->d_points, ctx->d_points + ctx->points_cap, npoints, min_x, min_y, pixel_size, map->cols, map->rows,
-        map->d_occ, map->occ_pitch);
+        map->d_occ, map->occ_pitch, cells);
     LAUNCH_CHECK(ctx);
+    map->raster_cells_n = cells ? npoints : -1;
     return B200SLAM_OK;
 }

@@ -115,6 +115,15 @@ int  b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const i
  * Only 8 bytes per point cross PCIe instead of 4 bytes per cell.  x, y: host arrays. */
 int  b200slam_map_rasterise(b200slam_ctx *ctx, b200slam_map *map, const float *x, const float *y,
                             int npoints, float pixel_size, int *rows, int *cols, float top_left[2]);
+/* The same with x and y in PAGE-LOCKED host memory (b200slam_host_alloc): the copies are queued straight
+ * from the caller's arrays -- no staging copy, no wait on the stream -- so the call returns as soon as the
+ * bounding box (the only host pass over the points) is known; x and y must stay unchanged until the next
+ * synchronising call on this context (b200slam_sync, a fetch).  B200SLAM_ERR_ARG for pageable arrays.
+ * With b200slam_map_edt and b200slam_score_lattice_async behind it this is the reference's own sequence
+ * OccupationalGrid -> euclidean_distance_transform -> FastMatch (main.c:884-918) with 8 bytes per map
+ * point crossing PCIe instead of 4 bytes per grid cell. */
+int  b200slam_map_rasterise_async(b200slam_ctx *ctx, b200slam_map *map, const float *x, const float *y,
+                                  int npoints, float pixel_size, int *rows, int *cols, float top_left[2]);
 /* occ -> field entirely on the device (async on the context's stream). */
 int  b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist);
 int  b200slam_map_download_field(b200slam_ctx *ctx, b200slam_map *map, float *out, int stride);

@@ -93,3 +93,43 @@ def test_points_to_pose_chain_matches_reference_flow(ctx, oracle, synth):
             assert gn == on and np.array_equal(bits(gpose), bits(opose))
         finally:
             m.close()
+
+
+@pytest.mark.gpu
+def test_rasterise_sequence_erases_exactly_the_previous_cells(ctx, oracle, synth):
+    """The map remembers the cells a rasterisation set and the next one erases those instead of clearing the
+    grid (csrc/raster.cu).  A sequence on ONE map -- growing and shrinking point sets (the cell list is
+    reallocated), both pixel sizes, a host upload of a full occupancy in between, pageable and page-locked
+    (b200slam_map_rasterise_async) points -- must leave exactly the oracle's grid every time."""
+    cap = 400
+    m = ctx.new_map(cap, cap)
+    try:
+        steps = [(300, 31, (9.0, 6.0), 0.1, False), (9000, 32, (30.0, 18.5), 0.1, True), (40, 33, (3.0, 2.0), 0.2, True),
+                 (6000, 34, (14.0, 30.0), 0.1, False), (6000, 35, (14.0, 9.0), 0.2, True)]
+        for k, (n, seed, extent, pix, pinned) in enumerate(steps):
+            x, y = _points(synth, n, seed, extent)
+            ogrid, otl = oracle.occupational_grid(x, y, pix, cap, cap)
+            if k == 3:                                   # someone uploads a dense grid: the cell list is void
+                m.rows, m.cols = cap, cap
+                ctx._check(ctx.L.b200slam_map_resize(m.h, cap, cap))
+                m.upload_occupancy(np.ones((cap, cap), np.int32))
+            if pinned:
+                px = ctx.pinned_empty((n,), np.float32); px[...] = x
+                py = ctx.pinned_empty((n,), np.float32); py[...] = y
+                rows, cols, tl = m.rasterise_async(px, py, pix)
+            else:
+                rows, cols, tl = m.rasterise(x, y, pix)
+            assert (rows, cols) == ogrid.shape
+            assert bits(np.array(tl)).tolist() == bits(np.array(otl)).tolist()
+            assert np.array_equal(m.download_occupancy(), ogrid), f"step {k}"
+            # nothing stale anywhere in the allocation either: the whole capacity, not just the region in use
+            ctx._check(ctx.L.b200slam_map_resize(m.h, cap, cap))
+            m.rows, m.cols = cap, cap
+            full = m.download_occupancy()
+            assert int(full.sum()) == int(ogrid.sum()), f"step {k}: stale cells outside the grid in use"
+            ctx._check(ctx.L.b200slam_map_resize(m.h, rows, cols))
+            m.rows, m.cols = rows, cols
+        with pytest.raises(Exception):                   # pageable arrays are refused by the async form
+            m.rasterise_async(np.zeros(8, np.float32), np.zeros(8, np.float32), 0.1)
+    finally:
+        m.close()
