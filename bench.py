@@ -787,6 +787,8 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
         floor_kind, floor = lattice_floor(w["n"], w["step"], w["pixel"])
         alg_winstr = floor * evals_per_rank / 32.0
         meas_winstr = ncu_counter(f"lattice_kernel:{workload}:warp_instructions")
+        meas_l1wf = ncu_counter(f"lattice_kernel:{workload}:l1_wavefronts")
+        l1_peak = info["sm_count"] * sm_mhz * 1e6 / 1e9                          # G wavefronts / s: one per cycle per SM
         roofs = {
             "edt_tma_kernel": {"bound": "hbm", "achieved": edt_bytes / (edt_ms * 1e-3) / 1e9, "peak": peak,
                                "unit": "GB/s", "ms": edt_ms, "ms_eager_alone": edt_ms_avg, "algorithmic_bytes": edt_bytes,
@@ -799,6 +801,10 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
                                "measured_warp_instructions": meas_winstr,
                                "measured_lane_instr_per_eval": (meas_winstr * 32.0 / evals_per_rank) if meas_winstr else None,
                                "issue_utilisation": (meas_winstr / (lat_ms * 1e-3) / 1e9 / issue_peak) if meas_winstr else None,
+                               "l1_wavefronts": {"measured_per_launch": meas_l1wf, "peak_gwf_per_s": l1_peak,
+                                                 "utilisation": (meas_l1wf / (lat_ms * 1e-3) / 1e9 / l1_peak) if meas_l1wf else None,
+                                                 "note": "second ceiling of the gathers: l1tex__data_pipe_lsu_wavefronts (global + "
+                                                         "shared) against one wavefront per cycle per SM"},
                                "traffic": ncu_counter(f"lattice_kernel:{workload}"),
                                "evals_per_s": evals_per_rank / (lat_ms * 1e-3),
                                "peak_how": f"4 warp schedulers x {info['sm_count']} SMs x {sm_mhz:.0f} MHz",
