@@ -793,6 +793,11 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
             "edt_tma_kernel": {"bound": "hbm", "achieved": edt_bytes / (edt_ms * 1e-3) / 1e9, "peak": peak,
                                "unit": "GB/s", "ms": edt_ms, "ms_eager_alone": edt_ms_avg, "algorithmic_bytes": edt_bytes,
                                "traffic": ncu_counter(f"edt_tma_kernel:{workload}"),
+                               "occupancy_bytes_per_cell_streamed": 1 if cells >= (1 << 20) else 4,
+                               "note": "algorithmic bytes are SURVEY.md 8d's 8 B / cell (int32 occupancy read + f32 written).  Maps of "
+                                       ">= 2^20 cells keep a byte shadow of the occupancy (packed at upload / written by the "
+                                       "rasteriser) and the kernel streams that: 5 B / cell actually move (`traffic`), so `frac` "
+                                       "can approach 8 / 5 of what an int32-reading kernel could reach",
                                "mcells_per_s": cells / (edt_ms * 1e-3) / 1e6, "how": how},
             "lattice_kernel": {"bound": "issue", "achieved": alg_winstr / (lat_ms * 1e-3) / 1e9, "peak": issue_peak,
                                "unit": "Gwarp-inst/s", "ms": lat_ms, "ms_eager_alone": lat_ms_avg,

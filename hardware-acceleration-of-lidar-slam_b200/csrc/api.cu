@@ -194,7 +194,10 @@ int b200slam_map_create(b200slam_ctx *ctx, int rows, int cols, b200slam_map **ou
                        sizeof(float) * ((size_t)m->field_pitch * rows + field_pad_floats(m->field_pitch)));
     if (e == cudaSuccess)
         e = cudaMemsetAsync(m->d_field_alloc, 0, sizeof(float) * field_pad_floats(m->field_pitch), ctx->stream);
+    if (e == cudaSuccess && (long long)rows * cols >= (1ll << 20) && !getenv("B200SLAM_EDT_NO_BYTES"))
+        e = cudaMalloc(&m->d_occ8, (size_t)m->occ_pitch * rows);      // byte shadow: big maps only (HBM-bound transform)
     if (e != cudaSuccess) {
+        cudaFree(m->d_occ8);
         cudaFree(m->d_occ);
         cudaFree(m->d_field_alloc);
         delete m;
@@ -212,6 +215,7 @@ void b200slam_map_destroy(b200slam_ctx *ctx, b200slam_map *map)
     if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (map->shared_nranks) comm_unshare_map(ctx, map);
     cudaFree(map->d_occ);
+    cudaFree(map->d_occ8);
     cudaFree(map->d_field_alloc);
     cudaFree(map->d_raster_cells);
     delete map;
@@ -242,6 +246,12 @@ int b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const in
                                     sizeof(int32_t) * (size_t)stride, sizeof(int32_t) * (size_t)map->cols,
                                     map->rows, cudaMemcpyHostToDevice, ctx->stream));
     map->raster_cells_n = -1;                 // contents no longer "zero except the rasterised cells"
+    map->occ8_valid = false;
+    if (map->d_occ8 && !map->occ_exposed) {
+        int rc = occ_pack_launch(ctx, map);
+        if (rc) return rc;
+        map->occ8_valid = true;
+    }
     return B200SLAM_OK;
 }
 
@@ -375,6 +385,8 @@ int b200slam_map_rasterise_async(b200slam_ctx *ctx, b200slam_map *map, const flo
 int b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist)
 {
     if (!ctx || !map) return B200SLAM_ERR_ARG;
+    if (map->d_occ8 && map->occ8_valid && max_dist > 1.0f && max_dist <= 15.0f)
+        return edt_launch_bytes(ctx, map->d_occ8, map->occ_pitch, map->d_field, map->field_pitch, map->rows, map->cols, max_dist);
     return edt_launch(ctx, map->d_occ, map->occ_pitch, map->d_field, map->field_pitch, map->rows,
                       map->cols, max_dist);
 }
@@ -413,7 +425,7 @@ int b200slam_map_device_ptrs(b200slam_map *map, int32_t **occ, int *occ_pitch, f
                              int *field_pitch)
 {
     if (!map) return B200SLAM_ERR_ARG;
-    if (occ) { *occ = map->d_occ; map->occ_exposed = true; map->raster_cells_n = -1; }
+    if (occ) { *occ = map->d_occ; map->occ_exposed = true; map->raster_cells_n = -1; map->occ8_valid = false; }
     if (occ_pitch) *occ_pitch = map->occ_pitch;
     if (field) *field = map->d_field;
     if (field_pitch) *field_pitch = map->field_pitch;

@@ -31,6 +31,12 @@ struct b200slam_map {
     // remembers those cells, so the next one erases O(points) cells instead of clearing O(cells) bytes:
     // raster_cells_n < 0: the allocation's contents are unknown (fresh, uploaded by the host) -> clear it all once;
     // occ_exposed: the raw pointer was handed out (b200slam_map_device_ptrs) -> always clear the region in use.
+    // Byte shadow of the occupancy (1 = occupied), same pitch, kept by every writer of d_occ inside the library
+    // (upload: a pack kernel; rasterisation: both stores) for maps of >= 2^20 cells: the transform is HBM bound
+    // there and reads 1 byte per cell instead of 4.  occ8_valid is false while d_occ may have been written behind
+    // the library's back (occ_exposed) -- the transform then reads the int32 grid.
+    uint8_t *d_occ8 = nullptr;
+    bool occ8_valid = false;
     int32_t *d_raster_cells = nullptr;
     size_t raster_cells_cap = 0;
     int raster_cells_n = -1;
@@ -281,6 +287,11 @@ int b200slam_set_error(b200slam_ctx *ctx, int code, const char *fmt, ...);
 // ---- internal entry points between translation units ---------------------------------
 int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
                int field_pitch, int rows, int cols, float max_dist);
+// The same reading the byte shadow of the occupancy (b200slam_map::d_occ8, pitch in bytes a multiple of 16).
+int edt_launch_bytes(b200slam_ctx *ctx, const uint8_t *d_occ8, int occ8_pitch, float *d_field,
+                     int field_pitch, int rows, int cols, float max_dist);
+// int32 occupancy -> byte shadow (rows x cols in use)
+int occ_pack_launch(b200slam_ctx *ctx, const b200slam_map *map);
 
 // Output rows [row_begin, row_end) only, each row also stored into `npeers` (<= 7) other fields
 // of identical layout (peer GPUs' copies of the map, mapped through CUDA IPC).

@@ -163,31 +163,36 @@ __device__ __forceinline__ void edt_emit_rows(const uint32_t (&win)[3 * R], type
     }
 }
 
-template <int R, int NW>
+// OT: element type of the occupancy the kernel streams -- the int32 grid (the reference's type), or its byte
+// shadow (1 byte per cell: a quarter of the read traffic of an HBM-bound kernel).
+template <int R, int NW, typename OT = int32_t>
 struct EdtCfg {
-    // The TMA box origin must be 16-byte aligned in global memory, so the stage starts SH
-    // columns left of the CTA's first output column (SH = R+1 rounded up to 4) and the
+    // The TMA box origin is kept 16-byte aligned in global memory, so the stage starts SH
+    // columns left of the CTA's first output column (SH = R+1 rounded up to 16 bytes) and the
     // ballot loads skip the DELTA = SH - (R+1) surplus columns.
-    static constexpr int SH = (R + 1 + 3) & ~3;
+    static constexpr int EB = (int)sizeof(OT);
+    static constexpr int AL = 16 / EB;                       // elements per 16 bytes
+    static constexpr int SH = (R + 1 + AL - 1) / AL * AL;
     static constexpr int DELTA = SH - (R + 1);
-    static constexpr int BOX_COLS = 64 * NW + 32 + 4;        // one box per stage (<= 256)
-    static constexpr int STAGE_BYTES = ((R * BOX_COLS * 4) + 127) & ~127;
-    static constexpr uint32_t TX_BYTES = R * BOX_COLS * 4;
+    // one box per stage (<= 256 columns, a multiple of 16 bytes): the last ballot word ends at 64 NW + 32 + DELTA
+    static constexpr int BOX_COLS = EB == 4 ? 64 * NW + 32 + 4 : (64 * NW + 32 + DELTA + AL - 1) / AL * AL;
+    static constexpr int STAGE_BYTES = ((R * BOX_COLS * EB) + 127) & ~127;
+    static constexpr uint32_t TX_BYTES = R * BOX_COLS * EB;
     static constexpr int THREADS = 32 * NW;
-    static_assert(BOX_COLS <= 256, "TMA box dimension limit");
+    static_assert(BOX_COLS <= 256 && BOX_COLS >= 64 * NW + 32 + DELTA, "TMA box dimension limit");
 };
 
 // Dynamic shared memory: [stage ring][sqrt table][mbarriers][arrival counters]
 // Output rows [row_begin, row_end) only (the whole grid, or one rank's block of a row-sharded
 // transform); the input halo above and below comes from the full occupancy either way.
-template <int R, int NW, int NST, bool MULTI>
-__global__ void __launch_bounds__(EdtCfg<R, NW>::THREADS)
+template <int R, int NW, int NST, bool MULTI, typename OT = int32_t>
+__global__ void __launch_bounds__(EdtCfg<R, NW, OT>::THREADS)
 edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out, uint32_t pitch_bytes,
                int row_begin, int row_end, int cols, int chunk_batches, int t2, float max_dist,
                const __grid_constant__ EdtPeers peers, unsigned int *__restrict__ error)
 {
     const int rows = row_end;
-    using C = EdtCfg<R, NW>;
+    using C = EdtCfg<R, NW, OT>;
     constexpr int B = R;                          // rows per stage / batch
     constexpr int WN = 3 * R;                     // register window rows
 
@@ -262,7 +267,7 @@ edt_tma_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ out
             pdl_wait_prior_grids();
             return;
         }
-        const int *st = reinterpret_cast<const int *>(smem_raw + (size_t)s * C::STAGE_BYTES) + woff;
+        const OT *st = reinterpret_cast<const OT *>(smem_raw + (size_t)s * C::STAGE_BYTES) + woff;
         // ---- pass 1: horizontal nearest-occupied distance from the ballots ------------
         int ld[B][3];
 #pragma unroll
@@ -372,20 +377,20 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-template <int R, int NW, int NST>
+template <int R, int NW, int NST, typename OT>
 size_t edt_smem_bytes(int t2)
 {
-    using C = EdtCfg<R, NW>;
+    using C = EdtCfg<R, NW, OT>;
     return (size_t)NST * C::STAGE_BYTES + (size_t)(t2 + 1) * EDT_SCALE + NST * (sizeof(uint64_t) + sizeof(int));
 }
 
-template <int R, int NW, int NST, bool MULTI>
-int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field, int field_pitch,
+template <int R, int NW, int NST, bool MULTI, typename OT = int32_t>
+int launch_tma(b200slam_ctx *ctx, const OT *d_occ, int occ_pitch, float *d_field, int field_pitch,
                int rows, int cols, int t2, float max_dist, int row_begin, int row_end, const EdtPeers &peers)
 {
-    using C = EdtCfg<R, NW>;
-    auto kern = edt_tma_kernel<R, NW, NST, MULTI>;
-    const size_t smem = edt_smem_bytes<R, NW, NST>(t2);
+    using C = EdtCfg<R, NW, OT>;
+    auto kern = edt_tma_kernel<R, NW, NST, MULTI, OT>;
+    const size_t smem = edt_smem_bytes<R, NW, NST, OT>(t2);
     static int occupancy_dev[64] = {};        // resident CTAs per SM (per instantiation and device)
     static size_t smem_set_dev[64] = {};
     int &occupancy = occupancy_dev[ctx->device & 63];
@@ -404,10 +409,11 @@ int launch_tma(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_
     if (!enc) return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)occ_pitch * sizeof(int32_t)};
+    const cuuint64_t gstr[1] = {(cuuint64_t)occ_pitch * sizeof(OT)};
     const cuuint32_t box[2] = {(cuuint32_t)C::BOX_COLS, (cuuint32_t)R};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<int32_t *>(d_occ), gdim, gstr, box,
+    CUresult cr = enc(&tmap, sizeof(OT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                      const_cast<OT *>(d_occ), gdim, gstr, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                       getenv("B200SLAM_EDT_L2P") ? (CUtensorMapL2promotion)atoi(getenv("B200SLAM_EDT_L2P"))
                                                  : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -487,6 +493,57 @@ int launch_fused(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *
 
 }  // namespace
 
+// Window radius R and clamp index t2 exactly as the float compare at main.c:235 decides.
+static void edt_radius(float max_dist, int *R_out, int *t2_out)
+{
+    const float thr = max_dist * max_dist;
+    int R = 0;
+    while ((float)((R + 1) * (R + 1)) < thr) R++;
+    int t2 = R * R;
+    while ((float)t2 < thr) t2++;       // smallest integer d2 that is NOT < max_dist^2
+    *R_out = R; *t2_out = t2;
+}
+
+namespace {
+__global__ void __launch_bounds__(256)
+occ_pack_kernel(const int32_t *__restrict__ occ, uint8_t *__restrict__ occ8, int pitch, int rows)
+{
+    // 4 cells per thread: one 16-byte load, one 4-byte store (the pitch is a multiple of 32 cells)
+    const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= (long)rows * pitch / 4) return;
+    const int4 v = reinterpret_cast<const int4 *>(occ)[i4];
+    reinterpret_cast<uint32_t *>(occ8)[i4] = (v.x != 0 ? 1u : 0u) | (v.y != 0 ? 0x100u : 0u) | (v.z != 0 ? 0x10000u : 0u) |
+                                             (v.w != 0 ? 0x1000000u : 0u);
+}
+}  // namespace
+
+int occ_pack_launch(b200slam_ctx *ctx, const b200slam_map *map)
+{
+    const long n4 = (long)map->rows * map->occ_pitch / 4;
+    occ_pack_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ctx->stream>>>(map->d_occ, map->d_occ8, map->occ_pitch, map->rows);
+    LAUNCH_CHECK(ctx);
+    return B200SLAM_OK;
+}
+
+int edt_launch_bytes(b200slam_ctx *ctx, const uint8_t *d_occ8, int occ8_pitch, float *d_field,
+                     int field_pitch, int rows, int cols, float max_dist)
+{
+    if (rows <= 0 || cols <= 0) return B200SLAM_OK;
+    if (!(max_dist > 0.0f) || max_dist > 255.0f)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "max_dist %g out of (0, 255]", max_dist);
+    int R, t2;
+    edt_radius(max_dist, &R, &t2);
+    EdtPeers peers = {};
+    switch (R) {
+#define CASE(RR) case RR: return launch_tma<RR, 3, 3, false, uint8_t>(ctx, d_occ8, occ8_pitch, d_field, field_pitch, rows, cols, t2, max_dist, 0, rows, peers);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+        CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+#undef CASE
+        default: break;
+    }
+    return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "byte-shadow EDT needs 1 < max_dist <= 15 (radius %d)", R);
+}
+
 int edt_launch(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, float *d_field,
                int field_pitch, int rows, int cols, float max_dist)
 {
@@ -510,12 +567,8 @@ int edt_launch_rows(b200slam_ctx *ctx, const int32_t *d_occ, int occ_pitch, floa
                                     : 0;
     if (!(max_dist > 0.0f) || max_dist > 255.0f)
         return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "max_dist %g out of (0, 255]", max_dist);
-    // Window radius and clamp index exactly as the float compare at main.c:235 decides.
-    const float thr = max_dist * max_dist;
-    int R = 0;
-    while ((float)((R + 1) * (R + 1)) < thr) R++;
-    int t2 = R * R;
-    while ((float)t2 < thr) t2++;       // smallest integer d2 that is NOT < max_dist^2
+    int R, t2;
+    edt_radius(max_dist, &R, &t2);
 
     // The TMA path needs a 16-byte aligned base and pitch (always true for b200slam_map).
     const bool tma_ok = (occ_pitch % 4 == 0) && ((uintptr_t)d_occ % 16 == 0);

@@ -17,18 +17,21 @@ raster_clear_kernel(int4 *__restrict__ occ, long n4)
 }
 
 __global__ void __launch_bounds__(256)
-raster_erase_kernel(const int32_t *__restrict__ cells, int n, int32_t *__restrict__ occ)
+raster_erase_kernel(const int32_t *__restrict__ cells, int n, int32_t *__restrict__ occ, uint8_t *__restrict__ occ8)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     const int off = cells[a];
-    if (off >= 0) occ[off] = 0;
+    if (off >= 0) {
+        occ[off] = 0;
+        if (occ8) occ8[off] = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256)
 raster_scatter_kernel(const float *__restrict__ px, const float *__restrict__ py, int n, float min_x,
                       float min_y, float pixel, int sgrid_x, int rows, int32_t *__restrict__ occ, int pitch,
-                      int32_t *__restrict__ cells)
+                      int32_t *__restrict__ cells, uint8_t *__restrict__ occ8)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
@@ -40,7 +43,10 @@ raster_scatter_kernel(const float *__restrict__ px, const float *__restrict__ py
     const int row = idx / sgrid_x, col = idx % sgrid_x;                     // main.c:348-349
     const bool in = row >= 0 && row < rows && col >= 0;
     const int off = in ? row * pitch + col : -1;                            // cells < 2^30 (b200slam_map_create)
-    if (in) occ[off] = 1;                                                   // main.c:355
+    if (in) {
+        occ[off] = 1;                                                       // main.c:355
+        if (occ8) occ8[off] = 1;
+    }
     if (cells) cells[a] = off;
 }
 
@@ -51,6 +57,7 @@ int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float mi
     // main.c:319 clears the whole array.  Here the occupancy is kept zero outside the cells the previous
     // rasterisation set, which are remembered, so clearing is erasing those (O(points), not O(cells)).
     int32_t *cells = nullptr;
+    uint8_t *occ8 = map->occ_exposed ? nullptr : map->d_occ8;          // the byte shadow follows the list mode only
     if (!map->occ_exposed) {
         if ((size_t)npoints > map->raster_cells_cap) {
             const size_t cap = ((size_t)npoints + 4095) & ~(size_t)4095;
@@ -70,18 +77,20 @@ int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float mi
     if (cells && map->raster_cells_n >= 0) {
         if (map->raster_cells_n > 0) {
             raster_erase_kernel<<<(map->raster_cells_n + 255) / 256, 256, 0, ctx->stream>>>(cells, map->raster_cells_n,
-                                                                                          map->d_occ);
+                                                                                          map->d_occ, occ8);
             LAUNCH_CHECK(ctx);
         }
     } else {
         const long n4 = (long)(cells ? map->cap_rows : map->rows) * map->occ_pitch / 4;
         raster_clear_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<int4 *>(map->d_occ), n4);
         LAUNCH_CHECK(ctx);
+        if (occ8) CUDA_TRY(ctx, cudaMemsetAsync(occ8, 0, (size_t)map->cap_rows * map->occ_pitch, ctx->stream));
     }
     raster_scatter_kernel<<<(npoints + 255) / 256, 256, 0, ctx->stream>>>(
         ctx->d_points, ctx->d_points + ctx->points_cap, npoints, min_x, min_y, pixel_size, map->cols, map->rows,
-        map->d_occ, map->occ_pitch, cells);
+        map->d_occ, map->occ_pitch, cells, occ8);
     LAUNCH_CHECK(ctx);
     map->raster_cells_n = cells ? npoints : -1;
+    map->occ8_valid = occ8 != nullptr;
     return B200SLAM_OK;
 }

@@ -159,3 +159,39 @@ def test_edt_row_ranges_compose_and_touch_nothing_else(ctx, oracle, synth):
             m.edt_rows(10, rows + 1)
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("max_dist", [10.0, 2.0, 15.0, 3.5])
+def test_edt_byte_shadow_and_int32_paths_agree(ctx, oracle, synth, monkeypatch, max_dist):
+    """Maps of >= 2^20 cells keep a byte shadow of the occupancy (uploads pack it, rasterisations write both) and
+    the transform streams that instead of the int32 grid (csrc/edt.cu, OT = uint8_t).  Both paths against the
+    oracle on the same grids -- ragged size (partial strips and batches), non-binary cells, a sub-rectangle
+    after b200slam_map_resize -- and the fall-back once the raw occupancy pointer has been handed out."""
+    import ctypes as C
+    rows, cols = 1111, 1203
+    occ = synth.grid_rooms(rows, cols, seed=21) * np.int32(-5) + synth.grid_bernoulli(rows, cols, 0.002, seed=22) * np.int32(1 << 9)
+    want = oracle.edt((occ != 0).astype(np.int32), max_dist)
+    sub = (700, 1000)
+    want_sub = oracle.edt((occ[:sub[0], :sub[1]] != 0).astype(np.int32), max_dist)
+    for no_bytes in (False, True):
+        if no_bytes:
+            monkeypatch.setenv("B200SLAM_EDT_NO_BYTES", "1")        # read when the map is created
+        m = ctx.new_map(rows, cols)
+        try:
+            m.upload_occupancy(occ).edt(max_dist)
+            assert np.array_equal(bits(m.download_field()), bits(want)), ("int32" if no_bytes else "bytes")
+            ctx._check(ctx.L.b200slam_map_resize(m.h, sub[0], sub[1]))
+            m.rows, m.cols = sub
+            m.edt(max_dist)                                          # same memory, smaller grid in use
+            assert np.array_equal(bits(m.download_field()), bits(want_sub))
+            if not no_bytes:
+                # the raw pointer leaves the library: the shadow can no longer be trusted, the int32 grid is read
+                p, pitch = C.c_void_p(), C.c_int32(0)
+                ctx._check(ctx.L.b200slam_map_device_ptrs(m.h, C.byref(p), C.byref(pitch), None, None))
+                ctx._check(ctx.L.b200slam_map_resize(m.h, rows, cols))
+                m.rows, m.cols = rows, cols
+                m.upload_occupancy(occ).edt(max_dist)
+                assert np.array_equal(bits(m.download_field()), bits(want))
+        finally:
+            monkeypatch.delenv("B200SLAM_EDT_NO_BYTES", raising=False)
+            m.close()
