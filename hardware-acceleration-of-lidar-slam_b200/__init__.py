@@ -115,6 +115,9 @@ def load_library() -> C.CDLL:
         "b200slam_mappoints_grow_async": (i, [vp, f]),
         "b200slam_scan_step_async": (i, [vp, c_float_p, i, vp, vp, c_float_p, c_float_p, c_float_p]),
         "b200slam_scan_step_resident_async": (i, [vp, C.c_int64, i, vp, vp, c_float_p, c_float_p, c_float_p]),
+        "b200slam_scan_chain_begin": (i, [vp, i, c_float_p, c_float_p, c_float_p, f, f]),
+        "b200slam_scan_chain_step_async": (i, [vp, i, C.c_int64, i, vp, vp, c_float_p, c_float_p]),
+        "b200slam_scan_chain_fetch": (i, [vp, i, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p]),
         "b200slam_csv_ingest": (i, [vp, vp, C.c_size_t, vp, C.c_int64, c_i64_p]),
         "b200slam_csv_values": (i, [vp, C.POINTER(vp), c_i64_p]),
         "b200slam_scan_transform": (i, [vp, c_float_p]),
@@ -438,6 +441,24 @@ class Context:
         self._check(self.L.b200slam_scan_step_resident_async(self.h, int(first_value), int(max_range), map_a.h, map_b.h,
                                                              _f3(pose), _f3(res_a), _f3(res_b)))
         self._nbeams = self._lidar_n
+
+    def scan_chain_begin(self, scan_index: int, pose, prev_pose, map_pose, mini_dt: float, mini_dr: float):
+        """Device-resident per-scan loop: set the pose state (prev_pose None: no motion model for the first scan)."""
+        self._check(self.L.b200slam_scan_chain_begin(self.h, int(scan_index), _f3(pose), None if prev_pose is None else _f3(prev_pose),
+                                                     _f3(map_pose), mini_dt, mini_dr))
+
+    def scan_chain_step_async(self, scan_index: int, first_value: int, map_a: Map, map_b: Map, res_a, res_b, max_range: int = 24):
+        self._check(self.L.b200slam_scan_chain_step_async(self.h, int(scan_index), int(first_value), int(max_range), map_a.h,
+                                                          map_b.h, _f3(res_a), _f3(res_b)))
+        self._nbeams = self._lidar_n
+
+    def scan_chain_fetch(self, scan_index: int):
+        """-> (pose_a, pose_b, scan size, bestHits_size, stopped)"""
+        pa, pb = (C.c_float * 3)(), (C.c_float * 3)()
+        n, bh, st = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.L.b200slam_scan_chain_fetch(self.h, int(scan_index), pa, pb, C.byref(n), C.byref(bh), C.byref(st)))
+        self._nbeams = n.value
+        return np.array(list(pa), np.float32), np.array(list(pb), np.float32), n.value, bh.value, st.value
 
     def mappoints_grow_async(self, threshold: float = 1.5):
         self._check(self.L.b200slam_mappoints_grow_async(self.h, threshold))

@@ -104,6 +104,7 @@ void b200slam_destroy(b200slam_ctx *ctx)
     if (ctx->scan_event) cudaEventDestroy(ctx->scan_event);
     cudaFreeHost(ctx->h_lat); cudaFree(ctx->d_lat);
     cudaFree(ctx->d_match); cudaFreeHost(ctx->h_match); cudaFreeHost(ctx->h_result);
+    cudaFree(ctx->d_chain); cudaFreeHost(ctx->h_chain_ring);
     cudaFree(ctx->d_keys); cudaFreeHost(ctx->h_keys); cudaFree(ctx->d_hit_values);
     cudaFree(ctx->d_scores);
     particles_unshare_blocks(ctx);
@@ -1003,6 +1004,107 @@ int b200slam_fastmatch_pair_fetch(b200slam_ctx *ctx, float pose_a[3], float pose
     for (int i = 0; i < 3; ++i) ctx->last.pose0[i] = pa[i];     // b200slam_match_fetch then describes the second match
     if (scan_size) *scan_size = ctx->nbeams;
     if (best_hits_size) *best_hits_size = m.best_hits;           // main.c:557
+    return B200SLAM_OK;
+}
+
+/* ---- the per-scan loop on the device: scans queued ahead of their results (main.c:859-970) ------------- */
+
+}  // extern "C"
+
+namespace {
+__global__ void chain_set_kernel(ChainDev *dst, const ChainDev v) { *dst = v; }
+}  // namespace
+
+extern "C" {
+
+int b200slam_scan_chain_begin(b200slam_ctx *ctx, int scan_index, const float pose[3], const float *prev_pose,
+                              const float map_pose[3], float mini_update_dt, float mini_update_dr)
+{
+    if (!ctx || !pose || !map_pose || scan_index < 0) return B200SLAM_ERR_ARG;
+    int rc = chain_trig_selftest(ctx);                    // once per context: the device's cosf / sinf == this host's libm
+    if (rc) return rc;
+    if (!ctx->d_chain) CUDA_TRY(ctx, cudaMalloc(&ctx->d_chain, sizeof(ChainDev)));
+    if (!ctx->h_chain_ring) {
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_chain_ring, sizeof(ChainSlot) * CHAIN_RING, cudaHostAllocMapped));
+        memset(ctx->h_chain_ring, 0, sizeof(ChainSlot) * CHAIN_RING);
+    }
+    ChainDev v;
+    for (int i = 0; i < 3; ++i) {
+        v.pose[i] = pose[i];
+        v.prev[i] = prev_pose ? prev_pose[i] : pose[i];
+        v.map_pose[i] = map_pose[i];
+    }
+    v.have_prev = prev_pose ? 1 : 0;
+    v.next_scan = scan_index;
+    v.stop = 0;
+    ctx->chain_mini_dt = mini_update_dt;
+    ctx->chain_mini_dr = mini_update_dr;
+    chain_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_chain, v);
+    LAUNCH_CHECK(ctx);
+    return B200SLAM_OK;
+}
+
+int b200slam_scan_chain_step_async(b200slam_ctx *ctx, int scan_index, int64_t first_value, int max_range, b200slam_map *map_a,
+                                   b200slam_map *map_b, const float res_a[3], const float res_b[3])
+{
+    if (!ctx || scan_index < 0 || first_value < 0 || !map_a || !map_b || !res_a || !res_b) return B200SLAM_ERR_ARG;
+    if (!ctx->d_chain) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_scan_chain_begin first");
+    if (ctx->lidar_n <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_lidar_set first");
+    if (!ctx->d_csv_values || first_value + ctx->lidar_n > ctx->csv_count)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "values [%lld, %lld) are not in the ingested CSV (%lld values)",
+                                  (long long)first_value, (long long)(first_value + ctx->lidar_n), (long long)ctx->csv_count);
+    if (!map_a->has_geometry || !map_b->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
+    int rc = ensure_scan_capacity(ctx, ctx->lidar_n);
+    if (!rc) rc = ensure_front(ctx);
+    if (rc) return rc;
+    ChainLaunch C;
+    C.scan_index = scan_index;
+    C.step_a[0] = C.step_a[1] = res_a[0]; C.step_a[2] = res_a[2];         // main.c:386-387
+    C.step_b[0] = C.step_b[1] = res_b[0]; C.step_b[2] = res_b[2];
+    rc = scan_chain_launch(ctx, map_a, map_b, C, ctx->d_csv_values + first_value, max_range);
+    if (rc) return rc;
+    ctx->nbeams = ctx->lidar_n;            // upper bound until a fetch
+    ctx->scan_n_dev = true;
+    ctx->scan_t_valid = false;
+    ctx->last.valid = true; ctx->last.is_poses = false; ctx->last.gathered = false; ctx->last.exchanged = false;
+    for (int i = 0; i < 3; ++i) { ctx->last.n[i] = 3; ctx->last.step[i] = C.step_b[i]; }
+    ctx->pair.valid = false;
+    return B200SLAM_OK;
+}
+
+int b200slam_scan_chain_fetch(b200slam_ctx *ctx, int scan_index, float pose_a[3], float pose_b[3], int *scan_size,
+                              int *best_hits_size, int *stopped)
+{
+    if (!ctx || scan_index < 0) return B200SLAM_ERR_ARG;
+    if (!ctx->h_chain_ring) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "no chained scan queued");
+    volatile ChainSlot *h = ctx->h_chain_ring + (scan_index % CHAIN_RING);
+    const unsigned long long want = (unsigned long long)scan_index + 1ull;
+    {
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        unsigned spins = 0;
+        while (h->seq != want) {
+            if ((++spins & 0xfffu) == 0) {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > 2.0) {
+                    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                    if (h->seq != want)
+                        return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "chained scan %d did not run (the chain had stopped, or "
+                                                  "was begun at another scan)", scan_index);
+                }
+            }
+        }
+        __sync_synchronize();
+    }
+    if (h->error) return device_error_check(ctx, h->error);
+    if (pose_a) for (int i = 0; i < 3; ++i) pose_a[i] = h->pose_a[i];
+    if (pose_b) for (int i = 0; i < 3; ++i) pose_b[i] = h->pose_b[i];
+    for (int i = 0; i < 3; ++i) ctx->last.pose0[i] = h->pose_a[i];
+    ctx->nbeams = h->scan_n;
+    if (ctx->mp_n_dev) ctx->mp_size = h->mp_n;
+    if (scan_size) *scan_size = h->scan_n;
+    if (best_hits_size) *best_hits_size = h->best_hits;
+    if (stopped) *stopped = h->stopped;
     return B200SLAM_OK;
 }
 

@@ -89,6 +89,23 @@ struct MatchHost {
     unsigned long long seq;
     long long trace[16];        // SM cycle counter at the fused kernel's phase boundaries (B200SLAM_FM_TRACE diagnostics)
 };
+// Device-resident per-scan loop (b200slam_scan_chain_*): the poses the motion model and the mini-update test of the
+// reference's main() need (main.c:875-898, 928-940) live here, so a scan's kernel can be queued before the scan in
+// front of it has finished.  A kernel of scan k runs only while next_scan == k and stop == 0; its tail commits the
+// new pose, advances next_scan and raises stop when the mini-update test fires (the kernels queued behind it then
+// return at once and leave the scan, the match state and bestHits[] of scan k in place for the host's map update).
+struct ChainDev {
+    float pose[3], prev[3], map_pose[3];
+    int have_prev, next_scan, stop;
+};
+// One slot per scan in a ring of mapped host memory; seq = scan index + 1, written last behind a system fence.
+struct ChainSlot {
+    float pose_a[3], pose_b[3];
+    int scan_n, best_hits, mp_n, stopped;
+    unsigned int error, pad;
+    unsigned long long seq;
+};
+constexpr int CHAIN_RING = 64;
 constexpr int MATCH_SMALL = 64;
 // Every device-side wait is bounded (%globaltimer against b200slam_ctx::spin_timeout_ns, or an iteration
 // cap for the TMA barrier): a dead or mis-ordered peer costs a timeout and an error code, never a hung GPU.
@@ -243,6 +260,12 @@ struct b200slam_ctx {
     struct { bool valid = false; float guess[3], step_a[3], step_b[3]; } pair;
     MatchHost *h_result = nullptr;        // mapped pinned (host pointer == device pointer under UVA)
     unsigned long long result_seq = 0;
+    // b200slam_scan_chain_*: device pose state, result ring (mapped pinned), whether the device's cosf / sinf have
+    // been checked against the running libm (0 = not yet, 1 = identical, -1 = differ: the chain is refused)
+    ChainDev *d_chain = nullptr;
+    ChainSlot *h_chain_ring = nullptr;
+    int chain_trig_ok = 0;
+    float chain_mini_dt = 0.0f, chain_mini_dr = 0.0f;
 
     // generic EDT scratch (u16 column distances)
     uint16_t *d_edt_scratch = nullptr;
@@ -320,6 +343,10 @@ struct LatticeLaunch {
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
 int exchange_collect_launch(b200slam_ctx *ctx);
+struct ChainLaunch { int scan_index; float step_a[3], step_b[3]; };
+int scan_chain_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_map *mb, const ChainLaunch &C,
+                      const float *d_ranges, int max_range);
+int chain_trig_selftest(b200slam_ctx *ctx);
 int scan_step_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_map *mb, const float *tables12,
                      const float *tables36, const float *d_ranges, int max_range);
 // B200SLAM_ERR_STATE (with a message) when a bounded device-side wait has given up since the last comm_init.

@@ -37,6 +37,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "trig.cuh"
 
 namespace {
 
@@ -888,6 +889,7 @@ struct FmMap {
     const float *field;       // [0][0]; field[-1] == 0
     int pitch, rows, cols;
     float ipixel;
+    float tlx, tly;           // top-left corner (chain mode: the axis tables are computed on the device)
 };
 
 // One launch = optional readAScan + one or two matches ("passes").  Pass 0 reads its axis tables ct | st | sxt | syt
@@ -903,6 +905,13 @@ struct FmArgs {
     const int *nbeams_dev;
     int nth, ntx, nty;
     int nbp;                  // row pitch of vals (beam capacity rounded up to a multiple of 32, plus 4)
+    // chain mode (b200slam_scan_chain_step_async): the lattice centre comes from the device's own pose state, the axis
+    // tables (main.c:424-437, cosf / sinf as glibc computes them: trig.cuh) are built here, the tail commits the pose
+    ChainDev *chain;
+    ChainSlot *chain_ring;
+    int scan_index;
+    float step_a[3], step_b[3];
+    float mini_dt, mini_dr;
     MatchDev *match;
     float *hit_values;        // the bestHits[] twin ([1] of the context's buffer)
     MatchHost *host_result;
@@ -1081,6 +1090,18 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
     // Everything this kernel reads (scan, beam count, match state) and writes (bestHits[] twin, match state) may
     // belong to the kernel in front until it has completed; being resident already saves the launch latency.
     pdl_wait_prior_grids();
+    [[maybe_unused]] float guess[3] = {0.0f, 0.0f, 0.0f};
+    if (A.chain) {
+        // the chain's state only changes in the tail of a kernel that has completed: the same answer in every CTA
+        const volatile ChainDev *cs = A.chain;
+        if (cs->stop != 0 || cs->next_scan != A.scan_index) return;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            // constant-velocity motion model, main.c:875-898: pose_guess = pose + DiffPose(previous_pose, pose)
+            const float p = cs->pose[i];
+            guess[i] = cs->have_prev ? __fadd_rn(p, __fsub_rn(p, cs->prev[i])) : p;
+        }
+    }
     int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
     if (A.ranges) {
         // ---- readAScan (main.c:71-95): drop r < range_min | r > max_range, x = r cos, y = r sin, compacted in
@@ -1146,9 +1167,30 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
                 ctT = tb + 3 * ith1; stT = tb + 9 + 3 * ith1; sxtT = tb + 18 + 3 * itx1; sytT = tb + 27 + 3 * ity1;
             }
             __syncthreads();                          // raw_s filled; vals / balm / pre / tab_s of the previous pass done with
-            if (tid < A.nth) { tab_s[tid] = ctT[tid]; tab_s[FM_MAX_CAND + tid] = stT[tid]; }
-            if (tid < A.ntx) tab_s[2 * FM_MAX_CAND + tid] = sxtT[tid];
-            if (tid < A.nty) tab_s[3 * FM_MAX_CAND + tid] = sytT[tid];
+            if (A.chain) {
+                // b200slam_lattice_value: p + (float)(k - n / 2) * s, the product rounded on its own (main.c:424-426)
+                auto lv = [](float p, float st, int k) { return __fadd_rn(p, __fmul_rn((float)(k - 1), st)); };
+                float c[3] = {guess[0], guess[1], guess[2]};
+                if (pass == 1) {                      // FastMatch2 starts from FastMatch's result (main.c:918)
+                    seed = key;
+                    const int lin1 = (int)(key & 0xffffffffull);
+                    c[0] = lv(guess[0], A.step_a[0], (lin1 / 3) % 3);
+                    c[1] = lv(guess[1], A.step_a[1], lin1 % 3);
+                    c[2] = lv(guess[2], A.step_a[2], lin1 / 9);
+                }
+                const float *stp = pass == 0 ? A.step_a : A.step_b;
+                if (tid < 3) {
+                    const float th = lv(c[2], stp[2], tid);
+                    tab_s[tid] = glibc_trig::sincos(th, 1);                                          // main.c:434
+                    tab_s[FM_MAX_CAND + tid] = glibc_trig::sincos(th, 0);                            // main.c:435
+                    tab_s[2 * FM_MAX_CAND + tid] = __fmul_rn(__fsub_rn(lv(c[0], stp[0], tid), M.tlx), M.ipixel);   // main.c:436
+                    tab_s[3 * FM_MAX_CAND + tid] = __fmul_rn(__fsub_rn(lv(c[1], stp[1], tid), M.tly), M.ipixel);   // main.c:437
+                }
+            } else {
+                if (tid < A.nth) { tab_s[tid] = ctT[tid]; tab_s[FM_MAX_CAND + tid] = stT[tid]; }
+                if (tid < A.ntx) tab_s[2 * FM_MAX_CAND + tid] = sxtT[tid];
+                if (tid < A.nty) tab_s[3 * FM_MAX_CAND + tid] = sytT[tid];
+            }
             for (int i = tid; i < (nchunk_pad << 5); i += FM_THREADS) {
                 const float2 p = i < nbeams ? raw_s[i] : make_float2(0.0f, 0.0f);                    // padding of the last group: any finite value
                 ps_s[i] = make_float2(__fmul_rn(p.x, M.ipixel), __fmul_rn(p.y, M.ipixel));           // main.c:418-419
@@ -1265,6 +1307,35 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
                 for (int i = 0; i < 16; ++i) h->trace[i] = (i < ntrace || (i >= 12 && i < 12 + A.npass)) ? trace_s[i] : 0;
             __threadfence_system();
             h->seq = A.host_seq;
+        }
+        if (A.chain) {
+            // ---- commit: the refined pose (main.c:592-594 of both matches, :920-922), the path's previous entry, the
+            // mini-update test (main.c:928-940); the result goes to the host through the ring, seq last ------------------
+            auto lv = [](float p, float st, int k) { return __fadd_rn(p, __fmul_rn((float)(k - 1), st)); };
+            ChainDev *cs = A.chain;
+            const int l1 = (int)(seed & 0xffffffffull), l2 = (int)(key & 0xffffffffull);
+            const int ia[3] = {(l1 / 3) % 3, l1 % 3, l1 / 9}, ib[3] = {(l2 / 3) % 3, l2 % 3, l2 / 9};
+            volatile ChainSlot *slot = A.chain_ring + (A.scan_index % CHAIN_RING);
+            bool update = false;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float pa = lv(guess[i], A.step_a[i], ia[i]);
+                const float pb = lv(pa, A.step_b[i], ib[i]);
+                const float dp = fabsf(__fsub_rn(pb, cs->map_pose[i]));                              // DiffPose(map.pose, pose)
+                update = update || dp > (i < 2 ? A.mini_dt : A.mini_dr);
+                cs->prev[i] = cs->pose[i];
+                cs->pose[i] = pb;
+                slot->pose_a[i] = pa; slot->pose_b[i] = pb;
+            }
+            cs->have_prev = 1;
+            cs->next_scan = A.scan_index + 1;
+            if (update) cs->stop = 1;
+            slot->scan_n = nbeams; slot->best_hits = bh;
+            slot->mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
+            slot->stopped = update ? 1 : 0;
+            slot->error = *reinterpret_cast<volatile unsigned int *>(&A.match->error);
+            __threadfence_system();
+            slot->seq = (unsigned long long)A.scan_index + 1ull;
         }
     }
 #undef FM_TRACE
@@ -1538,6 +1609,99 @@ int scan_step_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_m
     memcpy(T.v, tables12, sizeof(float) * 12);
     memcpy(T.v + FM_TAB_B, tables36, sizeof(float) * 36);
     return fastmatch_launch_args(ctx, A, T);
+}
+
+// One scan of the device-resident loop: the fused kernel in chain mode (no tables from the host, no pose argument).
+int scan_chain_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_map *mb, const ChainLaunch &C,
+                      const float *d_ranges, int max_range)
+{
+    FmArgs A = {};
+    const b200slam_map *mm[2] = {ma, mb};
+    for (int p = 0; p < 2; ++p) {
+        A.map[p].field = mm[p]->d_field; A.map[p].pitch = mm[p]->field_pitch; A.map[p].rows = mm[p]->rows;
+        A.map[p].cols = mm[p]->cols; A.map[p].ipixel = 1 / mm[p]->pixel_size;                 // main.c:383
+        A.map[p].tlx = mm[p]->top_left_x; A.map[p].tly = mm[p]->top_left_y;
+    }
+    A.npass = 2;
+    A.seeded0 = 0;
+    A.scan_x = ctx->d_scan_x; A.scan_y = ctx->d_scan_y;
+    A.nbeams = ctx->lidar_n; A.nbeams_dev = nullptr;
+    A.nth = A.ntx = A.nty = 3;
+    A.match = ctx->d_match;
+    A.hit_values = ctx->d_hit_values + ctx->scan_cap;
+    A.host_result = nullptr; A.host_seq = 0;
+    A.mp_n_dev = (ctx->mp_n_dev && ctx->d_front) ? &ctx->d_front->mp_n : nullptr;
+    A.ranges = d_ranges; A.cos_a = ctx->d_lidar; A.sin_a = ctx->d_lidar + ctx->lidar_n;
+    A.lidar_n = ctx->lidar_n; A.max_range = max_range; A.range_min = ctx->lidar_range_min;
+    A.scan_x_out = ctx->d_scan_x; A.scan_y_out = ctx->d_scan_y;
+    A.front = ctx->d_front;
+    A.chain = ctx->d_chain; A.chain_ring = ctx->h_chain_ring; A.scan_index = C.scan_index;
+    for (int i = 0; i < 3; ++i) { A.step_a[i] = C.step_a[i]; A.step_b[i] = C.step_b[i]; }
+    A.mini_dt = ctx->chain_mini_dt; A.mini_dr = ctx->chain_mini_dr;
+    if (A.nbeams > FM_MAX_BEAMS || fastmatch_smem_bytes(27, 3, A.nbeams) > 216 * 1024)
+        return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "scan of %d beams exceeds the fused scan step (%d)", A.nbeams, FM_MAX_BEAMS);
+    LatticeTables T = {};
+    // Programmatic dependent launch behind the scan in front: the kernel may become resident early (launch latency,
+    // shared-memory set-up), but it reads the chain's state -- which the kernel in front commits in its tail -- and
+    // everything else only behind its wait for that kernel's completion.
+    return fastmatch_launch_args(ctx, A, T);
+}
+
+namespace {
+__global__ void trig_probe_kernel(const float *__restrict__ in, int n, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = glibc_trig::sincos(in[i], 0);
+    out[n + i] = glibc_trig::sincos(in[i], 1);
+}
+}  // namespace
+
+// The device's restatement of glibc's sinf / cosf against the libm this process runs on, on a sample of the range the
+// chain serves: every 2^-10 step of [-16, 16], the floats next to every multiple of pi/4 (the branch points of the
+// range reduction) and 2^16 hashed values.  (tools/trig_check.cpp does the whole range on the CPU.)
+int chain_trig_selftest(b200slam_ctx *ctx)
+{
+    if (ctx->chain_trig_ok) return ctx->chain_trig_ok > 0 ? B200SLAM_OK
+                                   : b200slam_set_error(ctx, B200SLAM_ERR_STATE, "the device's cosf / sinf differ from this host's libm");
+    const int N1 = 32 * 1024 + 1, N2 = 21 * 16, N3 = 1 << 16, N = N1 + N2 + N3;
+    float *h = (float *)malloc(sizeof(float) * 3 * (size_t)N);
+    if (!h) return B200SLAM_ERR_NOMEM;
+    int n = 0;
+    for (int i = 0; i < N1; ++i) h[n++] = -16.0f + (float)i * (1.0f / 1024.0f);
+    for (int k = -10; k <= 10; ++k) {
+        float v = (float)((double)k * 0.78539816339744830962);
+        for (int j = 0; j < 8; ++j) v = nextafterf(v, -100.0f);
+        for (int j = 0; j < 16; ++j) { h[n++] = v; v = nextafterf(v, 100.0f); }
+    }
+    unsigned long long z = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < N3; ++i) {
+        z ^= z << 13; z ^= z >> 7; z ^= z << 17;
+        h[n++] = (float)((double)(z >> 11) * (1.0 / 9007199254740992.0) * 32.0 - 16.0);
+    }
+    float *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(float) * 3 * (size_t)N);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, sizeof(float) * N, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        trig_probe_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(d, N, d + N);
+        ctx->launches++;
+        e = cudaMemcpyAsync(h + N, d + N, sizeof(float) * 2 * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        free(h);
+        return b200slam_set_error(ctx, B200SLAM_ERR_CUDA, "trig self-test -> %s", cudaGetErrorString(e));
+    }
+    int bad = 0;
+    for (int i = 0; i < N; ++i) {
+        const float s = sinf(h[i]), c = cosf(h[i]);
+        if (memcmp(&s, &h[N + i], 4) || memcmp(&c, &h[2 * N + i], 4)) bad++;
+    }
+    free(h);
+    ctx->chain_trig_ok = bad ? -1 : 1;
+    return bad ? b200slam_set_error(ctx, B200SLAM_ERR_STATE, "the device's cosf / sinf differ from this host's libm (%d of %d samples)", bad, N)
+               : B200SLAM_OK;
 }
 
 int exchange_collect_launch(b200slam_ctx *ctx)

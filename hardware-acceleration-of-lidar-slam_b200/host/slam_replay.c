@@ -12,10 +12,13 @@
  *   - the dataset is read once, uploaded as raw text and parsed ON THE GPU (b200slam_csv_ingest: the
  *     reference's fscanf("%f,") loop, main.c:22-30, bit for bit); readAScan then reads its ranges from
  *     the resident values;
- *   - per scan the host queues ONE kernel -- readAScan, FastMatch and FastMatch2 in one CTA (no host step
- *     between them: scan.size stays on the device, and the second match picks its lattice by the first
- *     one's winner) -- and synchronises ONCE to fetch the two poses it needs for the motion model, the
- *     mini-update test (main.c:875-898, 928-940) and the next lattice's cosf / sinf;
+ *   - a scan is ONE kernel -- readAScan, FastMatch and FastMatch2 fused (no host step between them: scan.size
+ *     stays on the device, and the second match centres its lattice on the first one's winner);
+ *   - between map updates the loop itself runs ON THE DEVICE (b200slam_scan_chain_*): the motion model
+ *     (main.c:875-898), both lattices' tables -- cosf / sinf as glibc computes them -- and the mini-update test
+ *     (main.c:928-940) are evaluated by the kernels, which the host queues up to CHAIN_DEPTH scans ahead of the
+ *     results it reads from a ring of mapped memory (only to print the poses and to see a mini update coming);
+ *     B200SLAM_REPLAY_NO_CHAIN=1 keeps r02's host-driven loop: one kernel and one synchronisation per scan;
  *   - map growth (main.c:942-948) is queued without reading its count back; only a map rebuild (2 % of
  *     the scans) reads sizes, because the grid geometry is computed with the reference's host float
  *     operations (main.c:272-305).
@@ -34,6 +37,7 @@
 #include "b200slam.h"
 
 #define COLUMN 1079                                /* main.c:7 */
+#define CHAIN_DEPTH 16                             /* scans queued ahead of the one being fetched (ring: 64) */
 
 static b200slam_ctx *ctx;
 
@@ -143,6 +147,8 @@ int main(int argc, char **argv)
     for (int i = 0; i < 3; i++) { map_pose[i] = pose[i]; path[0][i] = pose[i]; }
 
     int miniUpdated = 1, path_iter = 1, rebuilds = 0;
+    int use_chain = !host_parse && getenv("B200SLAM_REPLAY_NO_CHAIN") == NULL;
+    int chain_active = 0, chain_queued = 0, chained_scans = 0, chains = 0;
     double t_read = 0, t_rebuild = 0, t_queue = 0, t_fetch = 0, t_grow = 0;      /* where the host's time goes */
     const double t_loop = now_s();
     for (int scan_iter = 1; scan_iter < row; scan_iter++) {
@@ -188,7 +194,38 @@ int main(int argc, char **argv)
         }
         /* main.c:901-922: FastMatch (coarse grid after a rebuild, else the fine one) then FastMatch2 from its
          * result -- two kernels back to back, one synchronisation */
-        if (miniUpdated)
+        int chained = 0;
+        if (!miniUpdated && use_chain) {
+            /* the device carries the poses from here on: (re)start the chain at this scan, keep it CHAIN_DEPTH ahead.
+             * The device's cosf / sinf are glibc's for |theta| <= 16: stay well inside */
+            if (chain_active && chain_queued <= scan_iter && fabsf(pose[2]) >= 13.0f) chain_active = 0;   /* host-driven from here */
+            if (!chain_active && fabsf(pose[2]) < 13.0f) {
+                const int rc = b200slam_scan_chain_begin(ctx, scan_iter, pose, scan_iter > 1 ? path[path_iter - 2] : NULL, map_pose,
+                                                         miniUpdateDT, miniUpdateDR);
+                if (rc) {
+                    fprintf(stderr, "b200slam_replay: device-side loop unavailable (%s); host-driven loop\n", b200slam_last_error(ctx));
+                    use_chain = 0;
+                } else {
+                    chain_active = 1;
+                    chain_queued = scan_iter;
+                    chains++;
+                }
+            }
+            if (chain_active) {
+                while (chain_queued < row && chain_queued < scan_iter + CHAIN_DEPTH &&
+                       (int64_t)(chain_queued + 1) * COLUMN <= nvalues &&
+                       (chain_queued == scan_iter || fabsf(pose[2]) + 0.1f * (float)(chain_queued - scan_iter) < 15.0f)) {
+                    must(b200slam_scan_chain_step_async(ctx, chain_queued, (int64_t)chain_queued * COLUMN, 24, fine, fine, fastResolution,
+                                                        fastResolution2), "scan chain step");
+                    chain_queued++;
+                }
+                chained = 1;
+                chained_scans++;
+            }
+        }
+        if (chained)
+            ;
+        else if (miniUpdated)
             must(b200slam_fastmatch_pair_async(ctx, coarse, fine, pose_guess, fastResolution, fastResolution2), "fastmatch pair");
         else if (host_parse)
             must(b200slam_scan_step_async(ctx, ranges, 24, fine, fine, pose_guess, fastResolution, fastResolution2), "scan step");
@@ -196,12 +233,22 @@ int main(int argc, char **argv)
             must(b200slam_scan_step_resident_async(ctx, (int64_t)scan_iter * COLUMN, 24, fine, fine, pose_guess, fastResolution,
                                                    fastResolution2), "scan step");
         t_queue += now_s() - t0; t0 = now_s();
-        must(b200slam_fastmatch_pair_fetch(ctx, NULL, pose, &size, NULL), "fastmatch pair fetch");
+        int stopped = 0;
+        if (chained) must(b200slam_scan_chain_fetch(ctx, scan_iter, NULL, pose, &size, NULL, &stopped), "scan chain fetch");
+        else must(b200slam_fastmatch_pair_fetch(ctx, NULL, pose, &size, NULL), "fastmatch pair fetch");
         t_fetch += now_s() - t0; t0 = now_s();
         /* mini update, main.c:928-961 */
         float dp[3];
         for (int i = 0; i < 3; i++) dp[i] = fabsf(pose[i] - map_pose[i]);
-        if (dp[0] > miniUpdateDT || dp[1] > miniUpdateDT || dp[2] > miniUpdateDR) {
+        const int update = dp[0] > miniUpdateDT || dp[1] > miniUpdateDT || dp[2] > miniUpdateDR;
+        if (chained) {
+            if (update != stopped) {               /* the device evaluated the same float compares */
+                fprintf(stderr, "b200slam_replay: scan %d: device mini-update test %d, host %d\n", scan_iter, stopped, update);
+                return 1;
+            }
+            if (stopped) chain_active = 0;         /* nothing queued behind this scan ran; the scan on the device is this one's */
+        }
+        if (update) {
             miniUpdated = 1;
             if (!scan_transform_flag) must(b200slam_scan_transform(ctx, pose), "scan_transform");
             must(b200slam_mappoints_grow_async(ctx, 1.5f), "mappoints_grow");
@@ -232,6 +279,7 @@ int main(int argc, char **argv)
                     "loop %.3f s wall -> %.1f us per scan on the device path\n", row, n, rebuilds,
             (unsigned long long)b200slam_launch_count(ctx), host_parse ? "parsed by fscanf" : "read + parsed on the GPU",
             t_parse, loop_s, row > 1 ? 1e6 * dev_s / (row - 1) : 0.0);
+    fprintf(stderr, "b200slam_replay: %d of the scans ran in %d device-side chains (up to %d queued ahead)\n", chained_scans, chains, CHAIN_DEPTH);
     fprintf(stderr, "b200slam_replay: host time per scan: queue readAScan %.1f us, map rebuilds %.1f us (%d of them), queue the match pair "
                     "%.1f us, wait for its result %.1f us, mini update / growth %.1f us\n", 1e6 * t_read / (row - 1),
             1e6 * t_rebuild / (row - 1), rebuilds, 1e6 * t_queue / (row - 1), 1e6 * t_fetch / (row - 1), 1e6 * t_grow / (row - 1));

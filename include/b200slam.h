@@ -292,6 +292,33 @@ int b200slam_scan_step_async(b200slam_ctx *ctx, const float *ranges, int max_ran
 int b200slam_scan_step_resident_async(b200slam_ctx *ctx, int64_t first_value, int max_range, b200slam_map *map_a,
                                       b200slam_map *map_b, const float pose[3], const float res_a[3], const float res_b[3]);
 
+/* The per-scan loop ON THE DEVICE (main.c:859-970): scans are queued AHEAD of their results.  The poses the loop
+ * carries from one scan to the next -- the current pose, the previous path entry (constant-velocity motion model,
+ * main.c:875-898) and map.pose (mini-update test, main.c:928-940) -- live in device memory; the kernel of scan k
+ * (readAScan + FastMatch + FastMatch2 fused, as b200slam_scan_step_resident_async) forms pose_guess itself, builds
+ * both lattices' axis tables on the device -- cosf / sinf exactly as glibc computes them (csrc/trig.cuh: the libm
+ * algorithm restated in double precision, identical on every float of |theta| <= 16; checked against the running
+ * libm by b200slam_scan_chain_begin on a sample and by tools/trig_check.cpp exhaustively) -- commits the refined
+ * pose in its tail and evaluates the mini-update test.  When the test fires the chain STOPS: the kernels already
+ * queued behind that scan return at once, so the scan, bestHits[] and the match state stay those of the scan that
+ * needs the map update, and the host does Transform / map growth / the rebuild as before, then begins a new chain.
+ *   b200slam_scan_chain_begin       sets the device state; scan_index = the first scan the chain will run;
+ *                                   prev_pose NULL: no motion model for that scan (scan_iter == 1, main.c:895-897).
+ *                                   B200SLAM_ERR_STATE when the device's cosf / sinf differ from this host's libm
+ *                                   (the caller then stays with b200slam_scan_step_resident_async)
+ *   b200slam_scan_chain_step_async  queues scan scan_index (its ranges: values [first_value, +lidar_n) of
+ *                                   b200slam_csv_ingest); any number may be queued ahead, in order; the caller
+ *                                   keeps |theta| <= 15 (beyond that use the host-driven calls)
+ *   b200slam_scan_chain_fetch       waits for scan scan_index's result in a ring of mapped host memory (64 scans
+ *                                   deep): FastMatch's and FastMatch2's poses, scan.size, bestHits_size, and
+ *                                   whether the mini-update test fired (*stopped: nothing behind this scan ran). */
+int b200slam_scan_chain_begin(b200slam_ctx *ctx, int scan_index, const float pose[3], const float *prev_pose,
+                              const float map_pose[3], float mini_update_dt, float mini_update_dr);
+int b200slam_scan_chain_step_async(b200slam_ctx *ctx, int scan_index, int64_t first_value, int max_range, b200slam_map *map_a,
+                                   b200slam_map *map_b, const float res_a[3], const float res_b[3]);
+int b200slam_scan_chain_fetch(b200slam_ctx *ctx, int scan_index, float pose_a[3], float pose_b[3], int *scan_size,
+                              int *best_hits_size, int *stopped);
+
 /* ---- scan ingest -----------------------------------------------------------
  * Replaces readDatasetLineByLine (Subsystem_1/main.c:22-30): `column` x fscanf(fp, "%f,", &value).  The whole
  * CSV text (values separated by ',' and / or white space) is parsed ON THE GPU: one upload of the raw bytes,

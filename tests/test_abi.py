@@ -87,7 +87,7 @@ def test_scoring_kernels_contain_no_fused_multiply_add(b200slam):
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     sass = subprocess.run([cuobjdump, "-sass", b200slam.LIB_PATH], capture_output=True, text=True, check=True).stdout
     # (raster_scatter_kernel is not on the list: its IEEE division, __fdiv_rn, is itself built from FFMAs)
-    watched = ("lattice_kernel", "poses_kernel", "scan_read_kernel", "scan_transform_kernel", "local_map_kernel")
+    watched = ("lattice_kernel", "poses_kernel", "fastmatch_kernel", "scan_read_kernel", "scan_transform_kernel", "local_map_kernel")
     current, seen, bad = None, set(), []
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)

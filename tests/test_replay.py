@@ -76,14 +76,18 @@ def test_dropin_replay_is_byte_identical(reference_run, dataset, b200slam):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("host_parse", [False, True])
-def test_device_resident_replay_is_byte_identical(reference_run, dataset, b200slam, host_parse):
+@pytest.mark.parametrize("mode", ["device_loop", "host_loop", "host_parse"])
+def test_device_resident_replay_is_byte_identical(reference_run, dataset, b200slam, mode):
     """b200slam_replay (host/slam_replay.c): the control flow of the reference's main() in C over the ABI,
     with readAScan / Transform / ExtractLocalMap / OccupationalGrid / both EDTs / FastMatch / FastMatch2 / map
     growth all on the device, the dataset parsed on the GPU (rank 4; host_parse: by the
     host's fscanf instead), one synchronisation per scan (FastMatch and FastMatch2 queued as a pair, sizes kept
     on the device).  Same pose trace, same map dump, byte for byte -- which also pins the inline map-growth code
-    of main() (main.c:942-948) end to end."""
+    of main() (main.c:942-948) end to end.
+    device_loop (the default): between map updates the loop runs on the device -- motion model, lattice tables with
+    the device's restatement of glibc's cosf / sinf, mini-update test -- with scans queued 16 ahead of their results
+    (b200slam_scan_chain_*); host_loop: B200SLAM_REPLAY_NO_CHAIN=1, one kernel and one synchronisation per scan."""
+    host_parse = mode == "host_parse"
     d, csv = dataset
     exe = os.path.join(os.path.dirname(b200slam.LIB_PATH), "b200slam_replay")
     assert os.path.exists(exe), "b200slam_replay missing: run __graft_entry__.build()"
@@ -91,6 +95,8 @@ def test_device_resident_replay_is_byte_identical(reference_run, dataset, b200sl
     env = dict(os.environ)
     if host_parse:
         env["B200SLAM_REPLAY_HOST_PARSE"] = "1"
+    if mode == "host_loop":
+        env["B200SLAM_REPLAY_NO_CHAIN"] = "1"
     p = subprocess.run([exe, csv, mapout, str(NSCANS)], capture_output=True, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     gpu_lines = [ln for ln in p.stdout.splitlines() if not ln.startswith("time taken")]
@@ -99,3 +105,96 @@ def test_device_resident_replay_is_byte_identical(reference_run, dataset, b200sl
     diff = [i for i, (a, b) in enumerate(zip(ref_lines, gpu_lines)) if a != b]
     assert not diff, f"first differing line {diff[0]}: ref={ref_lines[diff[0]]!r} gpu={gpu_lines[diff[0]]!r}"
     assert open(mapout, "rb").read() == ref_map
+    if mode == "device_loop":
+        assert "device-side loop unavailable" not in p.stderr, p.stderr[-1000:]
+        ran = [ln for ln in p.stderr.splitlines() if "device-side chains" in ln]
+        assert ran and int(ran[0].split(":")[1].split()[0]) > NSCANS * 0.9, p.stderr[-1000:]      # ~98 % of the scans
+
+
+def test_device_trig_restatement_equals_libm_on_every_float(tmp_path):
+    """csrc/trig.cuh restates glibc's sinf / cosf (double-precision polynomial after a fixed-point range reduction)
+    so that the device-resident scan loop can build its lattice tables without the host (main.c:434-435 take them
+    from libm).  Host build of the same source against the running libm, EVERY float of |y| <= 16 (the range the
+    device serves), both functions, both signs: bit-identical."""
+    import shutil
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "trig_check")
+    subprocess.run([gxx, "-O2", "-ffp-contract=off", "-mfma", "-pthread", "-o", exe, os.path.join(ROOT, "tools", "trig_check.cpp"), "-lm"],
+                   check=True)
+    p = subprocess.run([exe, "16", str(min(32, os.cpu_count() or 4))], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "mismatches 0 0" in p.stdout, p.stdout[-500:]
+
+
+@pytest.mark.gpu
+def test_scan_chain_matches_the_host_driven_steps(dataset, synth, b200slam):
+    """b200slam_scan_chain_*: scans queued ahead on the device (pose state, motion model, tables, mini-update test
+    in the kernels) against the same scans driven one by one from the host (b200slam_scan_step_resident_async with
+    the host's cosf / sinf): every pose bit-identical, the chain stops exactly where the host's test fires and the
+    scan left on the device is that scan's (the kernels queued behind it did not run)."""
+    nscan = 120
+    d, csv = dataset
+    with open(csv, "rb") as f:
+        txt = b"".join(f.readline() for _ in range(nscan))
+    n = synth.REF_BEAMS
+    a = np.empty(n, np.float32)
+    v = np.float32(-2.351831)
+    for i in range(n):                                   # accumulated in float like main.c:47-57
+        a[i] = v
+        v = np.float32(v + np.float32(0.004363))
+    res_a = np.array([0.05, 0.05, 0.008727], np.float32)
+    res_b = np.array([0.025, 0.025, 0.004363], np.float32)
+    dt, dr = np.float32(0.3), np.float32(0.0872665)
+
+    def run(chain):
+        c = b200slam.Context(0)
+        try:
+            c.lidar_set(a, 0.023)
+            assert len(c.csv_ingest(txt, nscan * n)) == nscan * n
+            fine = c.new_map(400, 400)
+            pose = np.zeros(3, np.float32)
+            c.scan_read_resident_async(0)
+            c.scan_transform(pose)
+            c.mappoints_from_scan()
+            c.local_map_extract(1.0)
+            fine.rasterise_local(0.1)
+            fine.edt(10.0)
+            poses, stops = [pose.copy()], []
+            map_pose = pose.copy()
+            k = 1
+            if chain:
+                c.scan_chain_begin(1, pose, None, map_pose, float(dt), float(dr))
+                for q in range(1, min(nscan, 60)):       # the ring holds 64 results
+                    c.scan_chain_step_async(q, q * n, fine, fine, res_a, res_b)
+                while k < min(nscan, 60):
+                    pa, pb, sz, bh, st = c.scan_chain_fetch(k)
+                    poses.append(pb.copy())
+                    k += 1
+                    if st:
+                        stops.append(k - 1)
+                        break
+            else:
+                while k < min(nscan, 60):
+                    guess = pose.copy() if k == 1 else (pose + (pose - poses[-2]).astype(np.float32)).astype(np.float32)
+                    c.scan_step_resident_async(k * n, fine, fine, guess, res_a, res_b)
+                    pa, pb, sz, bh = c.fastmatch_pair_fetch()
+                    pose = pb.copy()
+                    poses.append(pose.copy())
+                    k += 1
+                    dd = np.abs((pose - map_pose).astype(np.float32))
+                    if dd[0] > dt or dd[1] > dt or dd[2] > dr:
+                        stops.append(k - 1)
+                        break
+            c.sync()
+            sx = c.scan_download(transformed=False)
+            return poses, stops, sx
+        finally:
+            c.close()
+
+    ph, sh, xh = run(False)
+    pc, sc, xc = run(True)
+    assert len(ph) == len(pc) and sh == sc, (len(ph), len(pc), sh, sc)
+    assert len(ph) > 10
+    assert all(np.array_equal(p.view(np.uint32), q.view(np.uint32)) for p, q in zip(ph, pc))
+    assert np.array_equal(np.asarray(xh[0]).view(np.uint32), np.asarray(xc[0]).view(np.uint32))      # the scan left on the device
