@@ -116,7 +116,7 @@ def load_library() -> C.CDLL:
         "b200slam_scan_step_async": (i, [vp, c_float_p, i, vp, vp, c_float_p, c_float_p, c_float_p]),
         "b200slam_scan_step_resident_async": (i, [vp, C.c_int64, i, vp, vp, c_float_p, c_float_p, c_float_p]),
         "b200slam_scan_chain_begin": (i, [vp, i, c_float_p, c_float_p, c_float_p, f, f]),
-        "b200slam_scan_chain_step_async": (i, [vp, i, C.c_int64, i, vp, vp, c_float_p, c_float_p]),
+        "b200slam_scan_chain_step_async": (i, [vp, i, i, C.c_int64, i, vp, vp, c_float_p, c_float_p]),
         "b200slam_scan_chain_fetch": (i, [vp, i, c_float_p, c_float_p, c_int_p, c_int_p, c_int_p]),
         "b200slam_csv_ingest": (i, [vp, vp, C.c_size_t, vp, C.c_int64, c_i64_p]),
         "b200slam_csv_values": (i, [vp, C.POINTER(vp), c_i64_p]),
@@ -447,9 +447,11 @@ class Context:
         self._check(self.L.b200slam_scan_chain_begin(self.h, int(scan_index), _f3(pose), None if prev_pose is None else _f3(prev_pose),
                                                      _f3(map_pose), mini_dt, mini_dr))
 
-    def scan_chain_step_async(self, scan_index: int, first_value: int, map_a: Map, map_b: Map, res_a, res_b, max_range: int = 24):
-        self._check(self.L.b200slam_scan_chain_step_async(self.h, int(scan_index), int(first_value), int(max_range), map_a.h,
-                                                          map_b.h, _f3(res_a), _f3(res_b)))
+    def scan_chain_step_async(self, scan_index: int, first_value: int, map_a: Map, map_b: Map, res_a, res_b, max_range: int = 24,
+                              nscans: int = 1):
+        """Queue scans [scan_index, scan_index + nscans) as one kernel launch."""
+        self._check(self.L.b200slam_scan_chain_step_async(self.h, int(scan_index), int(nscans), int(first_value), int(max_range),
+                                                          map_a.h, map_b.h, _f3(res_a), _f3(res_b)))
         self._nbeams = self._lidar_n
 
     def scan_chain_fetch(self, scan_index: int):

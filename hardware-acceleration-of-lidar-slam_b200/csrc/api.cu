@@ -1044,21 +1044,23 @@ int b200slam_scan_chain_begin(b200slam_ctx *ctx, int scan_index, const float pos
     return B200SLAM_OK;
 }
 
-int b200slam_scan_chain_step_async(b200slam_ctx *ctx, int scan_index, int64_t first_value, int max_range, b200slam_map *map_a,
-                                   b200slam_map *map_b, const float res_a[3], const float res_b[3])
+int b200slam_scan_chain_step_async(b200slam_ctx *ctx, int scan_index, int nscans, int64_t first_value, int max_range,
+                                   b200slam_map *map_a, b200slam_map *map_b, const float res_a[3], const float res_b[3])
 {
-    if (!ctx || scan_index < 0 || first_value < 0 || !map_a || !map_b || !res_a || !res_b) return B200SLAM_ERR_ARG;
+    if (!ctx || scan_index < 0 || nscans < 1 || nscans > CHAIN_RING / 2 || first_value < 0 || !map_a || !map_b || !res_a || !res_b)
+        return B200SLAM_ERR_ARG;
     if (!ctx->d_chain) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_scan_chain_begin first");
     if (ctx->lidar_n <= 0) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "b200slam_lidar_set first");
-    if (!ctx->d_csv_values || first_value + ctx->lidar_n > ctx->csv_count)
+    if (!ctx->d_csv_values || first_value + (int64_t)nscans * ctx->lidar_n > ctx->csv_count)
         return b200slam_set_error(ctx, B200SLAM_ERR_ARG, "values [%lld, %lld) are not in the ingested CSV (%lld values)",
-                                  (long long)first_value, (long long)(first_value + ctx->lidar_n), (long long)ctx->csv_count);
+                                  (long long)first_value, (long long)(first_value + (int64_t)nscans * ctx->lidar_n), (long long)ctx->csv_count);
     if (!map_a->has_geometry || !map_b->has_geometry) return b200slam_set_error(ctx, B200SLAM_ERR_STATE, "map geometry not set");
     int rc = ensure_scan_capacity(ctx, ctx->lidar_n);
     if (!rc) rc = ensure_front(ctx);
     if (rc) return rc;
     ChainLaunch C;
     C.scan_index = scan_index;
+    C.count = nscans;
     C.step_a[0] = C.step_a[1] = res_a[0]; C.step_a[2] = res_a[2];         // main.c:386-387
     C.step_b[0] = C.step_b[1] = res_b[0]; C.step_b[2] = res_b[2];
     rc = scan_chain_launch(ctx, map_a, map_b, C, ctx->d_csv_values + first_value, max_range);

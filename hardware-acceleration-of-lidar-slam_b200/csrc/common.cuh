@@ -343,7 +343,7 @@ struct LatticeLaunch {
 constexpr size_t LATTICE_PARAM_FLOATS = 960;
 int lattice_launch(b200slam_ctx *ctx, const LatticeLaunch &L);
 int exchange_collect_launch(b200slam_ctx *ctx);
-struct ChainLaunch { int scan_index; float step_a[3], step_b[3]; };
+struct ChainLaunch { int scan_index, count; float step_a[3], step_b[3]; };
 int scan_chain_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_map *mb, const ChainLaunch &C,
                       const float *d_ranges, int max_range);
 int chain_trig_selftest(b200slam_ctx *ctx);

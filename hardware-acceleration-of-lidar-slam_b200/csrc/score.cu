@@ -910,6 +910,7 @@ struct FmArgs {
     ChainDev *chain;
     ChainSlot *chain_ring;
     int scan_index;
+    int chain_count;          // scans this launch runs one after the other (their ranges lidar_n floats apart), while the chain lasts
     float step_a[3], step_b[3];
     float mini_dt, mini_dr;
     MatchDev *match;
@@ -1090,11 +1091,18 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
     // Everything this kernel reads (scan, beam count, match state) and writes (bestHits[] twin, match state) may
     // belong to the kernel in front until it has completed; being resident already saves the launch latency.
     pdl_wait_prior_grids();
+    // Chain mode: one launch runs chain_count consecutive scans (a cluster barrier between them carries the committed
+    // pose from the first CTA to the others); everything else runs the body once.
+    for (int it = 0;; ++it) {
+    const int scan_index = A.scan_index + it;
     [[maybe_unused]] float guess[3] = {0.0f, 0.0f, 0.0f};
+    [[maybe_unused]] ChainSlot out = {};              // chain mode, first CTA's thread 0: this scan's result for the host
     if (A.chain) {
-        // the chain's state only changes in the tail of a kernel that has completed: the same answer in every CTA
+        // the chain's state only changes in a tail, behind a kernel boundary or the cluster barrier at the end of the
+        // loop: the same answer in every CTA
         const volatile ChainDev *cs = A.chain;
-        if (cs->stop != 0 || cs->next_scan != A.scan_index) return;
+        if (cs->stop != 0 || cs->next_scan != scan_index) return;
+        if (it > 0 && tid < FM_MAX_CHUNKS / FM_GROUP) group_done[tid] = 0;       // (a __syncthreads follows before its first use)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             // constant-velocity motion model, main.c:875-898: pose_guess = pose + DiffPose(previous_pose, pose)
@@ -1103,6 +1111,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
         }
     }
     int nbeams = A.nbeams_dev ? *A.nbeams_dev : A.nbeams;
+    const float *ranges = A.ranges ? A.ranges + (size_t)it * A.lidar_n : nullptr;
     if (A.ranges) {
         // ---- readAScan (main.c:71-95): drop r < range_min | r > max_range, x = r cos, y = r sin, compacted in
         // beam order (the same arithmetic as scan_read_kernel, frontend.cu); every CTA for itself, the first one
@@ -1114,7 +1123,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             float r = 0.0f;
             bool keep = false;
             if (i < A.lidar_n) {
-                r = A.ranges[i];
+                r = ranges[i];
                 keep = !((r < A.range_min) | (r > maxr));                             // main.c:78
             }
             const unsigned int m = __ballot_sync(0xffffffffu, keep);
@@ -1179,12 +1188,18 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
                     c[2] = lv(guess[2], A.step_a[2], lin1 / 9);
                 }
                 const float *stp = pass == 0 ? A.step_a : A.step_b;
-                if (tid < 3) {
-                    const float th = lv(c[2], stp[2], tid);
-                    tab_s[tid] = glibc_trig::sincos(th, 1);                                          // main.c:434
-                    tab_s[FM_MAX_CAND + tid] = glibc_trig::sincos(th, 0);                            // main.c:435
-                    tab_s[2 * FM_MAX_CAND + tid] = __fmul_rn(__fsub_rn(lv(c[0], stp[0], tid), M.tlx), M.ipixel);   // main.c:436
-                    tab_s[3 * FM_MAX_CAND + tid] = __fmul_rn(__fsub_rn(lv(c[1], stp[1], tid), M.tly), M.ipixel);   // main.c:437
+                // 12 table entries, 12 threads (a cosf / sinf is ~150 dependent double-precision operations: the six of
+                // them side by side, on the critical path of every pass)
+                if (tid < 12) {
+                    const int k = tid % 3, what = tid / 3;
+                    if (what < 2) {
+                        const float th = lv(c[2], stp[2], k);
+                        tab_s[what * FM_MAX_CAND + k] = glibc_trig::sincos(th, what == 0 ? 1 : 0);   // main.c:434-435
+                    } else if (what == 2) {
+                        tab_s[2 * FM_MAX_CAND + k] = __fmul_rn(__fsub_rn(lv(c[0], stp[0], k), M.tlx), M.ipixel);   // main.c:436
+                    } else {
+                        tab_s[3 * FM_MAX_CAND + k] = __fmul_rn(__fsub_rn(lv(c[1], stp[1], k), M.tly), M.ipixel);   // main.c:437
+                    }
                 }
             } else {
                 if (tid < A.nth) { tab_s[tid] = ctT[tid]; tab_s[FM_MAX_CAND + tid] = stT[tid]; }
@@ -1315,7 +1330,6 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
             ChainDev *cs = A.chain;
             const int l1 = (int)(seed & 0xffffffffull), l2 = (int)(key & 0xffffffffull);
             const int ia[3] = {(l1 / 3) % 3, l1 % 3, l1 / 9}, ib[3] = {(l2 / 3) % 3, l2 % 3, l2 / 9};
-            volatile ChainSlot *slot = A.chain_ring + (A.scan_index % CHAIN_RING);
             bool update = false;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -1325,18 +1339,30 @@ __global__ void __launch_bounds__(FM_THREADS, 1) fastmatch_kernel(const __grid_c
                 update = update || dp > (i < 2 ? A.mini_dt : A.mini_dr);
                 cs->prev[i] = cs->pose[i];
                 cs->pose[i] = pb;
-                slot->pose_a[i] = pa; slot->pose_b[i] = pb;
+                out.pose_a[i] = pa; out.pose_b[i] = pb;
             }
             cs->have_prev = 1;
-            cs->next_scan = A.scan_index + 1;
+            cs->next_scan = scan_index + 1;
             if (update) cs->stop = 1;
-            slot->scan_n = nbeams; slot->best_hits = bh;
-            slot->mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
-            slot->stopped = update ? 1 : 0;
-            slot->error = *reinterpret_cast<volatile unsigned int *>(&A.match->error);
-            __threadfence_system();
-            slot->seq = (unsigned long long)A.scan_index + 1ull;
+            out.scan_n = nbeams; out.best_hits = bh;
+            out.mp_n = A.mp_n_dev ? *A.mp_n_dev : 0;
+            out.stopped = update ? 1 : 0;
+            out.error = *reinterpret_cast<volatile unsigned int *>(&A.match->error);
         }
+    }
+    const bool more = A.chain && it + 1 < A.chain_count;
+    if (more) fm_cluster_sync();                      // the commit above is visible to every CTA; shared memory is free again
+    if (A.chain && lead && tid == 0) {
+        // the host's copy travels off the critical path: the other warps are already reading the next scan
+        volatile ChainSlot *slot = A.chain_ring + (scan_index % CHAIN_RING);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { slot->pose_a[i] = out.pose_a[i]; slot->pose_b[i] = out.pose_b[i]; }
+        slot->scan_n = out.scan_n; slot->best_hits = out.best_hits; slot->mp_n = out.mp_n; slot->stopped = out.stopped;
+        slot->error = out.error;
+        __threadfence_system();
+        slot->seq = (unsigned long long)scan_index + 1ull;
+    }
+    if (!more) break;
     }
 #undef FM_TRACE
 }
@@ -1635,7 +1661,7 @@ int scan_chain_launch(b200slam_ctx *ctx, const b200slam_map *ma, const b200slam_
     A.lidar_n = ctx->lidar_n; A.max_range = max_range; A.range_min = ctx->lidar_range_min;
     A.scan_x_out = ctx->d_scan_x; A.scan_y_out = ctx->d_scan_y;
     A.front = ctx->d_front;
-    A.chain = ctx->d_chain; A.chain_ring = ctx->h_chain_ring; A.scan_index = C.scan_index;
+    A.chain = ctx->d_chain; A.chain_ring = ctx->h_chain_ring; A.scan_index = C.scan_index; A.chain_count = C.count;
     for (int i = 0; i < 3; ++i) { A.step_a[i] = C.step_a[i]; A.step_b[i] = C.step_b[i]; }
     A.mini_dt = ctx->chain_mini_dt; A.mini_dr = ctx->chain_mini_dr;
     if (A.nbeams > FM_MAX_BEAMS || fastmatch_smem_bytes(27, 3, A.nbeams) > 216 * 1024)

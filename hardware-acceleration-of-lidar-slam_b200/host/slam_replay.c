@@ -37,7 +37,8 @@
 #include "b200slam.h"
 
 #define COLUMN 1079                                /* main.c:7 */
-#define CHAIN_DEPTH 16                             /* scans queued ahead of the one being fetched (ring: 64) */
+#define CHAIN_DEPTH 24                             /* scans queued ahead of the one being fetched (ring: 64) */
+#define CHAIN_BATCH 8                              /* scans per kernel launch */
 
 static b200slam_ctx *ctx;
 
@@ -212,13 +213,17 @@ int main(int argc, char **argv)
                 }
             }
             if (chain_active) {
-                while (chain_queued < row && chain_queued < scan_iter + CHAIN_DEPTH &&
-                       (int64_t)(chain_queued + 1) * COLUMN <= nvalues &&
-                       (chain_queued == scan_iter || fabsf(pose[2]) + 0.1f * (float)(chain_queued - scan_iter) < 15.0f)) {
-                    must(b200slam_scan_chain_step_async(ctx, chain_queued, (int64_t)chain_queued * COLUMN, 24, fine, fine, fastResolution,
-                                                        fastResolution2), "scan chain step");
-                    chain_queued++;
+                while (chain_queued < row && chain_queued + CHAIN_BATCH <= scan_iter + CHAIN_DEPTH + (chain_queued == scan_iter ? CHAIN_BATCH : 0)) {
+                    int nb = CHAIN_BATCH;                                 /* one launch = up to CHAIN_BATCH consecutive scans */
+                    if (chain_queued + nb > row) nb = row - chain_queued;
+                    while (nb > 0 && (int64_t)(chain_queued + nb) * COLUMN > nvalues) nb--;
+                    while (nb > 1 && fabsf(pose[2]) + 0.1f * (float)(chain_queued + nb - scan_iter) >= 15.0f) nb--;
+                    if (nb <= 0) break;
+                    must(b200slam_scan_chain_step_async(ctx, chain_queued, nb, (int64_t)chain_queued * COLUMN, 24, fine, fine,
+                                                        fastResolution, fastResolution2), "scan chain step");
+                    chain_queued += nb;
                 }
+                if (chain_queued <= scan_iter) { fprintf(stderr, "b200slam_replay: dataset ends at scan %d\n", scan_iter); return 1; }
                 chained = 1;
                 chained_scans++;
             }
@@ -279,7 +284,8 @@ int main(int argc, char **argv)
                     "loop %.3f s wall -> %.1f us per scan on the device path\n", row, n, rebuilds,
             (unsigned long long)b200slam_launch_count(ctx), host_parse ? "parsed by fscanf" : "read + parsed on the GPU",
             t_parse, loop_s, row > 1 ? 1e6 * dev_s / (row - 1) : 0.0);
-    fprintf(stderr, "b200slam_replay: %d of the scans ran in %d device-side chains (up to %d queued ahead)\n", chained_scans, chains, CHAIN_DEPTH);
+    fprintf(stderr, "b200slam_replay: %d of the scans ran in %d device-side chains (%d scans per launch, up to %d queued ahead)\n", chained_scans, chains,
+            CHAIN_BATCH, CHAIN_DEPTH);
     fprintf(stderr, "b200slam_replay: host time per scan: queue readAScan %.1f us, map rebuilds %.1f us (%d of them), queue the match pair "
                     "%.1f us, wait for its result %.1f us, mini update / growth %.1f us\n", 1e6 * t_read / (row - 1),
             1e6 * t_rebuild / (row - 1), rebuilds, 1e6 * t_queue / (row - 1), 1e6 * t_fetch / (row - 1), 1e6 * t_grow / (row - 1));

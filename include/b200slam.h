@@ -306,16 +306,18 @@ int b200slam_scan_step_resident_async(b200slam_ctx *ctx, int64_t first_value, in
  *                                   prev_pose NULL: no motion model for that scan (scan_iter == 1, main.c:895-897).
  *                                   B200SLAM_ERR_STATE when the device's cosf / sinf differ from this host's libm
  *                                   (the caller then stays with b200slam_scan_step_resident_async)
- *   b200slam_scan_chain_step_async  queues scan scan_index (its ranges: values [first_value, +lidar_n) of
- *                                   b200slam_csv_ingest); any number may be queued ahead, in order; the caller
- *                                   keeps |theta| <= 15 (beyond that use the host-driven calls)
+ *   b200slam_scan_chain_step_async  queues scans [scan_index, scan_index + nscans) as ONE kernel launch that runs
+ *                                   them one after the other while the chain lasts (their ranges: nscans x lidar_n
+ *                                   consecutive values of b200slam_csv_ingest from first_value; nscans <= 32);
+ *                                   launches may be queued ahead, in order, up to 64 scans in front of the last
+ *                                   fetched one; the caller keeps |theta| <= 15 (beyond that: the host-driven calls)
  *   b200slam_scan_chain_fetch       waits for scan scan_index's result in a ring of mapped host memory (64 scans
  *                                   deep): FastMatch's and FastMatch2's poses, scan.size, bestHits_size, and
  *                                   whether the mini-update test fired (*stopped: nothing behind this scan ran). */
 int b200slam_scan_chain_begin(b200slam_ctx *ctx, int scan_index, const float pose[3], const float *prev_pose,
                               const float map_pose[3], float mini_update_dt, float mini_update_dr);
-int b200slam_scan_chain_step_async(b200slam_ctx *ctx, int scan_index, int64_t first_value, int max_range, b200slam_map *map_a,
-                                   b200slam_map *map_b, const float res_a[3], const float res_b[3]);
+int b200slam_scan_chain_step_async(b200slam_ctx *ctx, int scan_index, int nscans, int64_t first_value, int max_range,
+                                   b200slam_map *map_a, b200slam_map *map_b, const float res_a[3], const float res_b[3]);
 int b200slam_scan_chain_fetch(b200slam_ctx *ctx, int scan_index, float pose_a[3], float pose_b[3], int *scan_size,
                               int *best_hits_size, int *stopped);
 

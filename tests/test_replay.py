@@ -165,8 +165,11 @@ def test_scan_chain_matches_the_host_driven_steps(dataset, synth, b200slam):
             k = 1
             if chain:
                 c.scan_chain_begin(1, pose, None, map_pose, float(dt), float(dr))
-                for q in range(1, min(nscan, 60)):       # the ring holds 64 results
-                    c.scan_chain_step_async(q, q * n, fine, fine, res_a, res_b)
+                q = 1
+                while q < min(nscan, 60):                # the ring holds 64 results; launches of 1, 2, 3, ... scans
+                    nb = min(1 + (q % 7), min(nscan, 60) - q)
+                    c.scan_chain_step_async(q, q * n, fine, fine, res_a, res_b, nscans=nb)
+                    q += nb
                 while k < min(nscan, 60):
                     pa, pb, sz, bh, st = c.scan_chain_fetch(k)
                     poses.append(pb.copy())
