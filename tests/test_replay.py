@@ -147,7 +147,7 @@ def test_scan_chain_matches_the_host_driven_steps(dataset, synth, b200slam):
     res_b = np.array([0.025, 0.025, 0.004363], np.float32)
     dt, dr = np.float32(0.3), np.float32(0.0872665)
 
-    def run(chain):
+    def run(chain, dt=dt, dr=dr, upto=60, window=None):
         c = b200slam.Context(0)
         try:
             c.lidar_set(a, 0.023)
@@ -163,14 +163,17 @@ def test_scan_chain_matches_the_host_driven_steps(dataset, synth, b200slam):
             poses, stops = [pose.copy()], []
             map_pose = pose.copy()
             k = 1
+            last = min(nscan, upto)
             if chain:
                 c.scan_chain_begin(1, pose, None, map_pose, float(dt), float(dr))
                 q = 1
-                while q < min(nscan, 60):                # the ring holds 64 results; launches of 1, 2, 3, ... scans
-                    nb = min(1 + (q % 7), min(nscan, 60) - q)
-                    c.scan_chain_step_async(q, q * n, fine, fine, res_a, res_b, nscans=nb)
-                    q += nb
-                while k < min(nscan, 60):
+                while k < last:
+                    # launches of 1, 2, 3, ... scans, queued up to `window` scans ahead of the result being read
+                    # (the ring of results holds 64: with a window the slots are reused)
+                    while q < last and (window is None or q < k + window):
+                        nb = min(1 + (q % 7), last - q)
+                        c.scan_chain_step_async(q, q * n, fine, fine, res_a, res_b, nscans=nb)
+                        q += nb
                     pa, pb, sz, bh, st = c.scan_chain_fetch(k)
                     poses.append(pb.copy())
                     k += 1
@@ -178,7 +181,7 @@ def test_scan_chain_matches_the_host_driven_steps(dataset, synth, b200slam):
                         stops.append(k - 1)
                         break
             else:
-                while k < min(nscan, 60):
+                while k < last:
                     guess = pose.copy() if k == 1 else (pose + (pose - poses[-2]).astype(np.float32)).astype(np.float32)
                     c.scan_step_resident_async(k * n, fine, fine, guess, res_a, res_b)
                     pa, pb, sz, bh = c.fastmatch_pair_fetch()
@@ -195,6 +198,12 @@ def test_scan_chain_matches_the_host_driven_steps(dataset, synth, b200slam):
         finally:
             c.close()
 
+    # thresholds nothing reaches: one chain over all 119 scans, results through a ring slot twice, 24 scans ahead at most
+    big = np.float32(1e6)
+    ph2, sh2, _ = run(False, big, big, upto=nscan)
+    pc2, sc2, _ = run(True, big, big, upto=nscan, window=24)
+    assert len(ph2) == nscan and len(pc2) == nscan and sh2 == sc2 == []
+    assert all(np.array_equal(p.view(np.uint32), q.view(np.uint32)) for p, q in zip(ph2, pc2))
     ph, sh, xh = run(False)
     pc, sc, xc = run(True)
     assert len(ph) == len(pc) and sh == sc, (len(ph), len(pc), sh, sc)
