@@ -738,19 +738,38 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
     expected_pts = job.bcast(expected_pts)
     barrier()
 
+    # DEPTH steps in flight, one context each (the contexts take turns): step i is issued once step i - DEPTH has been
+    # read back, so the steps in flight need DEPTH different maps (a map object more, fed the first map's points,
+    # when the ring is shorter).
+    DEPTH = max(2, int(os.environ.get("B200SLAM_BENCH_E2E_DEPTH", "3")))
+    pipe = list(pair)
+    while len(pipe) < DEPTH:
+        c_new = mod.Context(local_rank)
+        job.comm_init(c_new)
+        pipe.append(c_new)
+    emaps, esrc = list(maps), list(range(ring))
+    while len(emaps) < DEPTH:
+        m_new = ctx.new_map(rows, cols)
+        m_new.set_geometry(w["pixel"], w["top_left"])
+        emaps.append(m_new); esrc.append(0)
+    ER = len(emaps)
+
     def issue_pts(i, c):
-        m = maps[i % ring]
-        m.rasterise_async(ptx[i % ring], pty[i % ring], float(w["pixel"]), ctx=c)      # H2D points (pinned) + rasterise
+        m = emaps[i % ER]
+        m.rasterise_async(ptx[esrc[i % ER]], pty[esrc[i % ER]], float(w["pixel"]), ctx=c)   # H2D points (pinned) + rasterise
         c._check(c.L.b200slam_map_edt(c.h, m.h, 10.0))
         c.scan_upload(scan_x, scan_y)                                                  # H2D scan (pinned)
         c.score_lattice_async(m, w["pose0"], w["step"], n_global, row_b, row_e, 1 if allreduce else 0)
 
     def run_e2e_pts(n):
-        issue_pts(0, pair[0])
-        for i in range(1, n):
-            issue_pts(i, pair[i & 1])
-            pair[(i - 1) & 1].match_fetch()                    # D2H result of step i-1
-        return pair[(n - 1) & 1].match_fetch()
+        res_ = None
+        for i in range(n):
+            if i >= DEPTH:
+                res_ = pipe[i % DEPTH].match_fetch()           # D2H result of step i - DEPTH: its context and map are free again
+            issue_pts(i, pipe[i % DEPTH])
+        for i in range(max(n - DEPTH, 0), n):
+            res_ = pipe[i % DEPTH].match_fetch()
+        return res_
 
     KP = max(3, min(K, 50))
     run_e2e_pts(4)
@@ -772,7 +791,7 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
     # ---- verification: every launch sequence, on every rank, against rank 0's stand-alone winners ----------
     want = {"serial_graph": expected[last_map], "timed_region": expected[last_map],
             "e2e_one_context": expected[(KE - 1) % ring], "e2e": expected[(KE - 1) % ring],
-            "e2e_points": expected_pts[(KP - 1) % ring], "e2e_points_one_context": expected_pts[(KP - 1) % ring]}
+            "e2e_points": expected_pts[esrc[(KP - 1) % ER]], "e2e_points_one_context": expected_pts[esrc[(KP - 1) % ER]]}
     mism = {k: (v, want[k]) for k, v in checks.items() if tuple(v) != tuple(want[k])}
     if args.no_allreduce and world > 1:
         mism = {}                                              # diagnostic mode: ranks hold shard-local winners
@@ -863,7 +882,7 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
                     "calls": "b200slam_map_rasterise_async -> b200slam_map_edt -> b200slam_scan_upload -> "
                              "b200slam_score_lattice_async -> b200slam_match_fetch  (the reference's OccupationalGrid -> "
                              "euclidean_distance_transform -> FastMatch, main.c:884-918)",
-                    "how": "two contexts alternate: the next step's H2D runs under this step's kernels and result D2H",
+                    "how": f"{DEPTH} contexts take turns: the next steps' H2D and rasterisation run under this step's kernels and result D2H",
                     "one_context_ms_per_step": e2e_pts_serial_s / KP * 1e3},
             "e2e_int32_grid": {"value": total_evals / (e2e_s / KE), "unit": UNIT, "h2d_bytes_per_step": h2d,
                                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / KE * 1e3, "steps": KE,
@@ -892,6 +911,10 @@ def measure_workload(args, synth, workload, job: Job, K, want_cpu, sample_clocks
     for m in maps:
         m.close()
     job.barrier()                         # nobody tears its peer-mapped buffers down while a peer still spins on them
+    for m_x in emaps[ring:]:
+        m_x.close()
+    for c_x in pipe[2:]:
+        c_x.close()
     ctx_b.close()
     ctx.close()
     if not verified and not os.environ.get("B200SLAM_BENCH_NO_COLLECT"):

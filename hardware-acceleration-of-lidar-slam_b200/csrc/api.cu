@@ -252,6 +252,7 @@ int b200slam_map_upload_occupancy(b200slam_ctx *ctx, b200slam_map *map, const in
         int rc = occ_pack_launch(ctx, map);
         if (rc) return rc;
         map->occ8_valid = true;
+        map->occ8_rows = map->rows; map->occ8_cols = map->cols;
     }
     return B200SLAM_OK;
 }
@@ -386,7 +387,8 @@ int b200slam_map_rasterise_async(b200slam_ctx *ctx, b200slam_map *map, const flo
 int b200slam_map_edt(b200slam_ctx *ctx, b200slam_map *map, float max_dist)
 {
     if (!ctx || !map) return B200SLAM_ERR_ARG;
-    if (map->d_occ8 && map->occ8_valid && max_dist > 1.0f && max_dist <= 15.0f)
+    if (map->d_occ8 && map->occ8_valid && map->rows <= map->occ8_rows && map->cols <= map->occ8_cols && max_dist > 1.0f &&
+        max_dist <= 15.0f)
         return edt_launch_bytes(ctx, map->d_occ8, map->occ_pitch, map->d_field, map->field_pitch, map->rows, map->cols, max_dist);
     return edt_launch(ctx, map->d_occ, map->occ_pitch, map->d_field, map->field_pitch, map->rows,
                       map->cols, max_dist);

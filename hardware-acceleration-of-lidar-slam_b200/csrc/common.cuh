@@ -37,6 +37,7 @@ struct b200slam_map {
     // the library's back (occ_exposed) -- the transform then reads the int32 grid.
     uint8_t *d_occ8 = nullptr;
     bool occ8_valid = false;
+    int occ8_rows = 0, occ8_cols = 0;     // region the shadow covers (an upload packs the grid in use; a rasterisation: the capacity)
     int32_t *d_raster_cells = nullptr;
     size_t raster_cells_cap = 0;
     int raster_cells_n = -1;

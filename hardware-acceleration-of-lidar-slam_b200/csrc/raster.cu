@@ -92,5 +92,6 @@ int rasterise_launch(b200slam_ctx *ctx, b200slam_map *map, int npoints, float mi
     LAUNCH_CHECK(ctx);
     map->raster_cells_n = cells ? npoints : -1;
     map->occ8_valid = occ8 != nullptr;
+    map->occ8_rows = map->cap_rows; map->occ8_cols = map->cap_cols;
     return B200SLAM_OK;
 }
