@@ -771,8 +771,8 @@ __global__ void __launch_bounds__(POSES_THREADS) poses_kernel(const __grid_const
                     // The two products are summed with SCALAR adds: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
                     // into FFMA2 (one rounding) whatever --fmad says, which would break bit-exactness.
                     float ax, ay, bx, by;
-                    f2_unpack(f2_mul_rn(f2_pack(q.x, q.x), rot_a), ax, ay);         // x ct | x (-st)
-                    f2_unpack(f2_mul_rn(f2_pack(q.y, q.y), rot_b), bx, by);         // y st | y ct
+                    f2_unpack(f2_mul_rn(rot_a, f2_pack(q.x, q.x)), ax, ay);         // x ct | x (-st)
+                    f2_unpack(f2_mul_rn(rot_b, f2_pack(q.y, q.y)), bx, by);         // y st | y ct
                     const f32x2_t f = f2_add_rn(f2_pack(__fadd_rn(ax, bx), __fadd_rn(ay, by)), shift);
                     // (int)roundf(v) (main.c:483, 501) = truncate(v + 0.5 toward zero) for every v that can pass
                     // the range test; the truncation is a second toward-zero add of 2^23, which leaves the
