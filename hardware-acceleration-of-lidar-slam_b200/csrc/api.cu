@@ -7,7 +7,10 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <time.h>
+#if defined(__SSE__) || defined(__x86_64__)
 #include <xmmintrin.h>
+#define B200SLAM_HAVE_SSE 1
+#endif
 
 #include <new>
 
@@ -284,6 +287,15 @@ int ensure_points_capacity(b200slam_ctx *ctx, size_t npoints)
 // _mm_min_ps(v, acc) is exactly `v < acc ? v : acc`.
 static void points_bbox(const float *x, const float *y, int n, float bbox[4])
 {
+#ifndef B200SLAM_HAVE_SSE
+    bbox[0] = bbox[2] = x[0]; bbox[1] = bbox[3] = y[0];
+    for (int a = 0; a < n; ++a) {
+        if (x[a] < bbox[0]) bbox[0] = x[a];
+        if (x[a] > bbox[2]) bbox[2] = x[a];
+        if (y[a] < bbox[1]) bbox[1] = y[a];
+        if (y[a] > bbox[3]) bbox[3] = y[a];
+    }
+#else
     __m128 lox = _mm_set1_ps(x[0]), hix = lox, loy = _mm_set1_ps(y[0]), hiy = loy;
     int a = 0;
     for (; a + 4 <= n; a += 4) {
@@ -305,6 +317,7 @@ static void points_bbox(const float *x, const float *y, int n, float bbox[4])
         if (y[a] < bbox[1]) bbox[1] = y[a];
         if (y[a] > bbox[3]) bbox[3] = y[a];
     }
+#endif
 }
 
 int rasterise_from_bbox(b200slam_ctx *ctx, b200slam_map *map, int npoints, const float bbox[4], float pixel_size,
