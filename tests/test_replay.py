@@ -210,3 +210,44 @@ def test_scan_chain_matches_the_host_driven_steps(dataset, synth, b200slam):
     assert len(ph) > 10
     assert all(np.array_equal(p.view(np.uint32), q.view(np.uint32)) for p, q in zip(ph, pc))
     assert np.array_equal(np.asarray(xh[0]).view(np.uint32), np.asarray(xc[0]).view(np.uint32))      # the scan left on the device
+
+
+@pytest.mark.gpu
+def test_scan_chain_out_of_order_scan_does_not_run(dataset, synth, b200slam):
+    """A chained scan only runs when it is the one the device state expects: queued with a gap it returns at once, the
+    state stays put, and fetching its result is an error (after the bounded wait), not a hang or a stale slot."""
+    d, csv = dataset
+    n = synth.REF_BEAMS
+    with open(csv, "rb") as f:
+        txt = b"".join(f.readline() for _ in range(12))
+    a = np.empty(n, np.float32)
+    v = np.float32(-2.351831)
+    for i in range(n):
+        a[i] = v
+        v = np.float32(v + np.float32(0.004363))
+    res_a = np.array([0.05, 0.05, 0.008727], np.float32)
+    res_b = np.array([0.025, 0.025, 0.004363], np.float32)
+    c = b200slam.Context(0)
+    try:
+        c.lidar_set(a, 0.023)
+        c.csv_ingest(txt, 12 * n)
+        fine = c.new_map(400, 400)
+        pose = np.zeros(3, np.float32)
+        c.scan_read_resident_async(0)
+        c.scan_transform(pose)
+        c.mappoints_from_scan()
+        c.local_map_extract(1.0)
+        fine.rasterise_local(0.1)
+        fine.edt(10.0)
+        c.scan_chain_begin(3, pose, None, pose, 0.3, 0.0872665)
+        c.scan_chain_step_async(5, 5 * n, fine, fine, res_a, res_b)          # the chain expects scan 3
+        with pytest.raises(b200slam.B200SlamError):
+            c.scan_chain_fetch(5)
+        c.scan_chain_step_async(3, 3 * n, fine, fine, res_a, res_b, nscans=2)
+        _, p3, _, _, st3 = c.scan_chain_fetch(3)
+        _, p4, _, _, st4 = c.scan_chain_fetch(4)
+        assert st3 == 0 and st4 == 0 and np.all(np.isfinite(p3)) and np.all(np.isfinite(p4))
+        with pytest.raises(b200slam.B200SlamError):                          # more scans than the CSV holds
+            c.scan_chain_step_async(5, 5 * n, fine, fine, res_a, res_b, nscans=8)
+    finally:
+        c.close()
